@@ -1,0 +1,83 @@
+// Shared declarations for libssn_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+namespace ssnb {
+
+// NHWC view: a channel slice [coff, coff+C) of a buffer whose pixel pitch is `pitch` elements.
+struct View {
+  void* base = nullptr;
+  int H = 0, W = 0, C = 0, pitch = 0, coff = 0;
+};
+
+extern std::atomic<long long> g_launches;  // every kernel launch of this library bumps it
+void set_thread_error(const std::string& s);
+
+#define SSNB_LAUNCH_CHECK(what)                                                       \
+  do {                                                                                \
+    ssnb::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ssnb::set_thread_error(std::string(what) + ": " + cudaGetErrorString(_e));      \
+      return 2;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// ---- SIMT convolution family (simt_conv.cu) ---------------------------------------------------
+struct ConvArgs {
+  const void* src; int SH, SW, Csrc, src_pitch, src_coff;   // x (fwd) or dz (dgrad)
+  void* dst;       int DH, DW, Cdst, dst_pitch, dst_coff;   // y (fwd) or dx (dgrad)
+  const void* wgt;                                          // [tap][csrc][cdst], storage type
+  const float* bias;                                        // [Cdst] or nullptr
+  int F, k, stride, pad;
+  int relu, accumulate, dgrad;
+};
+struct WgradArgs {
+  const void* dz; int OH, OW, Cout, dz_pitch, dz_coff;
+  const void* x;  int IH, IW, Cin, x_pitch, x_coff;
+  float* partial;                                           // [splits][taps][Cout][Cin]
+  int F, k, stride, pad, rows_per_split, splits;
+};
+template <typename T> int launch_conv(const ConvArgs& a, cudaStream_t s);
+template <typename T> int launch_wgrad(const WgradArgs& a, cudaStream_t s);
+// dW_ref[co][ci][r][s] = mult[co] * sum_splits partial ; mult = bn_scale * 1/loss_scale
+int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
+                          float out_scale, float* dw_ref, cudaStream_t s);
+template <typename T>
+int launch_bias_grad(const void* dz, int rows, int C, int pitch, int coff, const float* mult, float out_scale,
+                     float* partial, int splits, float* db, cudaStream_t s);
+
+// ---- glue (simt_glue.cu) ------------------------------------------------------------------------
+template <typename T> int launch_nchw_to_nhwc(const float* src, int F, int C, int H, int W, View dst, float scale, cudaStream_t s);
+template <typename T> int launch_nhwc_to_nchw(View src, int F, float scale, float* dst, cudaStream_t s);
+template <typename T>
+int launch_maxpool_fwd(View src, View dst, int F, int k, int stride, int pad, uint8_t* argmax, cudaStream_t s);
+template <typename T>
+int launch_maxpool_bwd(View dsrc, View ddst, int F, int k, int stride, int pad, const uint8_t* argmax, int accumulate,
+                       cudaStream_t s);
+template <typename T> int launch_avgpool3_fwd(View src, View dst, int F, int accumulate, cudaStream_t s);
+template <typename T> int launch_gpool_fwd(View src, int F, float* feat, cudaStream_t s);
+template <typename T> int launch_gpool_bwd(const float* dfeat, float scale, View ddst, int F, cudaStream_t s);
+template <typename T> int launch_relu_mask(View dy, View y, int F, cudaStream_t s);
+template <typename T> int launch_fill_zero(View v, int F, cudaStream_t s);
+
+// weight packing (pack.cu): fold BN, produce kernel layouts
+// wf [tap][ci][co], wd [tap][co][ci] in storage type T; bias' [co] fp32; scale [co] fp32
+template <typename T>
+int launch_pack_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* mean,
+                     const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
+                     cudaStream_t s);
+
+}  // namespace ssnb

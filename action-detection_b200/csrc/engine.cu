@@ -1,0 +1,507 @@
+// BNInception execution engine: graph table, workspace planner, forward/backward schedules and the
+// backbone part of the C ABI (include/ssnb.h).  Replaces the reference's YAML-driven op
+// interpreter (model_zoo/bninception/pytorch_load.py:8-61, layer_factory.py:25-83,
+// bn_inception.yaml) and the autograd graph PyTorch builds from it.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ssnb.h"
+#include "common.cuh"
+#include "umma_conv.cuh"
+
+namespace ssnb {
+
+std::atomic<long long> g_launches{0};
+static thread_local std::string t_error;
+void set_thread_error(const std::string& s) { t_error = s; }
+const std::string& thread_error() { return t_error; }
+
+// ---- graph table ---------------------------------------------------------------------------------
+struct BlockSpec { const char* name; int c1, c3r, c3, cdr, cd1, cd2; int pool_max; int cproj; int stride; };
+// bn_inception.yaml:30-551
+static const BlockSpec kBlocks[10] = {
+    {"3a", 64, 64, 64, 64, 96, 96, 0, 32, 1},      {"3b", 64, 64, 96, 64, 96, 96, 0, 64, 1},
+    {"3c", 0, 128, 160, 64, 96, 96, 1, 0, 2},      {"4a", 224, 64, 96, 96, 128, 128, 0, 128, 1},
+    {"4b", 192, 96, 128, 96, 128, 128, 0, 128, 1}, {"4c", 160, 128, 160, 128, 160, 160, 0, 128, 1},
+    {"4d", 96, 128, 192, 160, 192, 192, 0, 128, 1}, {"4e", 0, 128, 192, 192, 256, 256, 1, 0, 2},
+    {"5a", 352, 192, 320, 160, 224, 224, 0, 128, 1}, {"5b", 352, 192, 320, 192, 224, 224, 1, 128, 1}};
+
+struct ConvSpec { std::string id; int cin, cout, k, stride, pad; };
+
+static std::vector<ConvSpec> conv_table(int in_ch) {
+  std::vector<ConvSpec> v;
+  v.push_back({"conv1_7x7_s2", in_ch, 64, 7, 2, 3});
+  v.push_back({"conv2_3x3_reduce", 64, 64, 1, 1, 0});
+  v.push_back({"conv2_3x3", 64, 192, 3, 1, 1});
+  int cx = 192;
+  for (const BlockSpec& b : kBlocks) {
+    std::string p = std::string("inception_") + b.name + "_";
+    if (b.c1) v.push_back({p + "1x1", cx, b.c1, 1, 1, 0});
+    v.push_back({p + "3x3_reduce", cx, b.c3r, 1, 1, 0});
+    v.push_back({p + "3x3", b.c3r, b.c3, 3, b.stride, 1});
+    v.push_back({p + "double_3x3_reduce", cx, b.cdr, 1, 1, 0});
+    v.push_back({p + "double_3x3_1", b.cdr, b.cd1, 3, 1, 1});
+    v.push_back({p + "double_3x3_2", b.cd1, b.cd2, 3, b.stride, 1});
+    if (b.cproj) v.push_back({p + "pool_proj", cx, b.cproj, 1, 1, 0});
+    cx = b.c1 + b.c3 + b.cd2 + (b.cproj ? b.cproj : cx);
+  }
+  return v;
+}
+
+// ---- planned objects -----------------------------------------------------------------------------
+struct Buffer { std::string name; int H, W, C; size_t off = 0, goff = 0; };
+struct Value { std::string name; int buf, coff, C; };
+enum OpKind { OP_CONV = 0, OP_MAXPOOL = 1, OP_AVGPOOL = 2, OP_GPOOL = 3 };
+struct Op {
+  OpKind kind; std::string id; int in_val, out_val;
+  int conv = -1, k = 0, stride = 1, pad = 0;
+  size_t argmax_off = 0;
+  int grad_accumulate = 0;  // backward: dIn += (another consumer wrote first)
+  int wsplits = 1, wrows = 0;
+  UmmaConvPlan umma;        // tcgen05 plan (FAST mode, eligible layers)
+};
+struct PackedConv { size_t wf, wd, bias, scale; };
+
+}  // namespace ssnb
+
+using namespace ssnb;
+
+struct ssnb_engine {
+  ssnb_config cfg;
+  int F = 0;
+  bool fp16 = false;
+  size_t esz = 4;
+  std::vector<ConvSpec> convs;
+  std::vector<Buffer> bufs;
+  std::vector<Value> vals;
+  std::map<std::string, int> val_by_name;
+  std::vector<Op> ops;
+  std::vector<PackedConv> packed;
+  size_t ws_bytes = 0, partial_off = 0, partial_bytes = 0, bpartial_off = 0;
+  char* ws = nullptr;
+  bool weights_ready = false;
+  std::vector<float*> dw, db;
+  std::string error;
+  long long launches0 = 0;
+  UmmaContext umma_ctx;
+
+  int fail(int code, const std::string& msg) { error = msg; return code; }
+  View view(int val, bool grad) const {
+    const Value& v = vals[val];
+    const Buffer& b = bufs[v.buf];
+    View w;
+    w.base = ws + (grad ? b.goff : b.off);
+    w.H = b.H; w.W = b.W; w.C = v.C; w.pitch = b.C; w.coff = v.coff;
+    return w;
+  }
+};
+
+namespace ssnb {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static int pool_out(int h, int k, int s, int p) {   // ceil_mode (layer_factory.py:46-50)
+  int o = (h + 2 * p - k + s - 1) / s + 1;
+  if ((o - 1) * s >= h + p) --o;
+  return o;
+}
+
+static int add_buffer(ssnb_engine* e, const std::string& name, int H, int W, int C) {
+  e->bufs.push_back({name, H, W, C});
+  return (int)e->bufs.size() - 1;
+}
+static int add_value(ssnb_engine* e, const std::string& name, int buf, int coff, int C) {
+  e->vals.push_back({name, buf, coff, C});
+  e->val_by_name[name] = (int)e->vals.size() - 1;
+  return (int)e->vals.size() - 1;
+}
+
+static void build_graph(ssnb_engine* e) {
+  const int cin = e->cfg.in_channels;
+  e->convs = conv_table(cin);
+  int ci = 0;
+  auto conv_op = [&](int in_val, int out_val) {
+    const ConvSpec& c = e->convs[ci];
+    Op o; o.kind = OP_CONV; o.id = c.id; o.in_val = in_val; o.out_val = out_val; o.conv = ci;
+    o.k = c.k; o.stride = c.stride; o.pad = c.pad;
+    e->ops.push_back(o);
+    ++ci;
+  };
+  auto pool_op = [&](OpKind kind, const std::string& id, int in_val, int out_val, int k, int s, int p) {
+    Op o; o.kind = kind; o.id = id; o.in_val = in_val; o.out_val = out_val; o.k = k; o.stride = s; o.pad = p;
+    e->ops.push_back(o);
+  };
+  auto whole = [&](const std::string& name, int H, int W, int C) {
+    return add_value(e, name, add_buffer(e, name, H, W, C), 0, C);
+  };
+  int x = whole("data", 224, 224, cin);
+  int v = whole("conv1_7x7_s2_bn", 112, 112, 64); conv_op(x, v); x = v;
+  v = whole("pool1_3x3_s2", 56, 56, 64); pool_op(OP_MAXPOOL, "pool1_3x3_s2", x, v, 3, 2, 0); x = v;
+  v = whole("conv2_3x3_reduce_bn", 56, 56, 64); conv_op(x, v); x = v;
+  v = whole("conv2_3x3_bn", 56, 56, 192); conv_op(x, v); x = v;
+  v = whole("pool2_3x3_s2", 28, 28, 192); pool_op(OP_MAXPOOL, "pool2_3x3_s2", x, v, 3, 2, 0); x = v;
+  int H = 28, cx = 192;
+  for (const BlockSpec& b : kBlocks) {
+    const std::string p = std::string("inception_") + b.name + "_";
+    const int OHW = (b.stride == 2) ? pool_out(H, 3, 2, 0) : H;
+    const int ctot = b.c1 + b.c3 + b.cd2 + (b.cproj ? b.cproj : cx);
+    const int cat = add_buffer(e, p + "output", OHW, OHW, ctot);
+    const int red = add_buffer(e, p + "reduce", H, H, b.c3r + b.cdr);
+    int off = 0;
+    if (b.c1) { v = add_value(e, p + "1x1_bn", cat, off, b.c1); conv_op(x, v); off += b.c1; }
+    int r3 = add_value(e, p + "3x3_reduce_bn", red, 0, b.c3r); conv_op(x, r3);
+    v = add_value(e, p + "3x3_bn", cat, off, b.c3); conv_op(r3, v); off += b.c3;
+    int rd = add_value(e, p + "double_3x3_reduce_bn", red, b.c3r, b.cdr); conv_op(x, rd);
+    int d1 = whole(p + "double_3x3_1_bn", H, H, b.cd1); conv_op(rd, d1);
+    v = add_value(e, p + "double_3x3_2_bn", cat, off, b.cd2); conv_op(d1, v); off += b.cd2;
+    if (b.stride == 2) {
+      v = add_value(e, p + "pool", cat, off, cx);
+      pool_op(OP_MAXPOOL, p + "pool", x, v, 3, 2, 0);
+    } else {
+      int pl = whole(p + "pool", H, H, cx);
+      pool_op(b.pool_max ? OP_MAXPOOL : OP_AVGPOOL, p + "pool", x, pl, 3, 1, 1);
+      v = add_value(e, p + "pool_proj_bn", cat, off, b.cproj); conv_op(pl, v);
+    }
+    x = add_value(e, p + "output", cat, 0, ctot);
+    H = OHW; cx = ctot;
+  }
+  // global_pool writes the caller's feat tensor; it has no workspace buffer
+  Op g; g.kind = OP_GPOOL; g.id = "global_pool"; g.in_val = x; g.out_val = -1; g.k = 7;
+  e->ops.push_back(g);
+}
+
+static void plan(ssnb_engine* e) {
+  const size_t F = (size_t)e->F;
+  size_t off = 0;
+  for (Buffer& b : e->bufs) { b.off = off; off = align_up(off + F * b.H * b.W * b.C * e->esz, 1024); }
+  if (e->cfg.training)
+    for (Buffer& b : e->bufs) { b.goff = off; off = align_up(off + F * b.H * b.W * b.C * e->esz, 1024); }
+  for (Op& o : e->ops)
+    if (o.kind == OP_MAXPOOL) {
+      const Buffer& ob = e->bufs[e->vals[o.out_val].buf];
+      o.argmax_off = off;
+      off = align_up(off + F * ob.H * ob.W * e->vals[o.out_val].C, 1024);
+    }
+  e->packed.resize(e->convs.size());
+  for (size_t i = 0; i < e->convs.size(); ++i) {
+    const ConvSpec& c = e->convs[i];
+    const size_t n = (size_t)c.cout * c.cin * c.k * c.k;
+    e->packed[i].wf = off; off = align_up(off + n * e->esz, 1024);
+    e->packed[i].wd = off; off = align_up(off + n * e->esz, 1024);
+    e->packed[i].bias = off; off = align_up(off + c.cout * 4, 256);
+    e->packed[i].scale = off; off = align_up(off + c.cout * 4, 256);
+  }
+  // backward bookkeeping: accumulate flags + split-K sizing
+  size_t pmax = 0;
+  if (e->cfg.training) {
+    std::vector<char> written(e->vals.size(), 0);
+    for (int i = (int)e->ops.size() - 1; i >= 0; --i) {
+      Op& o = e->ops[i];
+      o.grad_accumulate = written[o.in_val];
+      written[o.in_val] = 1;
+      if (o.kind == OP_CONV) {
+        const ConvSpec& c = e->convs[o.conv];
+        const Buffer& ob = e->bufs[e->vals[o.out_val].buf];
+        const long long M = (long long)F * ob.H * ob.W;
+        const int taps = c.k * c.k;
+        const bool flat = c.cin < 16;
+        const long long tiles = (long long)((c.cout + 63) / 64) * (flat ? (taps * c.cin + 63) / 64 : ((c.cin + 63) / 64) * taps);
+        long long splits = (592 + tiles - 1) / tiles;
+        if (splits > 128) splits = 128;
+        while (splits > 1 && M / splits < 256) --splits;
+        long long rows = (M + splits - 1) / splits;
+        rows = (rows + 15) / 16 * 16;
+        splits = (M + rows - 1) / rows;
+        o.wsplits = (int)splits; o.wrows = (int)rows;
+        const size_t need = (size_t)splits * taps * c.cout * c.cin * 4;
+        if (need > pmax) pmax = need;
+      }
+    }
+  }
+  e->partial_off = off; e->partial_bytes = pmax; off = align_up(off + pmax, 1024);
+  e->bpartial_off = off; off = align_up(off + 64 * 512 * 4, 1024);
+  umma_plan_workspace(e->umma_ctx, off);   // FAST-mode extras (packed fp16 tensor-core weights etc.)
+  e->ws_bytes = off;
+}
+
+// ---- op execution --------------------------------------------------------------------------------
+#define DISPATCH(e, call_f, call_h) ((e)->fp16 ? (call_h) : (call_f))
+
+static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* feat, cudaStream_t s) {
+  const int F = e->F;
+  if (o.kind == OP_CONV) {
+    const ConvSpec& c = e->convs[o.conv];
+    const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
+    if (e->fp16 && o.umma.enabled) return umma_conv_forward(e->umma_ctx, o.umma, s);
+    ConvArgs a;
+    a.src = in.base; a.SH = in.H; a.SW = in.W; a.Csrc = in.C; a.src_pitch = in.pitch; a.src_coff = in.coff;
+    a.dst = out.base; a.DH = out.H; a.DW = out.W; a.Cdst = out.C; a.dst_pitch = out.pitch; a.dst_coff = out.coff;
+    a.wgt = e->ws + e->packed[o.conv].wf; a.bias = (const float*)(e->ws + e->packed[o.conv].bias);
+    a.F = F; a.k = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = 1; a.accumulate = 0; a.dgrad = 0;
+    return DISPATCH(e, launch_conv<float>(a, s), launch_conv<__half>(a, s));
+  }
+  if (o.kind == OP_MAXPOOL) {
+    const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
+    uint8_t* am = (uint8_t*)(e->ws + o.argmax_off);
+    return DISPATCH(e, launch_maxpool_fwd<float>(in, out, F, o.k, o.stride, o.pad, am, s),
+                    launch_maxpool_fwd<__half>(in, out, F, o.k, o.stride, o.pad, am, s));
+  }
+  if (o.kind == OP_AVGPOOL) {
+    const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
+    return DISPATCH(e, launch_avgpool3_fwd<float>(in, out, F, 0, s), launch_avgpool3_fwd<__half>(in, out, F, 0, s));
+  }
+  if (o.kind == OP_GPOOL) {
+    if (!feat) return e->fail(SSNB_EINVAL, "global_pool needs the feat output pointer");
+    const View in = e->view(o.in_val, false);
+    return DISPATCH(e, launch_gpool_fwd<float>(in, F, feat, s), launch_gpool_fwd<__half>(in, F, feat, s));
+  }
+  return SSNB_EINVAL;
+}
+
+static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t s) {
+  const int F = e->F;
+  const float gs = e->fp16 ? e->cfg.grad_scale : 1.0f;
+  int rc = 0;
+  if (o.kind == OP_GPOOL) {
+    if (!dfeat) return e->fail(SSNB_EINVAL, "global_pool backward needs dfeat");
+    const View din = e->view(o.in_val, true);
+    return DISPATCH(e, launch_gpool_bwd<float>(dfeat, gs, din, F, s), launch_gpool_bwd<__half>(dfeat, gs, din, F, s));
+  }
+  if (o.kind == OP_MAXPOOL) {
+    const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
+    const uint8_t* am = (const uint8_t*)(e->ws + o.argmax_off);
+    return DISPATCH(e, launch_maxpool_bwd<float>(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s),
+                    launch_maxpool_bwd<__half>(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s));
+  }
+  if (o.kind == OP_AVGPOOL) {
+    const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
+    return DISPATCH(e, launch_avgpool3_fwd<float>(dout, din, F, o.grad_accumulate, s),
+                    launch_avgpool3_fwd<__half>(dout, din, F, o.grad_accumulate, s));
+  }
+  // convolution: dz = dy * (y > 0); db, dW from dz; dx = dgrad(dz)
+  const ConvSpec& c = e->convs[o.conv];
+  const View x = e->view(o.in_val, false), y = e->view(o.out_val, false);
+  const View dx = e->view(o.in_val, true), dy = e->view(o.out_val, true);
+  if ((rc = DISPATCH(e, launch_relu_mask<float>(dy, y, F, s), launch_relu_mask<__half>(dy, y, F, s)))) return rc;
+  const float* scale = (const float*)(e->ws + e->packed[o.conv].scale);
+  float* partial = (float*)(e->ws + e->partial_off);
+  float* bpartial = (float*)(e->ws + e->bpartial_off);
+  const long long M = (long long)F * y.H * y.W;
+  if (e->db.size() && e->db[o.conv]) {
+    int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
+    rc = DISPATCH(e, launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, e->db[o.conv], s),
+                  launch_bias_grad<__half>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, e->db[o.conv], s));
+    if (rc) return rc;
+  }
+  if (e->dw.size() && e->dw[o.conv]) {
+    WgradArgs w;
+    w.dz = dy.base; w.OH = y.H; w.OW = y.W; w.Cout = y.C; w.dz_pitch = dy.pitch; w.dz_coff = dy.coff;
+    w.x = x.base; w.IH = x.H; w.IW = x.W; w.Cin = x.C; w.x_pitch = x.pitch; w.x_coff = x.coff;
+    w.partial = partial; w.F = F; w.k = c.k; w.stride = c.stride; w.pad = c.pad;
+    w.rows_per_split = o.wrows; w.splits = o.wsplits;
+    if ((rc = DISPATCH(e, launch_wgrad<float>(w, s), launch_wgrad<__half>(w, s)))) return rc;
+    if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s))) return rc;
+  }
+  if (e->vals[o.in_val].name != "data") {
+    ConvArgs a;
+    a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
+    a.dst = dx.base; a.DH = dx.H; a.DW = dx.W; a.Cdst = dx.C; a.dst_pitch = dx.pitch; a.dst_coff = dx.coff;
+    a.wgt = e->ws + e->packed[o.conv].wd; a.bias = nullptr;
+    a.F = F; a.k = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = 0; a.accumulate = o.grad_accumulate; a.dgrad = 1;
+    rc = DISPATCH(e, launch_conv<float>(a, s), launch_conv<__half>(a, s));
+  }
+  return rc;
+}
+
+int engine_tail_view(ssnb_handle h, View* v, int* F, int* fp16) {
+  if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
+  *v = h->view(h->ops.back().in_val, false);
+  *F = h->F; *fp16 = h->fp16 ? 1 : 0;
+  return 0;
+}
+
+}  // namespace ssnb
+
+// ---- C ABI -----------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ssnb_version(void) { return "libssn_b200 0.1 (sm_100a)"; }
+
+const char* ssnb_last_error(ssnb_handle h) { return h ? h->error.c_str() : ssnb::thread_error().c_str(); }
+
+int ssnb_num_convs(void) { return 69; }
+
+int ssnb_conv_info(int idx, int in_channels, char* name, int name_cap, int* cin, int* cout, int* k, int* stride, int* pad) {
+  std::vector<ConvSpec> t = conv_table(in_channels);
+  if (idx < 0 || idx >= (int)t.size()) { set_thread_error("ssnb_conv_info: index out of range"); return SSNB_EINVAL; }
+  if (name && name_cap > 0) { snprintf(name, name_cap, "%s", t[idx].id.c_str()); }
+  if (cin) *cin = t[idx].cin; if (cout) *cout = t[idx].cout; if (k) *k = t[idx].k;
+  if (stride) *stride = t[idx].stride; if (pad) *pad = t[idx].pad;
+  return SSNB_OK;
+}
+
+int ssnb_create(const ssnb_config* cfg, ssnb_handle* out) {
+  if (!cfg || !out) { set_thread_error("ssnb_create: null argument"); return SSNB_EINVAL; }
+  if (cfg->frames <= 0 || cfg->in_channels <= 0 || cfg->in_channels > 64) { set_thread_error("ssnb_create: bad frames/in_channels"); return SSNB_EINVAL; }
+  if (cfg->precision != SSNB_EXACT_FP32 && cfg->precision != SSNB_FAST_FP16) { set_thread_error("ssnb_create: unknown precision"); return SSNB_EINVAL; }
+  ssnb_engine* e = new ssnb_engine();
+  e->cfg = *cfg;
+  if (!(e->cfg.grad_scale > 0.f)) e->cfg.grad_scale = 1.0f;
+  e->F = cfg->frames;
+  e->fp16 = cfg->precision == SSNB_FAST_FP16;
+  e->esz = e->fp16 ? 2 : 4;
+  build_graph(e);
+  if ((int)e->convs.size() != 69) { delete e; set_thread_error("internal: conv table size"); return SSNB_ESTATE; }
+  umma_context_init(e->umma_ctx, e->fp16);
+  plan(e);
+  e->launches0 = g_launches.load();
+  *out = e;
+  return SSNB_OK;
+}
+
+int ssnb_destroy(ssnb_handle h) {
+  if (!h) return SSNB_OK;
+  umma_context_destroy(h->umma_ctx);
+  delete h;
+  return SSNB_OK;
+}
+
+size_t ssnb_workspace_bytes(ssnb_handle h) { return h ? h->ws_bytes : 0; }
+
+int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
+  if (!h) return SSNB_EINVAL;
+  if (!dev_ptr || bytes < h->ws_bytes) return h->fail(SSNB_EINVAL, "workspace too small");
+  if (((uintptr_t)dev_ptr) % 1024) return h->fail(SSNB_EINVAL, "workspace must be 1024-byte aligned");
+  h->ws = (char*)dev_ptr;
+  h->weights_ready = false;
+  // bind tcgen05 plans (tensor maps need final addresses)
+  for (Op& o : h->ops)
+    if (o.kind == OP_CONV && h->fp16) {
+      const ConvSpec& c = h->convs[o.conv];
+      int rc = umma_conv_bind(h->umma_ctx, o.umma, h->view(o.in_val, false), h->view(o.out_val, false), h->F, c.cin, c.cout,
+                              c.k, c.stride, c.pad, h->ws, o.conv, (const float*)(h->ws + h->packed[o.conv].bias));
+      if (rc) return h->fail(rc, "umma_conv_bind(" + c.id + "): " + ssnb::thread_error());
+    }
+  return SSNB_OK;
+}
+
+int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* b, const float* const* gamma,
+                      const float* const* beta, const float* const* mean, const float* const* var, void* stream) {
+  if (!h || !h->ws) return h ? h->fail(SSNB_ESTATE, "set_workspace first") : SSNB_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (size_t i = 0; i < h->convs.size(); ++i) {
+    const ConvSpec& c = h->convs[i];
+    const PackedConv& p = h->packed[i];
+    int rc = h->fp16 ? launch_pack_conv<__half>(w[i], b[i], gamma[i], beta[i], mean[i], var[i], c.cout, c.cin, c.k,
+                                                (__half*)(h->ws + p.wf), (__half*)(h->ws + p.wd), (float*)(h->ws + p.bias),
+                                                (float*)(h->ws + p.scale), s)
+                     : launch_pack_conv<float>(w[i], b[i], gamma[i], beta[i], mean[i], var[i], c.cout, c.cin, c.k,
+                                               (float*)(h->ws + p.wf), (float*)(h->ws + p.wd), (float*)(h->ws + p.bias),
+                                               (float*)(h->ws + p.scale), s);
+    if (rc) return h->fail(rc, "pack_weights(" + c.id + "): " + ssnb::thread_error());
+  }
+  if (h->fp16) {
+    for (Op& o : h->ops)
+      if (o.kind == OP_CONV && o.umma.enabled) {
+        const ConvSpec& c = h->convs[o.conv];
+        int rc = umma_conv_pack(h->umma_ctx, o.umma, (const __half*)(h->ws + h->packed[o.conv].wf), c.cin, c.cout, c.k, s);
+        if (rc) return h->fail(rc, "umma_conv_pack(" + c.id + "): " + ssnb::thread_error());
+      }
+  }
+  h->weights_ready = true;
+  return SSNB_OK;
+}
+
+int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void* stream) {
+  if (!h || !input_nchw || !feat) return h ? h->fail(SSNB_EINVAL, "null argument") : SSNB_EINVAL;
+  if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
+  cudaStream_t s = (cudaStream_t)stream;
+  const View d = h->view(h->val_by_name["data"], false);
+  int rc = h->fp16 ? launch_nchw_to_nhwc<__half>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s)
+                   : launch_nchw_to_nhwc<float>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s);
+  if (rc) return h->fail(rc, "input layout: " + ssnb::thread_error());
+  for (const Op& o : h->ops)
+    if ((rc = run_fwd(h, o, input_nchw, feat, s))) return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error());
+  return SSNB_OK;
+}
+
+int ssnb_bind_grads(ssnb_handle h, float* const* dw, float* const* db) {
+  if (!h) return SSNB_EINVAL;
+  h->dw.assign(h->convs.size(), nullptr); h->db.assign(h->convs.size(), nullptr);
+  for (size_t i = 0; i < h->convs.size(); ++i) { if (dw) h->dw[i] = dw[i]; if (db) h->db[i] = db[i]; }
+  return SSNB_OK;
+}
+
+int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float* const* db, void* stream) {
+  if (!h || !dfeat) return h ? h->fail(SSNB_EINVAL, "null argument") : SSNB_EINVAL;
+  if (!h->cfg.training) return h->fail(SSNB_ESTATE, "engine created without training=1");
+  if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
+  ssnb_bind_grads(h, dw, db);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
+    int rc = run_bwd(h, h->ops[i], dfeat, s);
+    if (rc) return h->fail(rc, "bwd " + h->ops[i].id + ": " + ssnb::thread_error());
+  }
+  return SSNB_OK;
+}
+
+int ssnb_num_ops(ssnb_handle h) { return h ? (int)h->ops.size() : 0; }
+
+int ssnb_op_info(ssnb_handle h, int op, char* kind, int kind_cap, char* in_name, int in_cap, char* out_name, int out_cap) {
+  if (!h || op < 0 || op >= (int)h->ops.size()) return SSNB_EINVAL;
+  static const char* kn[] = {"conv", "maxpool", "avgpool", "gpool"};
+  const Op& o = h->ops[op];
+  if (kind) snprintf(kind, kind_cap, "%s", kn[o.kind]);
+  if (in_name) snprintf(in_name, in_cap, "%s", h->vals[o.in_val].name.c_str());
+  if (out_name) snprintf(out_name, out_cap, "%s", o.out_val >= 0 ? h->vals[o.out_val].name.c_str() : "feat");
+  return SSNB_OK;
+}
+
+int ssnb_value_shape(ssnb_handle h, const char* name, int* c, int* hh, int* ww) {
+  if (!h || !name) return SSNB_EINVAL;
+  auto it = h->val_by_name.find(name);
+  if (it == h->val_by_name.end()) return h->fail(SSNB_EINVAL, std::string("unknown value ") + name);
+  const View v = h->view(it->second, false);
+  if (c) *c = v.C; if (hh) *hh = v.H; if (ww) *ww = v.W;
+  return SSNB_OK;
+}
+
+int ssnb_value_write(ssnb_handle h, const char* name, int grad, const float* src_nchw, void* stream) {
+  if (!h || !name || !src_nchw || !h->ws) return SSNB_EINVAL;
+  auto it = h->val_by_name.find(name);
+  if (it == h->val_by_name.end()) return h->fail(SSNB_EINVAL, std::string("unknown value ") + name);
+  if (grad && !h->cfg.training) return h->fail(SSNB_ESTATE, "no gradient buffers");
+  const View v = h->view(it->second, grad != 0);
+  const float sc = (grad && h->fp16) ? h->cfg.grad_scale : 1.0f;
+  int rc = h->fp16 ? launch_nchw_to_nhwc<__half>(src_nchw, h->F, v.C, v.H, v.W, v, sc, (cudaStream_t)stream)
+                   : launch_nchw_to_nhwc<float>(src_nchw, h->F, v.C, v.H, v.W, v, sc, (cudaStream_t)stream);
+  return rc ? h->fail(rc, ssnb::thread_error()) : SSNB_OK;
+}
+
+int ssnb_value_read(ssnb_handle h, const char* name, int grad, float* dst_nchw, void* stream) {
+  if (!h || !name || !dst_nchw || !h->ws) return SSNB_EINVAL;
+  auto it = h->val_by_name.find(name);
+  if (it == h->val_by_name.end()) return h->fail(SSNB_EINVAL, std::string("unknown value ") + name);
+  if (grad && !h->cfg.training) return h->fail(SSNB_ESTATE, "no gradient buffers");
+  const View v = h->view(it->second, grad != 0);
+  const float sc = (grad && h->fp16) ? 1.0f / h->cfg.grad_scale : 1.0f;
+  int rc = h->fp16 ? launch_nhwc_to_nchw<__half>(v, h->F, sc, dst_nchw, (cudaStream_t)stream)
+                   : launch_nhwc_to_nchw<float>(v, h->F, sc, dst_nchw, (cudaStream_t)stream);
+  return rc ? h->fail(rc, ssnb::thread_error()) : SSNB_OK;
+}
+
+int ssnb_run_op(ssnb_handle h, int op, int backward, void* stream) {
+  if (!h || op < 0 || op >= (int)h->ops.size()) return SSNB_EINVAL;
+  if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
+  const Op& o = h->ops[op];
+  if (o.kind == OP_GPOOL) return h->fail(SSNB_ENOSUPPORT, "run_op: global_pool runs through backbone_fwd/bwd");
+  int rc = backward ? run_bwd(h, o, nullptr, (cudaStream_t)stream) : run_fwd(h, o, nullptr, nullptr, (cudaStream_t)stream);
+  return rc ? h->fail(rc, o.id + ": " + ssnb::thread_error()) : SSNB_OK;
+}
+
+int64_t ssnb_launch_count(ssnb_handle h) { return h ? (int64_t)(g_launches.load() - h->launches0) : 0; }
+int64_t ssnb_global_launch_count(void) { return (int64_t)g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""BNInception with the reference's module surface (model_zoo/bninception/pytorch_load.py:8-61),
+executed by libssn_b200's engine instead of an op-by-op PyTorch interpreter.
+
+The nn.Conv2d / nn.BatchNorm2d children exist as parameter holders only: they give the module the
+reference's state_dict keys (`<yaml id>.weight|bias`, `<id>_bn.weight|bias|running_mean|
+running_var`, `fc.*`) and make SSN.get_optim_policies (ssn_models.py:203-251) work unchanged; their
+own forward() is never called.  forward(x[N,C,224,224]) -> fc(global_pool features [N,1024]).
+"""
+import torch
+from torch import nn
+
+from ssn_b200 import _lib
+from ssn_b200.engine import BackboneEngine, BackboneFunction, conv_table
+
+
+class BNInception(nn.Module):
+    def __init__(self, model_path=None, num_classes=101, weight_url=None, in_channels=3):
+        super(BNInception, self).__init__()
+        # model_path / weight_url are accepted for signature compatibility; the graph is built into
+        # the library and there is no network access for pretrained weights.
+        self._conv_names = []
+        for (name, cin, cout, k, stride, pad) in conv_table(in_channels):
+            setattr(self, name, nn.Conv2d(cin, cout, k, stride, pad, bias=True))
+            setattr(self, name + "_bn", nn.BatchNorm2d(cout, momentum=0.1))
+            self._conv_names.append(name)
+        self.fc = nn.Linear(1024, 1000)
+        self.last_layer_name = "fc"
+        self.precision = _lib.EXACT_FP32
+        self.grad_scale = 1.0
+        self._engines = {}
+
+    # ---- engine management --------------------------------------------------------------------
+    def set_precision(self, precision, grad_scale=None):
+        """precision: ssn_b200.EXACT_FP32 (fp32 SIMT) or ssn_b200.FAST_FP16 (tcgen05)."""
+        self.precision = precision
+        if grad_scale is not None:
+            self.grad_scale = float(grad_scale)
+        self._engines = {}
+
+    def _convs(self):
+        return [getattr(self, n) for n in self._conv_names]
+
+    def _bns(self):
+        return [getattr(self, n + "_bn") for n in self._conv_names]
+
+    def in_channels(self):
+        return getattr(self, self._conv_names[0]).in_channels
+
+    def _weights_version(self):
+        v = 0
+        for c, b in zip(self._convs(), self._bns()):
+            v += c.weight._version + c.bias._version + b.weight._version + b.bias._version \
+                + b.running_mean._version + b.running_var._version
+        return (v, id(self._convs()[0].weight), self._convs()[0].weight.data_ptr())
+
+    def engine_for(self, frames, training, device):
+        key = (frames, bool(training), self.precision, self.in_channels(), str(device))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = BackboneEngine(self.in_channels(), frames, self.precision, training, self.grad_scale, device)
+            self._engines[key] = eng
+        ver = self._weights_version()
+        if eng.packed_version != ver:
+            cs, bs = self._convs(), self._bns()
+            eng.pack([c.weight.data for c in cs], [c.bias.data for c in cs], [b.weight.data for b in bs],
+                     [b.bias.data for b in bs], [b.running_mean for b in bs], [b.running_var for b in bs])
+            eng.packed_version = ver
+        return eng
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise RuntimeError("BNInception(B200) runs on CUDA only: move the model and input to the GPU "
+                               "(libssn_b200 has no CPU path)")
+        for b in self._bns():
+            if b.training:
+                raise NotImplementedError("only bn_mode='frozen' (all BatchNorm2d in eval mode) is accelerated; "
+                                          "'partial'/'full' are listed as next steps in DESIGN.md")
+        cs = self._convs()
+        params = [c.weight for c in cs] + [c.bias for c in cs]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        eng = self.engine_for(input.shape[0], need_grad, input.device)
+        if need_grad:
+            feat = BackboneFunction.apply(input, eng, len(cs), *params)
+        else:
+            feat = eng.forward(input)
+        return self.fc(feat)

@@ -1,0 +1,425 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the reference-shaped module surface) against
+the CPU oracle and the committed golden vectors.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ssn_oracle as O
+from oracle import synth
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+# ---- STPP ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,cfg,seg", [("pyr", (1, (1, 2), 1), (2, 5, 2)), ("flat", [1, 1, 1], (2, 5, 2)),
+                                         ("seg3", [1, 1, 1], (1, 1, 1)), ("seg3nan", (1, (1, 2), 1), (1, 1, 1)),
+                                         ("deep", ((1, 2), (1, 2, 4), 2), (4, 8, 4))])
+def test_stpp_golden(golden_dir, tag, cfg, seg):
+    dev = _cuda()
+    from ops.ssn_ops import StructuredTemporalPyramidPooling
+    z = _load(golden_dir, "stpp.npz")
+    ft = torch.tensor(z[tag + "_ft"], device=dev, requires_grad=True)
+    S = sum(seg)
+    mod = StructuredTemporalPyramidPooling(ft.shape[1], True, configs=cfg)
+    a, c = mod(ft, torch.tensor(z[tag + "_sc"], device=dev), [seg[0], seg[0] + seg[1], S])
+    # <= 2 ulp; NaN positions must coincide
+    ref_a, ref_c = z[tag + "_act"], z[tag + "_comp"]
+    assert np.array_equal(np.isnan(c.detach().cpu().numpy()), np.isnan(ref_c))
+    np.testing.assert_allclose(a.detach().cpu().numpy(), ref_a, rtol=3e-7, atol=1e-7)
+    np.testing.assert_allclose(np.nan_to_num(c.detach().cpu().numpy()), np.nan_to_num(ref_c), rtol=3e-7, atol=1e-7)
+    assert mod.feat_multiplier == int(z[tag + "_mult"])
+    loss = (a * torch.tensor(z[tag + "_wa"], device=dev)).sum() + (torch.nan_to_num(c) * torch.tensor(z[tag + "_wc"], device=dev)).sum()
+    loss.backward()
+    got = ft.grad.cpu().numpy()
+    ref = z[tag + "_dft"]
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(np.nan_to_num(got[ok]), ref[ok], rtol=2e-6, atol=1e-6)
+
+
+def test_stpp_large_property():
+    """full-size property: STPP is linear in ft and the course part equals the mean of segments 2..6"""
+    dev = _cuda()
+    from ops.ssn_ops import StructuredTemporalPyramidPooling
+    n, D = 4096, 1024
+    g = torch.Generator().manual_seed(5)
+    ft = torch.randn(n * 9, D, generator=g).to(dev)
+    sc = torch.rand(n, 2, generator=g).to(dev)
+    mod = StructuredTemporalPyramidPooling(D, True)
+    a1, c1 = mod(ft, sc, [2, 7, 9])
+    a2, c2 = mod(ft * 2.0, sc, [2, 7, 9])
+    assert torch.equal(a2, a1 * 2.0) and torch.equal(c2, c1 * 2.0)
+    ref = ft.view(n, 9, D)[:, 2:7].mean(1)
+    assert rel_l2(a1, ref) < 1e-6
+    # checksum of checksums: sum over parts of course pyramid == relation between levels
+    lvl1 = c1[:, D:2 * D] * 3.0
+    lvl2 = (c1[:, 2 * D:3 * D] * 3.0 * 2 + c1[:, 3 * D:4 * D] * 3.0 * 3) / 5.0
+    assert rel_l2(lvl2, lvl1) < 1e-5
+
+
+# ---- losses -----------------------------------------------------------------------------------------
+def test_losses_golden(golden_dir):
+    dev = _cuda()
+    import ops.ssn_ops as R
+    z = _load(golden_dir, "losses.npz")
+    pred = torch.tensor(z["ohem_pred"], device=dev)
+    labels = torch.tensor(z["ohem_labels"], device=dev)
+    for tag, pos, ratio, gs in (("pos", 1, 1.0, 1), ("neg", -1, 0.17, 7), ("half", -1, 0.5, 4)):
+        p = pred.clone().requires_grad_(True)
+        l = R.OHEMHingeLoss.apply(p, labels, pos, ratio, gs)
+        assert tuple(l.shape) == (1,)
+        (l * 1.7).sum().backward()
+        np.testing.assert_allclose(l.detach().cpu().numpy(), z["ohem_" + tag + "_loss"], rtol=1e-6)
+        got, ref = p.grad.cpu().numpy(), z["ohem_" + tag + "_grad"]
+        assert np.array_equal(got != 0, ref != 0)          # kept-index sets: exact
+        np.testing.assert_allclose(got, ref, rtol=1e-6)
+    p = pred.clone().requires_grad_(True)
+    l = R.OHEMHingeLoss.apply(p, torch.tensor(z["ohem_wrap_labels"], device=dev), -1, 0.3, 7)
+    l.sum().backward()
+    np.testing.assert_allclose(l.detach().cpu().numpy(), z["ohem_wrap_loss"], rtol=1e-6)
+    np.testing.assert_array_equal(p.grad.cpu().numpy(), z["ohem_wrap_grad"])
+    p = pred.clone().requires_grad_(True)
+    cl = R.CompletenessLoss()(p, labels, 1, 7)
+    cl.sum().backward()
+    np.testing.assert_allclose(cl.detach().cpu().numpy(), z["comp_loss"], rtol=1e-6)
+    np.testing.assert_allclose(p.grad.cpu().numpy(), z["comp_grad"], rtol=1e-6)
+    rp = torch.tensor(z["reg_pred"], device=dev, requires_grad=True)
+    l = R.ClassWiseRegressionLoss()(rp, torch.tensor(z["reg_labels"], device=dev), torch.tensor(z["reg_targets"], device=dev))
+    l.backward()
+    np.testing.assert_allclose(l.item(), z["reg_loss"], rtol=1e-6)
+    np.testing.assert_allclose(rp.grad.cpu().numpy(), z["reg_grad"], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("tag,cfg", [("flat", (1, 1, 1)), ("pyr", (1, (1, 2), 1))])
+def test_stpp_reorganized_golden(golden_dir, tag, cfg):
+    dev = _cuda()
+    from ops.ssn_ops import STPPReorgainzed
+    z = _load(golden_dir, "test_path.npz")
+    K = 3
+    scores = torch.tensor(z[tag + "_scores"], device=dev)
+    st = STPPReorgainzed(scores.shape[1], K + 1, K, 2 * K, True, True, stpp_cfg=cfg)
+    a, c, r = st.forward(scores, torch.tensor(z[tag + "_ticks"]), torch.tensor(z[tag + "_sc"]))
+    for got, name in ((a, "_act"), (c, "_comp"), (r, "_reg")):
+        ref = z[tag + name]
+        got = got.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=2e-6, atol=1e-6)
+
+
+def test_stpp_reorganized_vs_oracle_big():
+    dev = _cuda()
+    from ops.ssn_ops import STPPReorgainzed
+    g = torch.Generator().manual_seed(3)
+    K, T, N = 20, 400, 300
+    cfg = (1, (1, 2), 1)
+    D = (K + 1) + 5 * K + 5 * 2 * K
+    scores = torch.randn(T, D, generator=g)
+    ticks = torch.sort(torch.randint(0, T, (N, 4), generator=g), dim=1)[0]
+    sc = torch.rand(N, 2, generator=g)
+    ref = O.stpp_reorganized(scores, ticks, sc, K + 1, K, 2 * K, cfg)
+    got = STPPReorgainzed(D, K + 1, K, 2 * K, True, True, stpp_cfg=cfg).forward(scores.to(dev), ticks, sc)
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ---- heads --------------------------------------------------------------------------------------------
+def _heads_case(dev, videos, K, M, seed):
+    g = torch.Generator().manual_seed(seed)
+    n = videos * 8
+    course = torch.randn(n, 1024, generator=g)
+    stpp = torch.randn(n, 1024 * M, generator=g)
+    hd = synth.synth_heads(K, M, seed=seed, std=0.02, bias_std=0.1)
+    ptype = torch.tensor([0, 1, 1, 1, 1, 1, 1, 2]).repeat(videos)
+    target = torch.randint(1, K + 1, (n,), generator=g)
+    target[ptype == 2] = 0
+    rtarget = torch.randn(n, 2, generator=g)
+    return course, stpp, hd, ptype, target, rtarget
+
+
+@pytest.mark.parametrize("videos,K,M", [(4, 20, 5), (2, 4, 3), (8, 200, 5)])
+def test_fused_heads_loss_vs_oracle(videos, K, M):
+    dev = _cuda()
+    import ssn_models
+    from ssn_b200.engine import heads_loss_fused
+    course, stpp, hd, ptype, target, rtarget = _heads_case(dev, videos, K, M, 7)
+    # oracle
+    c0 = course.clone().requires_grad_(True); s0 = stpp.clone().requires_grad_(True)
+    hp = {k: v.clone().requires_grad_(True) for k, v in hd.items()}
+    F = torch.nn.functional
+    ra = F.linear(c0, hp["activity_fc.weight"], hp["activity_fc.bias"])
+    rc = F.linear(s0, hp["completeness_fc.weight"], hp["completeness_fc.bias"])
+    rr = F.linear(s0, hp["regressor_fc.weight"], hp["regressor_fc.bias"]).view(-1, K, 2)
+    ai = ((ptype == 0) | (ptype == 2)).nonzero().view(-1); ci = ((ptype == 0) | (ptype == 1)).nonzero().view(-1)
+    ri = (ptype == 0).nonzero().view(-1)
+    loss, (la, lc, lr) = O.total_loss((ra[ai], target[ai], rc[ci], target[ci], rr[ri], target[ri], rtarget[ri]))
+    loss.backward()
+    # product
+    act_fc = ssn_models._HeadLinear(1024, K + 1).to(dev); comp_fc = ssn_models._HeadLinear(1024 * M, K).to(dev)
+    reg_fc = ssn_models._HeadLinear(1024 * M, 2 * K).to(dev)
+    for fc, nm in ((act_fc, "activity_fc"), (comp_fc, "completeness_fc"), (reg_fc, "regressor_fc")):
+        fc.weight.data.copy_(hd[nm + ".weight"]); fc.bias.data.copy_(hd[nm + ".bias"])
+    out = heads_loss_fused(course.to(dev), stpp.to(dev), act_fc, comp_fc, reg_fc, ptype.to(dev), target.to(dev),
+                           rtarget.to(dev), K, M)
+    np.testing.assert_allclose(out["losses"].cpu().numpy(), [la.item(), lc.item(), lr.item(), loss.item()], rtol=2e-5)
+    assert rel_l2(out["raw_act"], ra.detach()) < 1e-5 and rel_l2(out["raw_comp"], rc.detach()) < 1e-5
+    assert rel_l2(out["raw_reg"], rr.detach().reshape(-1, 2 * K)) < 1e-5
+    assert rel_l2(out["d_course"], c0.grad) < 1e-5 and rel_l2(out["d_stpp"], s0.grad) < 1e-5
+    for k, nm in (("act", "activity_fc"), ("comp", "completeness_fc"), ("reg", "regressor_fc")):
+        assert rel_l2(out["d_%s_w" % k], hp[nm + ".weight"].grad) < 1e-5, nm
+        assert rel_l2(out["d_%s_b" % k], hp[nm + ".bias"].grad) < 1e-5, nm
+    # kept (non-zero) gradient positions of the completeness logits are exact
+    # (recovered through d_comp_b support: classes with any kept row)
+    assert np.array_equal(out["d_comp_b"].cpu().numpy() != 0, hp["completeness_fc.bias"].grad.numpy() != 0)
+
+
+# ---- backbone ---------------------------------------------------------------------------------------------
+def _load_backbone(model_base, bb, dev):
+    sd = model_base.state_dict()
+    for k, v in bb.items():
+        sd[k].copy_(v)
+    return model_base.to(dev)
+
+
+@pytest.fixture(scope="module")
+def backbone_rgb():
+    return synth.synth_backbone(3, seed=0)
+
+
+def test_backbone_exact_golden(golden_dir, backbone_rgb):
+    """EXACT mode, whole backbone, 18 frames: against the reference's own output (golden)."""
+    dev = _cuda()
+    import model_zoo
+    from ops.ssn_ops import Identity
+    z = _load(golden_dir, "ssn_e2e.npz")
+    net = model_zoo.BNInception()
+    net.fc = Identity()
+    _load_backbone(net, backbone_rgb, dev).eval()
+    x, *_ = synth.synth_batch(2, 4, 3, seed=0)
+    frames = x.view(-1, 3, 224, 224)[:18].to(dev)
+    with torch.no_grad():
+        out = net(frames)
+    err = rel_l2(out, torch.tensor(z["rgb_base_out18"]))
+    assert err < 1e-4, err     # tolerance: 1e-3 relative fp32 (north_star); measured ~1e-6
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_backbone_per_layer(backbone_rgb, precision):
+    """each op fed the ORACLE's input for that op; forward outputs and (training) backward
+    gradients compared per kernel boundary.  exact: 1e-5; fast(fp16 operands): 1e-3 rel-L2."""
+    dev = _cuda()
+    from ssn_b200 import _lib
+    from ssn_b200.engine import BackboneEngine
+    Fn = 2
+    tol = 2e-5 if precision == "exact" else 1e-3
+    x = synth.synth_frames(Fn, 3, seed=3)
+    bb = {k: v.clone() for k, v in backbone_rgb.items()}
+    for k in bb:
+        if k.endswith(".weight") and "_bn" not in k or k.endswith(".bias") and "_bn" not in k:
+            bb[k].requires_grad_(True)
+    taps = {}
+    xr = x.clone().requires_grad_(True)
+    feat = O.backbone_forward(bb, xr, 3, taps=taps)
+    taps["data"] = xr
+    for t in taps.values():
+        if t.requires_grad:
+            t.retain_grad()
+    g = torch.Generator().manual_seed(9)
+    dfeat = torch.randn(feat.shape, generator=g) * 0.01
+    feat.backward(dfeat)
+    eng = BackboneEngine(3, Fn, _lib.EXACT_FP32 if precision == "exact" else _lib.FAST_FP16, True, 1024.0, dev)
+    names = [n for (n, *_r) in O.conv_layers(3)]
+    eng.pack([bb[n + ".weight"].detach().to(dev) for n in names], [bb[n + ".bias"].detach().to(dev) for n in names],
+             [bb[n + "_bn.weight"].to(dev) for n in names], [bb[n + "_bn.bias"].to(dev) for n in names],
+             [bb[n + "_bn.running_mean"].to(dev) for n in names], [bb[n + "_bn.running_var"].to(dev) for n in names])
+    dw = [torch.zeros_like(bb[n + ".weight"].detach()).to(dev) for n in names]
+    db = [torch.zeros_like(bb[n + ".bias"].detach()).to(dev) for n in names]
+    eng.bind_grads(dw, db)
+    conv_idx = 0
+    worst = {}
+    for i, (kind, iname, oname) in enumerate(eng.ops()):
+        if kind == "gpool":
+            continue
+        eng.write(iname, taps[iname].detach().to(dev))
+        eng.run_op(i, backward=False)
+        got = eng.read(oname)
+        e = rel_l2(got, taps[oname].detach())
+        worst["fwd " + oname] = e
+        assert e < tol, ("fwd", oname, e)
+        # backward of this op: feed oracle activations (already there) and oracle output-gradient
+        gout = taps[oname].grad
+        eng.write(oname, taps[oname].detach().to(dev))            # the op's true output (ReLU mask source)
+        eng.write(oname, gout.to(dev), grad=True)
+        if iname != "data":
+            eng.write(iname, torch.zeros_like(taps[iname].detach()).to(dev), grad=True)
+        eng.run_op(i, backward=True)
+        if kind == "conv":
+            n = names[conv_idx]
+            ew = rel_l2(dw[conv_idx], bb[n + ".weight"].grad)
+            eb = rel_l2(db[conv_idx], bb[n + ".bias"].grad)
+            worst["wgrad " + n] = ew
+            assert ew < tol * 2 and eb < tol * 2, ("wgrad", n, ew, eb)
+            conv_idx += 1
+    # dgrad per op: run each op's backward alone into a zeroed input-gradient and compare with the
+    # oracle's autograd contribution of that op (computed by a local vjp)
+    for i, (kind, iname, oname) in enumerate(eng.ops()):
+        if kind == "gpool" or iname == "data":
+            continue
+        gout = taps[oname].grad
+        xin = taps[iname].detach().clone().requires_grad_(True)
+        ref_in = _oracle_single_op(bb, kind, oname, xin)
+        (gref,) = torch.autograd.grad(ref_in, xin, gout)
+        eng.write(iname, taps[iname].detach().to(dev))
+        eng.write(oname, taps[oname].detach().to(dev))
+        eng.write(oname, gout.to(dev), grad=True)
+        if kind == "maxpool":
+            eng.run_op(i, backward=False)                      # regenerate argmax for this input
+            eng.write(oname, gout.to(dev), grad=True)
+        eng.write(iname, torch.zeros_like(xin.detach()).to(dev), grad=True)
+        # force "first writer" semantics irrespective of plan flags: zeroed buffer + accumulate is the same
+        eng.run_op(i, backward=True)
+        got = eng.read(iname, grad=True)
+        e = rel_l2(got, gref)
+        worst["dgrad " + oname] = e
+        assert e < tol * 2, ("dgrad", oname, e)
+    print("per-layer worst (%s): %s" % (precision, sorted(worst.items(), key=lambda kv: -kv[1])[:5]))
+
+
+def _oracle_single_op(bb, kind, oname, xin):
+    Fnn = torch.nn.functional
+    if kind == "conv":
+        id_ = oname[:-3]
+        spec = {n: (k, s, p) for (n, _ci, _co, k, s, p) in O.conv_layers(3)}[id_]
+        z = Fnn.conv2d(xin, bb[id_ + ".weight"].detach(), bb[id_ + ".bias"].detach(), spec[1], spec[2])
+        z = Fnn.batch_norm(z, bb[id_ + "_bn.running_mean"], bb[id_ + "_bn.running_var"], bb[id_ + "_bn.weight"].detach(),
+                           bb[id_ + "_bn.bias"].detach(), False, 0.1, 1e-5)
+        return Fnn.relu(z)
+    for k_, id_, out, ins, a in O.bninception_ops(3):
+        if k_ == "pool" and out == oname:
+            return O._pool(xin, a)
+    raise KeyError(oname)
+
+
+def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
+    """whole SSN, B=2 videos (144 frames), EXACT mode, through the reference-shaped module surface
+    and the reference's training-loop calls (ssn_train.py:207-236): outputs, losses and every
+    gradient against the oracle (itself pinned to the reference by tests/golden/ssn_e2e.npz)."""
+    dev = _cuda()
+    import ssn_models
+    import ops.ssn_ops as R
+    K = 4
+    model = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+    hd = synth.synth_heads(K, 5, seed=0, std=0.02, bias_std=0.1)
+    sd = model.state_dict()
+    for k, v in backbone_rgb.items():
+        sd["base_model." + k].copy_(v)
+    for k, v in hd.items():
+        sd[k].copy_(v)
+    model = model.to(dev)
+    model.train()
+    x, sc, tgt, rtgt, ptype = synth.synth_batch(2, K, 3, seed=0)
+    outs = model(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
+    act, act_t, comp, comp_t, reg, reg_l, reg_t = outs
+    la = torch.nn.CrossEntropyLoss()(act, act_t)
+    lc = R.CompletenessLoss()(comp, comp_t, 1, 7)
+    lr = R.ClassWiseRegressionLoss()(reg, reg_l, reg_t)
+    loss = la + 0.1 * lc + 0.1 * lr
+    loss.backward()
+    z = _load(golden_dir, "ssn_e2e.npz")
+    for name, o in zip(("act", "act_t", "comp", "comp_t", "reg", "reg_l", "reg_t"), outs):
+        ref = z["rgb_" + name]
+        if ref.dtype.kind == "f":
+            assert rel_l2(o.detach(), torch.tensor(ref)) < 1e-4, name
+        else:
+            np.testing.assert_array_equal(o.cpu().numpy(), ref)     # index selection: bit-exact
+    np.testing.assert_allclose([la.item(), lc.item(), lr.item(), loss.item()], z["rgb_losses"], rtol=1e-4)
+    assert rel_l2(model.base_model.conv1_7x7_s2.weight.grad, torch.tensor(z["rgb_g_conv1_w"])) < 1e-3
+    assert rel_l2(model.base_model.conv1_7x7_s2.bias.grad, torch.tensor(z["rgb_g_conv1_b"])) < 1e-3
+    assert rel_l2(model.base_model.inception_3c_3x3.weight.grad[:8], torch.tensor(z["rgb_g_3c_3x3_w"])) < 1e-3
+    assert rel_l2(model.base_model.inception_5b_1x1.weight.grad[:4], torch.tensor(z["rgb_g_5b_1x1_w"])) < 1e-3
+    assert rel_l2(model.activity_fc.weight.grad, torch.tensor(z["rgb_g_act_w"])) < 1e-4
+    names = [str(s) for s in z["rgb_grad_names"]]
+    params = dict(model.named_parameters())
+    bad = []
+    for n_, ga in zip(names, z["rgb_grad_abs"]):
+        got = params[n_].grad.double().abs().sum().item()
+        if abs(got - ga) > 1e-3 * ga + 1e-9:
+            bad.append((n_, got, ga))
+    assert not bad, bad[:5]
+
+    # the fused step must reproduce the modular path
+    model2 = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+    model2.load_state_dict(model.state_dict())
+    model2 = model2.to(dev).train()
+    losses = model2.fused_step(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
+    np.testing.assert_allclose(losses.cpu().numpy(), [la.item(), lc.item(), lr.item(), loss.item()], rtol=1e-5)
+    p2 = dict(model2.named_parameters())
+    for n_, p in params.items():
+        if p.grad is not None:
+            assert rel_l2(p2[n_].grad, p.grad) < 1e-4, n_
+
+
+def test_flow_forward_exact(golden_dir):
+    dev = _cuda()
+    import ssn_models
+    z = _load(golden_dir, "ssn_e2e.npz")
+    K = 4
+    model = ssn_models.SSN(K, 2, 5, 2, "Flow", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+    bb = synth.synth_backbone(10, seed=0)
+    hd = synth.synth_heads(K, 5, seed=0, std=0.02, bias_std=0.1)
+    sd = model.state_dict()
+    for k, v in bb.items():
+        sd["base_model." + k].copy_(v)
+    for k, v in hd.items():
+        sd[k].copy_(v)
+    model = model.to(dev).train()
+    x, sc, tgt, rtgt, ptype = synth.synth_batch(2, K, 10, seed=0)
+    with torch.no_grad():
+        outs = model(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
+    for name, o in zip(("act", "act_t", "comp", "comp_t", "reg", "reg_l", "reg_t"), outs):
+        ref = z["flow_" + name]
+        if ref.dtype.kind == "f":
+            assert rel_l2(o, torch.tensor(ref)) < 1e-4, name
+        else:
+            np.testing.assert_array_equal(o.cpu().numpy(), ref)
+
+
+def test_test_forward_and_prepare_test_fc(backbone_rgb):
+    """test path: prepare_test_fc folding + test_forward == heads applied after STPP on a constant
+    video (pool∘FC = FC∘pool), ssn_models.py:176-201, ssn_test.py:83-87."""
+    dev = _cuda()
+    import ssn_models
+    K = 4
+    model = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, test_mode=True, stpp_cfg=(1, 1, 1))
+    hd = synth.synth_heads(K, 3, seed=1, std=0.02, bias_std=0.1)
+    sd = model.state_dict()
+    for k, v in backbone_rgb.items():
+        sd["base_model." + k].copy_(v)
+    for k, v in hd.items():
+        sd[k].copy_(v)
+    model.prepare_test_fc()
+    w_ref, b_ref = O.prepare_test_fc(hd, 3)
+    np.testing.assert_array_equal(model.test_fc.weight.data.numpy(), w_ref.numpy())
+    np.testing.assert_array_equal(model.test_fc.bias.data.numpy(), b_ref.numpy())
+    model = model.to(dev).eval()
+    x = synth.synth_frames(4, 3, seed=5).to(dev)
+    with torch.no_grad():
+        scores, base_out = model(x, None, None, None, None)
+    ref_feat = O.backbone_forward(backbone_rgb, x.cpu(), 3)
+    assert rel_l2(base_out, ref_feat) < 1e-4
+    assert rel_l2(scores, torch.nn.functional.linear(ref_feat, w_ref, b_ref)) < 1e-4

@@ -1,0 +1,82 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/ssnb.h declares, the
+host-side tables agree with the oracle, and argument validation works without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import ssn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssn_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ssnb.h")).read()
+    declared = set(re.findall(r"\b(ssnb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), "libssn_b200.so does not export " + name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+
+
+def test_conv_table_matches_oracle():
+    from ssn_b200.engine import conv_table
+    for cin in (3, 10):
+        assert conv_table(cin) == [tuple(r) for r in O.conv_layers(cin)]
+
+
+def test_engine_plan_without_gpu():
+    from ssn_b200 import _lib
+    cfg = _lib.Config(3, 18, _lib.EXACT_FP32, 1, 1.0, (C.c_int32 * 3)())
+    h = C.c_void_p()
+    _lib.check(_lib.lib.ssnb_create(C.byref(cfg), C.byref(h)))
+    assert _lib.lib.ssnb_workspace_bytes(h) > 0
+    n = _lib.lib.ssnb_num_ops(h)
+    assert n == 69 + 13        # 69 convs, 12 spatial pools + global pool
+    shape = [C.c_int() for _ in range(3)]
+    _lib.check(_lib.lib.ssnb_value_shape(h, b"inception_4e_output", *[C.byref(s) for s in shape]), h)
+    assert [s.value for s in shape] == [1056, 7, 7]
+    assert _lib.lib.ssnb_value_shape(h, b"nonexistent", None, None, None) != 0
+    assert b"unknown value" in _lib.lib.ssnb_last_error(h)
+    # calls that need device state fail with an error code, not a crash
+    assert _lib.lib.ssnb_backbone_fwd(h, None, None, None) != 0
+    _lib.lib.ssnb_destroy(h)
+    bad = _lib.Config(3, 0, 0, 0, 1.0, (C.c_int32 * 3)())
+    assert _lib.lib.ssnb_create(C.byref(bad), C.byref(h)) != 0
+
+
+def test_module_surface_matches_reference(golden_dir):
+    import json
+    import ssn_models
+    m = ssn_models.SSN(20, 2, 5, 2, "RGB", base_model="BNInception", dropout=0.8)
+    assert sum(p.numel() for p in m.parameters()) == 10599025
+    g = json.load(open(os.path.join(golden_dir, "bninception_graph.json")))
+    ref_keys = ["base_model." + k for k in g["state_dict_keys"] if not k.startswith("fc.")]
+    mine = [k for k in m.state_dict().keys() if k.startswith("base_model.")]
+    assert mine == ref_keys
+    assert isinstance(m.base_model.fc, torch.nn.Dropout)
+    pol = m.get_optim_policies()
+    assert [len(p["params"]) for p in pol] == [1, 1, 71, 71, 0]
+    assert [(p["lr_mult"], p["decay_mult"]) for p in pol] == [(1, 1), (2, 0), (1, 1), (2, 0), (1, 0)]
+    m.train()
+    assert all(not b.training for b in m.base_model.modules() if isinstance(b, torch.nn.BatchNorm2d))
+    assert (m.crop_size, m.scale_size, m.input_mean, m.input_std) == (224, 256, [104, 117, 128], [1])
+    with pytest.raises(ValueError):
+        ssn_models.SSN(20, 2, 5, 2, "RGB", base_model="nope")
+    with pytest.raises(RuntimeError):          # no CPU fallback: fails loudly
+        m(torch.zeros(2, 8 * 9 * 3, 224, 224), torch.zeros(2, 8, 2), torch.zeros(2, 8).long(), torch.zeros(2, 8, 2),
+          torch.zeros(2, 8).long())
+
+
+def test_stpp_part_table_matches_oracle():
+    from ops.ssn_ops import StructuredTemporalPyramidPooling
+    for cfg, seg in (((1, (1, 2), 1), [2, 7, 9]), ([1, 1, 1], [2, 7, 9]), (((1, 2), (1, 2, 4), 2), [4, 12, 16]),
+                     ((1, (1, 2), 1), [1, 2, 3])):
+        mod = StructuredTemporalPyramidPooling(1024, True, configs=cfg)
+        lo, hi, nm, col = mod.part_table(seg)
+        assert list(zip(lo, hi, nm, col)) == O.stpp_parts(cfg, seg)
+    with pytest.raises(ValueError):
+        StructuredTemporalPyramidPooling(8, True, configs=("x", 1, 1))
