@@ -3,6 +3,7 @@
 // interpreter (model_zoo/bninception/pytorch_load.py:8-61, layer_factory.py:25-83,
 // bn_inception.yaml) and the autograd graph PyTorch builds from it.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -61,7 +62,8 @@ struct Op {
   size_t argmax_off = 0;
   int grad_accumulate = 0;  // backward: dIn += (another consumer wrote first)
   int wsplits = 1, wrows = 0;
-  UmmaConvPlan umma;        // tcgen05 plan (FAST mode, eligible layers)
+  UmmaConvPlan umma;        // tcgen05 forward plan (FAST mode, stride-1 layers)
+  UmmaConvPlan umma_dgrad;  // tcgen05 data-gradient plan
 };
 struct PackedConv { size_t wf, wd, bias, scale; };
 
@@ -222,7 +224,6 @@ static void plan(ssnb_engine* e) {
   }
   e->partial_off = off; e->partial_bytes = pmax; off = align_up(off + pmax, 1024);
   e->bpartial_off = off; off = align_up(off + 64 * 512 * 4, 1024);
-  umma_plan_workspace(e->umma_ctx, off);   // FAST-mode extras (packed fp16 tensor-core weights etc.)
   e->ws_bytes = off;
 }
 
@@ -234,7 +235,7 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
   if (o.kind == OP_CONV) {
     const ConvSpec& c = e->convs[o.conv];
     const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
-    if (e->fp16 && o.umma.enabled) return umma_conv_forward(e->umma_ctx, o.umma, s);
+    if (e->fp16 && o.umma.enabled) return umma_conv_launch(e->umma_ctx, o.umma, s);
     ConvArgs a;
     a.src = in.base; a.SH = in.H; a.SW = in.W; a.Csrc = in.C; a.src_pitch = in.pitch; a.src_coff = in.coff;
     a.dst = out.base; a.DH = out.H; a.DW = out.W; a.Cdst = out.C; a.dst_pitch = out.pitch; a.dst_coff = out.coff;
@@ -305,6 +306,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s))) return rc;
   }
   if (e->vals[o.in_val].name != "data") {
+    if (e->fp16 && o.umma_dgrad.enabled) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s);
     ConvArgs a;
     a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
     a.dst = dx.base; a.DH = dx.H; a.DW = dx.W; a.Cdst = dx.C; a.dst_pitch = dx.pitch; a.dst_coff = dx.coff;
@@ -376,14 +378,23 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
   if (((uintptr_t)dev_ptr) % 1024) return h->fail(SSNB_EINVAL, "workspace must be 1024-byte aligned");
   h->ws = (char*)dev_ptr;
   h->weights_ready = false;
-  // bind tcgen05 plans (tensor maps need final addresses)
-  for (Op& o : h->ops)
-    if (o.kind == OP_CONV && h->fp16) {
-      const ConvSpec& c = h->convs[o.conv];
-      int rc = umma_conv_bind(h->umma_ctx, o.umma, h->view(o.in_val, false), h->view(o.out_val, false), h->F, c.cin, c.cout,
-                              c.k, c.stride, c.pad, h->ws, o.conv, (const float*)(h->ws + h->packed[o.conv].bias));
-      if (rc) return h->fail(rc, "umma_conv_bind(" + c.id + "): " + ssnb::thread_error());
+  // bind tcgen05 plans (tensor maps need final addresses); SSNB_DISABLE_UMMA=1 keeps FAST mode on the SIMT kernels
+  const char* dis = getenv("SSNB_DISABLE_UMMA");
+  const bool use_umma = h->fp16 && !(dis && dis[0] == '1');
+  for (Op& o : h->ops) {
+    o.umma.enabled = false; o.umma_dgrad.enabled = false;
+    if (o.kind != OP_CONV || !use_umma) continue;
+    const ConvSpec& c = h->convs[o.conv];
+    if (c.stride != 1 || c.cin % 8 != 0) continue;      // conv1 and the four stride-2 convs stay on the SIMT kernel
+    int rc = umma_conv_bind_fwd(h->umma_ctx, o.umma, h->view(o.in_val, false), h->view(o.out_val, false), h->F, c.cin, c.cout,
+                                c.k, c.pad, (const __half*)(h->ws + h->packed[o.conv].wd), (const float*)(h->ws + h->packed[o.conv].bias));
+    if (rc) return h->fail(rc, "umma_conv_bind_fwd(" + c.id + "): " + ssnb::thread_error());
+    if (h->cfg.training && h->vals[o.in_val].name != "data") {
+      rc = umma_conv_bind_dgrad(h->umma_ctx, o.umma_dgrad, h->view(o.out_val, true), h->view(o.in_val, true), h->F, c.cin, c.cout,
+                                c.k, c.pad, (const __half*)(h->ws + h->packed[o.conv].wf), o.grad_accumulate);
+      if (rc) return h->fail(rc, "umma_conv_bind_dgrad(" + c.id + "): " + ssnb::thread_error());
     }
+  }
   return SSNB_OK;
 }
 
@@ -401,14 +412,6 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                                                (float*)(h->ws + p.wf), (float*)(h->ws + p.wd), (float*)(h->ws + p.bias),
                                                (float*)(h->ws + p.scale), s);
     if (rc) return h->fail(rc, "pack_weights(" + c.id + "): " + ssnb::thread_error());
-  }
-  if (h->fp16) {
-    for (Op& o : h->ops)
-      if (o.kind == OP_CONV && o.umma.enabled) {
-        const ConvSpec& c = h->convs[o.conv];
-        int rc = umma_conv_pack(h->umma_ctx, o.umma, (const __half*)(h->ws + h->packed[o.conv].wf), c.cin, c.cout, c.k, s);
-        if (rc) return h->fail(rc, "umma_conv_pack(" + c.id + "): " + ssnb::thread_error());
-      }
   }
   h->weights_ready = true;
   return SSNB_OK;

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(HL_THREADS) heads_loss_kernel(HeadsArgs a) {
     const int G = c.comp_group, P = c.fg_per_video, Ng = G - P;
     const int ngroups = cnt[1] / G;
     const int keep_neg = c.keep_neg;
-    const float denom = (float)c.comp_denom;
+    const float denom = c.comp_denom;
     for (int g = threadIdx.x; g < ngroups; g += HL_THREADS) {
       float ls = 0.f;
       for (int q = 0; q < P; ++q) {          // positives: ratio 1.0, all kept
@@ -613,7 +613,7 @@ int ssnb_heads_loss_fwd_bwd(const ssnb_heads_cfg* cfg, const float* course_ft, c
                             float* d_act_b, float* d_comp_w, float* d_comp_b, float* d_reg_w, float* d_reg_b, void* workspace,
                             void* stream) {
   if (!cfg || !workspace) { set_thread_error("heads_loss: null cfg/workspace"); return SSNB_EINVAL; }
-  if (cfg->feat_dim % HL_SLICE || cfg->n <= 0 || cfg->comp_group <= cfg->fg_per_video || cfg->comp_group - cfg->fg_per_video > 64 || cfg->comp_denom <= 0) {
+  if (cfg->feat_dim % HL_SLICE || cfg->n <= 0 || cfg->comp_group <= cfg->fg_per_video || cfg->comp_group - cfg->fg_per_video > 64 || !(cfg->comp_denom > 0.f)) {
     set_thread_error("heads_loss: feat_dim must be a multiple of 128; 1..64 negatives per group"); return SSNB_EINVAL; }
   const int slices = (cfg->feat_dim + cfg->feat_dim * cfg->feat_mult) / HL_SLICE;
   if (slices > 148) { set_thread_error("heads_loss: more feature slices than SMs (grid barrier needs co-residency)"); return SSNB_ENOSUPPORT; }

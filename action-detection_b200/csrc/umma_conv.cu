@@ -1,10 +1,308 @@
-// placeholder: tcgen05 path not wired yet (all layers run on the SIMT engine)
+// tcgen05 implicit-GEMM convolution (sm_100a): TMA-staged operand tiles, single-thread UMMA issue,
+// fp32 accumulators in TMEM, warp-specialised persistent CTAs.
+//
+//   warp 0      : TMA producer   (A: 4-D activation box, B: 3-D weight box, SWIZZLE_128B)
+//   warp 1      : TMEM allocator + MMA issuer (tcgen05.mma.cta_group::1.kind::f16, M=128, N=block_n)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> bias/ReLU or accumulate -> fp16 NHWC store)
+//
+// Rows of the M tile are the pixels of one TMA box (bw x bh x bf); taps shift the box origin and
+// rely on TMA's out-of-bounds zero fill for the convolution padding.
+#include <cstdio>
+#include <cstring>
+
 #include "umma_conv.cuh"
+#include "umma_dev.cuh"
+
 namespace ssnb {
-void umma_context_init(UmmaContext& ctx, bool fp16) { ctx.active = false; (void)fp16; }
+
+namespace {
+
+using namespace umma;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KiB
+constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TileCoord { int w0, h0, f0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const UmmaConvParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  t.n0 = nt * p.block_n;
+  t.w0 = (m % p.tiles_w) * p.bw; m /= p.tiles_w;
+  t.h0 = (m % p.tiles_h) * p.bh; m /= p.tiles_h;
+  t.f0 = m * p.bf;
+  return t;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
+  const int ksteps = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, t.n0, tap);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.block_n);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t ad = make_desc_k_sw128(sa + k * UMMA_K * 2);
+            const uint64_t bd = make_desc_k_sw128(sb + k * UMMA_K * 2);
+            umma_f16(d_tmem, ad, bd, idesc, (ks | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                   // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5; TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rf = row / (p.bw * p.bh);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
+      const bool valid = (rf < p.bf) && (w < p.W) && (h < p.H) && (f < p.F);
+      __half* orow = p.out + ((long long)(f * p.H + h) * p.W + w) * p.out_pitch + p.out_coff + t.n0;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + t.n0 + c0 + j);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+          if (p.accumulate) {
+            uint4 o0 = dst[0], o1 = dst[1];
+            const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&o1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+              v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          uint4 q0, q1;
+          __half2* g0 = reinterpret_cast<__half2*>(&q0);
+          __half2* g1 = reinterpret_cast<__half2*>(&q1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { g0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); g1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]); }
+          dst[0] = q0; dst[1] = q1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // 4 arrivals (one per epilogue warp) release it
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int resolve_encode(UmmaContext& ctx) {
+  if (ctx.encode_tiled) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    cudaGetLastError();
+    set_thread_error("cuTensorMapEncodeTiled not available from the driver");
+    return 2;
+  }
+  ctx.encode_tiled = fn;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ctx.num_sms = sms;
+  return 0;
+}
+
+int encode(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, const cuuint64_t* dims, const cuuint64_t* strides,
+           const cuuint32_t* box) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx.encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, addr, dims, strides,
+                                                                box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d)", (int)r, rank);
+    set_thread_error(buf);
+    return 2;
+  }
+  return 0;
+}
+
+void pick_box(int W, int& bw, int& bh, int& bf) {
+  if (W % 8 == 0 && W >= 56) { bw = 8; bh = 8; bf = 2; }
+  else if (W % 4 == 0) { bw = 4; bh = 4; bf = 8; }
+  else if (W % 2 == 0) { bw = 2; bh = 2; bf = 32; }
+  else if (W <= 8) { bw = W; bh = 1; bf = BLOCK_M / W; }
+  else { bw = 1; bh = 1; bf = 128; }
+}
+
+int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int K, int N, int k, const __half* w) {
+  plan.enabled = false;
+  if (int rc = resolve_encode(ctx)) return rc;
+  if (a.H != o.H || a.W != o.W) { set_thread_error("umma conv: stride-1 geometry only"); return 1; }
+  if (K % 8 || N % 16 || a.pitch % 8 || a.coff % 8 || o.pitch % 8 || o.coff % 8 || k * k > UMMA_MAX_TAPS) {
+    set_thread_error("umma conv: unsupported channel alignment"); return 1; }
+  UmmaConvParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.W = a.W; p.H = a.H; p.F = F;
+  pick_box(a.W, p.bw, p.bh, p.bf);
+  p.tiles_w = (a.W + p.bw - 1) / p.bw; p.tiles_h = (a.H + p.bh - 1) / p.bh; p.tiles_f = (F + p.bf - 1) / p.bf;
+  // N split: largest block_n <= 256, multiple of 16, dividing N
+  p.n_tiles = 1;
+  while (N / p.n_tiles > 256 || N % p.n_tiles || (N / p.n_tiles) % 16) { ++p.n_tiles; if (p.n_tiles > 16) { set_thread_error("umma conv: cannot split N"); return 1; } }
+  p.block_n = N / p.n_tiles;
+  p.kchunks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.ntaps = k * k;
+  p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)F};
+    cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
+    if (int rc = encode(ctx, &plan.tmap_a, 4, reinterpret_cast<__half*>(a.base) + a.coff, dims, str, box)) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)(k * k)};
+    cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n, 1};
+    if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(w), dims, str, box)) return rc;
+  }
+  plan.enabled = true;
+  return 0;
+}
+
+}  // namespace
+
+int umma_resolve_encode(UmmaContext& ctx) { return resolve_encode(ctx); }
+int umma_encode_f16(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, const cuuint64_t* dims,
+                    const cuuint64_t* strides, const cuuint32_t* box) {
+  return encode(ctx, m, rank, addr, dims, strides, box);
+}
+
+void umma_context_init(UmmaContext& ctx, bool fp16) { ctx.active = fp16; }
 void umma_context_destroy(UmmaContext&) {}
-void umma_plan_workspace(UmmaContext&, size_t&) {}
-int umma_conv_bind(UmmaContext&, UmmaConvPlan& p, View, View, int, int, int, int, int, int, char*, int, const float*) { p.enabled = false; return 0; }
-int umma_conv_pack(UmmaContext&, UmmaConvPlan&, const __half*, int, int, int, cudaStream_t) { return 0; }
-int umma_conv_forward(UmmaContext&, const UmmaConvPlan&, cudaStream_t) { return 1; }
+
+int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
+                       const __half* w_tap_n_k, const float* bias) {
+  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, k, w_tap_n_k)) return rc;
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = r - pad; plan.p.tap_dx[r * k + s] = s - pad; }
+  plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;
+  return 0;
+}
+
+int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
+                         const __half* w_tap_k_n, int accumulate) {
+  // dx[p, ci] = sum_{r,s,co} dz[p + (pad-r, pad-s), co] * W[co][ci][r][s] : K = cout, N = cin
+  if (int rc = bind_common(ctx, plan, dz, dx, F, cout, cin, k, w_tap_k_n)) return rc;
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = pad - r; plan.p.tap_dx[r * k + s] = pad - s; }
+  plan.p.bias = nullptr; plan.p.relu = 0; plan.p.accumulate = accumulate;
+  return 0;
+}
+
+int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s) {
+  if (!plan.enabled) { set_thread_error("umma conv: plan not bound"); return 3; }
+  if (!ctx.attr_set) {
+    if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      set_thread_error("umma conv: cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
+    ctx.attr_set = true;
+  }
+  const UmmaConvParams& p = plan.p;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
+  const int grid = total < ctx.num_sms ? total : ctx.num_sms;
+  umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_b, p);
+  SSNB_LAUNCH_CHECK("umma_conv_kernel");
+  return 0;
+}
+
 }  // namespace ssnb

@@ -1,38 +1,80 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM convolution for SSNB_FAST_FP16 — interface.
+//
+// One kernel family computes   out[p, n] = epi( sum_taps sum_c  A[p + shift(tap), c] * B[tap][n][c] )
+// over NHWC fp16 tensors: A tiles are 4-D TMA boxes of the activation view (zero-filled outside
+// the image = free padding), B tiles are 3-D TMA boxes of the packed weights, accumulators live
+// in TMEM, the epilogue fuses folded-BN bias + ReLU (forward) or accumulation (data gradient).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#include <cuda.h>
 
 #include "common.cuh"
 
 namespace ssnb {
 
+constexpr int UMMA_MAX_TAPS = 16;
+
 struct UmmaContext {
   bool active = false;
-  void* encode_tiled = nullptr;     // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
-  size_t ws_base = 0, ws_bytes = 0; // region of the engine workspace owned by the tcgen05 path
+  void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
   int num_sms = 148;
+  bool attr_set = false;
+};
+
+struct UmmaConvParams {
+  int W, H, F;                    // spatial dims shared by input and output (stride-1 convolutions)
+  int bw, bh, bf;                 // TMA box in pixels; bw*bh*bf <= 128 rows of the M tile
+  int tiles_w, tiles_h, tiles_f;
+  int n_tiles, block_n;           // N split of Cout
+  int kchunks, ntaps;             // ceil(Cin/64), filter taps
+  int tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
+  __half* out; int out_pitch, out_coff, Cout;
+  const float* bias;              // [Cout] or nullptr
+  int relu, accumulate;
 };
 
 struct UmmaConvPlan {
   bool enabled = false;
   CUtensorMap tmap_a, tmap_b;
-  int F = 0, H = 0, W = 0, Cin = 0, Cout = 0, k = 1, pad = 0;
-  int bw = 0, bh = 0, bf = 0;          // TMA box (pixels) = bw*bh*bf = 128 rows of the M tile
-  int tiles_w = 0, tiles_h = 0, tiles_f = 0, n_tiles = 1, block_n = 0, kchunks = 0;
-  void* out = nullptr; int out_pitch = 0, out_coff = 0;
-  const float* bias = nullptr;
-  size_t wpack_off = 0;                // packed fp16 weights [tap][Cout_pad][Cin_pad]
-  int cin_pad = 0, cout_pad = 0;
+  UmmaConvParams p;
 };
 
 void umma_context_init(UmmaContext& ctx, bool fp16);
 void umma_context_destroy(UmmaContext& ctx);
-void umma_plan_workspace(UmmaContext& ctx, size_t& off);
-int umma_conv_bind(UmmaContext& ctx, UmmaConvPlan& p, View in, View out, int F, int cin, int cout, int k, int stride,
-                   int pad, char* ws, int conv_idx, const float* bias);
-int umma_conv_pack(UmmaContext& ctx, UmmaConvPlan& p, const __half* wf, int cin, int cout, int k, cudaStream_t s);
-int umma_conv_forward(UmmaContext& ctx, const UmmaConvPlan& p, cudaStream_t s);
+// forward convolution plan (stride 1): in/out views, weights wd = [tap][cout][cin] fp16
+int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
+                       const __half* w_tap_n_k, const float* bias);
+// data-gradient plan (stride 1): dz/dx gradient views, weights wf = [tap][cin][cout] fp16
+int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
+                         const __half* w_tap_k_n, int accumulate);
+int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s);
+
+// host helpers shared by the tensor-core kernels
+int umma_resolve_encode(UmmaContext& ctx);
+int umma_encode_f16(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, const cuuint64_t* dims,
+                    const cuuint64_t* strides, const cuuint32_t* box);
+
+// ---- weight gradient on tcgen05 (umma_wgrad.cu) -------------------------------------------------------
+// partial[split][tap][co][ci] = sum over the split's pixels of dz[p, co] * x[p + (r-pad, s-pad), ci]
+// (both operands MN-major: the reduction dimension is the pixel index).
+struct UmmaWgradParams {
+  int W, H, F;
+  int bw, bh, bf;                 // 64-pixel TMA box
+  int tiles_w, tiles_h, tiles_f;
+  int ptiles_per_split, splits;
+  int ntaps, tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
+  int Cout, Cin, m_tiles, n_tiles, block_n;
+  float* partial;
+};
+struct UmmaWgradPlan {
+  bool enabled = false;
+  CUtensorMap tmap_dz, tmap_x;
+  UmmaWgradParams p;
+};
+// returns the number of splits chosen through *splits (the caller sizes `partial` from it)
+int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int k, int pad,
+                    float* partial, int max_splits);
+int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s);
 
 }  // namespace ssnb

@@ -28,7 +28,7 @@ class HeadsCfg(C.Structure):
     _fields_ = [("n", C.c_int32), ("props_per_video", C.c_int32), ("num_class", C.c_int32),
                 ("feat_dim", C.c_int32), ("feat_mult", C.c_int32), ("fg_per_video", C.c_int32),
                 ("comp_group", C.c_int32), ("global_videos", C.c_int32), ("keep_neg", C.c_int32),
-                ("comp_denom", C.c_int32), ("comp_w", C.c_float), ("reg_w", C.c_float),
+                ("comp_denom", C.c_float), ("comp_w", C.c_float), ("reg_w", C.c_float),
                 ("loss_scale", C.c_float)]
 
 

@@ -235,8 +235,9 @@ def heads_loss_fused(course_ft, stpp_ft, act_fc, comp_fc, reg_fc, prop_type, tar
     videos = n // props_per_video
     gv = videos if global_videos is None else global_videos
     neg = comp_group - fg_per_video
+    denom_global = gv * fg_per_video + int(gv * neg * ohem_ratio)
     cfg = _lib.HeadsCfg(n, props_per_video, K, D, feat_mult, fg_per_video, comp_group, gv,
-                        int(neg * ohem_ratio), gv * fg_per_video + int(gv * neg * ohem_ratio), comp_w, reg_w, loss_scale)
+                        int(neg * ohem_ratio), float(denom_global) * videos / gv, comp_w, reg_w, loss_scale)
     f32 = dict(dtype=torch.float32, device=dev)
     out = {"raw_act": torch.empty(n, K + 1, **f32), "raw_comp": torch.empty(n, K, **f32),
            "raw_reg": torch.empty(n, 2 * K, **f32), "losses": torch.empty(4, **f32),

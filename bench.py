@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — SSN forward/backward hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fast|exact]
+  N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): THUMOS14-shape synthetic, per GPU 4 videos x 8 proposals x
+9 segments RGB 224x224 (32 proposals, 288 frames), K=20 classes, STPP (1,(1,2),1), dropout 0,
+frozen BN.  A step = BNInception fwd -> global-pool+STPP -> heads + multi-task loss (+ all
+gradients) -> backbone bwd -> NCCL gradient allreduce (N>1) -> SGD step -> weight re-pack.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "action-detection_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+VIDEOS_PER_GPU, PROPS, SEG, K_CLASSES, STPP_CFG = 4, 8, 9, 20, (1, (1, 2), 1)
+FLOP_PER_FRAME_FWD = 2 * 2031576064
+FLOP_PER_FRAME_FWDBWD = 2 * (2031576064 + 1913562112 + 2031576064)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.stop_flag, self.index = [], False, index
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference(steps, warmup, videos=2):
+    """The reference's CPU PyTorch path for this workload, restated by the oracle (the reference
+    scripts do not parse on py3.12), all host threads, bounded sample."""
+    import torch
+    from oracle import ssn_oracle as O, synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synth.synth_backbone(3, seed=0, calib_frames=2)
+    hd = synth.synth_heads(K_CLASSES, 5, seed=0)
+    for d in (bb, hd):
+        for k in d:
+            if "_bn." not in k:
+                d[k].requires_grad_(True)
+    batch = synth.synth_batch(videos, K_CLASSES, 3, seed=0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        outs = O.ssn_train_forward(bb, hd, *batch, stpp_cfg=STPP_CFG)
+        loss, _ = O.total_loss(outs)
+        loss.backward()
+        for d in (bb, hd):
+            for v in d.values():
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    props = videos * PROPS
+    best = min(times)
+    mean = sum(times) / len(times)
+    return {"value": props / mean, "best": props / best, "ms_per_step": mean * 1e3, "cores": torch.get_num_threads(),
+            "sample": "%d videos = %d proposals x 9 seg fwd+bwd per step, %d steps" % (videos, props, len(times))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(max(1, min(args.steps, 3)), max(0, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": "proposals/sec (9-seg BNInception SSN fwd+bwd)", "value": r["value"],
+            "unit": "proposals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "THUMOS14-shape synthetic: 9-seg RGB 224x224 BNInception SSN fwd+bwd, K=20, STPP (1,(1,2),1)",
+                       "note": "reference CPU PyTorch path (oracle restatement, kind=port), bounded sample"},
+            "cpu_baseline": {"value": r["value"], "unit": "proposals/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-scale", type=float, default=4096.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import ssn_models
+    from ssn_b200 import _lib
+    from oracle import synth          # synthetic weights/inputs generator (test infrastructure, not measured)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    prec = _lib.FAST_FP16 if args.precision == "fast" else _lib.EXACT_FP32
+    torch.manual_seed(0)
+    model = ssn_models.SSN(K_CLASSES, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=STPP_CFG)
+    bb = synth.synth_backbone(3, seed=0, calib_frames=2)
+    sd = model.state_dict()
+    for k, v in bb.items():
+        sd["base_model." + k].copy_(v)
+    model = model.to(dev).train()
+    model.set_precision(prec, args.grad_scale)
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    policies = model.get_optim_policies()
+    groups = [{"params": g["params"], "lr": 1e-5 * g["lr_mult"], "weight_decay": 5e-4 * g["decay_mult"]} for g in policies if g["params"]]
+    opt = torch.optim.SGD(groups, lr=1e-5, momentum=0.9)
+
+    # per-rank shard of the global batch (weak scaling: fixed work per GPU); inputs resident in HBM
+    nb = 2   # distinct device-resident batches, alternated
+    batches = [tuple(t.to(dev) for t in synth.synth_batch(VIDEOS_PER_GPU, K_CLASSES, 3, seed=100 * rank + i)) for i in range(nb)]
+    host_batches = [tuple(t.pin_memory() for t in synth.synth_batch(VIDEOS_PER_GPU, K_CLASSES, 3, seed=100 * rank + i)) for i in range(nb)]
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(batch):
+        flat_grad.zero_()
+        losses = model.fused_step(*batch, global_videos=VIDEOS_PER_GPU * world, loss_scale=1.0 / world)
+        if world > 1:
+            dist.all_reduce(flat_grad)
+        opt.step()
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(batches[i % nb])
+    barrier()
+    launches0 = _lib.lib.ssnb_global_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    with ClockSampler(local) as clocks:
+        for i in range(args.steps):
+            l2_flush.zero_()                      # flush L2 between timed iterations (outside the event pair)
+            ev[2 * i].record()
+            losses = step(batches[i % nb])
+            ev[2 * i + 1].record()
+        barrier()
+    launches = _lib.lib.ssnb_global_launch_count() - launches0
+    ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    props_step = VIDEOS_PER_GPU * PROPS * world
+    value = props_step * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: the reference-facing module calls (ssn_train.py:207-236) with HOST inputs ----------
+    import ops.ssn_ops as R
+    act_crit, comp_crit, reg_crit = torch.nn.CrossEntropyLoss(), R.CompletenessLoss(), R.ClassWiseRegressionLoss()
+
+    def e2e_step(hb):
+        x, sc, tg, rt, pt = (t_.to(dev, non_blocking=True) for t_ in hb)
+        flat_grad.zero_()
+        a, at, c, ct, r, rl, rtt = model(x, sc, tg, rt, pt)
+        loss = act_crit(a, at) + 0.1 * comp_crit(c, ct, 1, 7) + 0.1 * reg_crit(r, rl, rtt)
+        (loss / world).backward()
+        if world > 1:
+            dist.all_reduce(flat_grad)
+        opt.step()
+        return loss.item()                      # device -> host read of the step's result
+
+    e2e_steps = max(3, args.steps // 2)
+    for i in range(3):
+        e2e_step(host_batches[i % nb])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(host_batches[i % nb])
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = props_step * e2e_steps / (t.item() / 1e3)
+    h2d = sum(t_.numel() * t_.element_size() for t_ in host_batches[0])
+
+    # ---- roofline of the dominant kernel: per-op CUDA-event timing of the conv launches -----------
+    peaks, peak_src = measured_peaks()
+    roof = None
+    if rank == 0:
+        eng = model.base_model.engine_for(VIDEOS_PER_GPU * PROPS * SEG, True, dev)
+        table = {n: (ci, co, k, s, p) for (n, ci, co, k, s, p) in __import__("ssn_b200.engine", fromlist=["conv_table"]).conv_table(3)}
+        tot_ms, tot_flop, n_l = 0.0, 0.0, 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i, (kind, iname, oname) in enumerate(eng.ops()):
+            if kind != "conv":
+                continue
+            ci, co, k, s, p = table[oname[:-3]]
+            if s != 1 or ci % 8:
+                continue                           # conv1 / stride-2 layers run on the SIMT kernel
+            _c, hh, ww = eng.value_shape(oname)
+            best = 1e9
+            for _ in range(3):
+                l2_flush.zero_()
+                a.record(); eng.run_op(i, False); b.record(); b.synchronize()
+                best = min(best, a.elapsed_time(b))
+            tot_ms += best
+            tot_flop += 2.0 * eng.frames * hh * ww * co * ci * k * k
+            n_l += 1
+        achieved = tot_flop / (tot_ms / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops", 1590.0)
+        roof = {"bound": "tensor", "kernel": "umma_conv_kernel (forward launches, 64 stride-1 layers)" if prec == _lib.FAST_FP16 else "conv_kernel<float> (SIMT)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src + " bf16 burst (kernel timed alone)", "launches_timed": n_l,
+                "flop_per_launch_avg": tot_flop / n_l, "ms_per_launch_avg": tot_ms / n_l}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(2, 1)
+        cpu = {"value": r["value"], "unit": "proposals/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": "proposals/sec (9-seg BNInception SSN fwd+bwd)", "value": value, "unit": "proposals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate" if prec == _lib.FAST_FP16 else "f32", "data": "synthetic",
+                "config": {"workload": "THUMOS14-shape synthetic: batch 32 proposals x 9 segments RGB 224x224 per GPU, BNInception SSN "
+                                       "fwd+bwd (+allreduce+SGD+repack), K=20, STPP (1,(1,2),1), dropout 0, frozen BN",
+                           "global_batch_proposals": props_step, "frames_per_gpu": VIDEOS_PER_GPU * PROPS * SEG,
+                           "parallelism": "dp%d" % world, "precision": args.precision, "l2": "flushed between timed steps (256 MiB write)",
+                           "grad_scale": args.grad_scale},
+                "clocks": clocks.summary(), "gpu_launches": int(launches),
+                "tflops_step": FLOP_PER_FRAME_FWDBWD * VIDEOS_PER_GPU * PROPS * SEG / (ms_total / args.steps / 1e3) / 1e12,
+                "losses": [float(v) for v in losses.tolist()],
+                "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                        "steps": e2e_steps, "path": "SSN.forward + CrossEntropy/CompletenessLoss/ClassWiseRegressionLoss + backward from pinned host tensors"},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -136,7 +136,9 @@ typedef struct {
   int32_t comp_group;    /* fg + incomplete per video (ssn_train.py:190) */
   int32_t global_videos; /* videos in the GLOBAL batch: completeness denominator */
   int32_t keep_neg;      /* int((comp_group - fg_per_video) * ohem_ratio), host-computed (ops/ssn_ops.py:191) */
-  int32_t comp_denom;    /* pos_cnt + int(neg_cnt * ohem_ratio) over the GLOBAL batch (ops/ssn_ops.py:236-239) */
+  float comp_denom;      /* (pos_cnt + int(neg_cnt * ohem_ratio)) of the GLOBAL batch (ops/ssn_ops.py:236-239)
+                            divided by the number of data-parallel ranks, so that rank-averaged losses and
+                            gradients equal the global-batch ones */
   float comp_w, reg_w;   /* 0.1, 0.1 (ssn_opts.py:35-37) */
   float loss_scale;      /* multiplies every gradient (1/world_size for data parallel) */
 } ssnb_heads_cfg;
