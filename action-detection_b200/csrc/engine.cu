@@ -64,6 +64,7 @@ struct Op {
   int wsplits = 1, wrows = 0;
   UmmaConvPlan umma;        // tcgen05 forward plan (FAST mode, stride-1 layers)
   UmmaConvPlan umma_dgrad;  // tcgen05 data-gradient plan
+  UmmaWgradPlan umma_wgrad; // tcgen05 weight-gradient plan
 };
 struct PackedConv { size_t wf, wd, bias, scale; };
 
@@ -296,7 +297,10 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
                   launch_bias_grad<__half>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, e->db[o.conv], s));
     if (rc) return rc;
   }
-  if (e->dw.size() && e->dw[o.conv]) {
+  if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
+    if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s))) return rc;
+    if ((rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s))) return rc;
+  } else if (e->dw.size() && e->dw[o.conv]) {
     WgradArgs w;
     w.dz = dy.base; w.OH = y.H; w.OW = y.W; w.Cout = y.C; w.dz_pitch = dy.pitch; w.dz_coff = dy.coff;
     w.x = x.base; w.IH = x.H; w.IW = x.W; w.Cin = x.C; w.x_pitch = x.pitch; w.x_coff = x.coff;
@@ -382,7 +386,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
   const char* dis = getenv("SSNB_DISABLE_UMMA");
   const bool use_umma = h->fp16 && !(dis && dis[0] == '1');
   for (Op& o : h->ops) {
-    o.umma.enabled = false; o.umma_dgrad.enabled = false;
+    o.umma.enabled = false; o.umma_dgrad.enabled = false; o.umma_wgrad.enabled = false;
     if (o.kind != OP_CONV || !use_umma) continue;
     const ConvSpec& c = h->convs[o.conv];
     if (c.stride != 1 || c.cin % 8 != 0) continue;      // conv1 and the four stride-2 convs stay on the SIMT kernel
@@ -393,6 +397,12 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       rc = umma_conv_bind_dgrad(h->umma_ctx, o.umma_dgrad, h->view(o.out_val, true), h->view(o.in_val, true), h->F, c.cin, c.cout,
                                 c.k, c.pad, (const __half*)(h->ws + h->packed[o.conv].wf), o.grad_accumulate);
       if (rc) return h->fail(rc, "umma_conv_bind_dgrad(" + c.id + "): " + ssnb::thread_error());
+    }
+    const char* disw = getenv("SSNB_DISABLE_UMMA_WGRAD");
+    if (h->cfg.training && !(disw && disw[0] == '1')) {
+      rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), h->view(o.in_val, false), h->F, c.cin, c.cout,
+                           c.k, c.pad, (float*)(h->ws + h->partial_off), o.wsplits);
+      if (rc) return h->fail(rc, "umma_wgrad_bind(" + c.id + "): " + ssnb::thread_error());
     }
   }
   return SSNB_OK;

@@ -136,7 +136,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && t.n0 + c0 < p.Cout) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -237,10 +237,10 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.W = a.W; p.H = a.H; p.F = F;
   pick_box(a.W, p.bw, p.bh, p.bf);
   p.tiles_w = (a.W + p.bw - 1) / p.bw; p.tiles_h = (a.H + p.bh - 1) / p.bh; p.tiles_f = (F + p.bf - 1) / p.bf;
-  // N split: largest block_n <= 256, multiple of 16, dividing N
-  p.n_tiles = 1;
-  while (N / p.n_tiles > 256 || N % p.n_tiles || (N / p.n_tiles) % 16) { ++p.n_tiles; if (p.n_tiles > 16) { set_thread_error("umma conv: cannot split N"); return 1; } }
-  p.block_n = N / p.n_tiles;
+  // N split: equal tiles of block_n <= 256 (multiple of 16); the last tile may overhang N (TMA zero-fills the
+  // missing weight rows, the epilogue masks the columns)
+  p.n_tiles = (N + 255) / 256;
+  p.block_n = (((N + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
   p.kchunks = (K + BLOCK_K - 1) / BLOCK_K;
   p.ntaps = k * k;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;

@@ -1,0 +1,202 @@
+// tcgen05 weight-gradient kernel (sm_100a).  dW[tap][co][ci] = sum_p dz[p, co] * x[p + shift(tap), ci]
+// is a GEMM whose reduction runs over pixels, so both operands are MN-major in shared memory:
+// a TMA box is [64 pixels][64 channels] (128-byte rows, SWIZZLE_128B) and the UMMA descriptors walk
+// it with 8-pixel groups every 1024 B (SBO) and 64-channel atoms every 8 KiB (LBO).
+//
+//   CTA = (co tile of 128, ci tile of block_n <= 256, tap, pixel split); K loop over 64-pixel boxes.
+//   warp 0: TMA producer, warp 1: MMA issuer (M=128, N=block_n, fp32 TMEM accumulator),
+//   warps 2..5: epilogue -> split-K partials (reduced in fixed order by wgrad_finalize_kernel).
+#include <cstdio>
+#include <cstring>
+
+#include "umma_conv.cuh"
+#include "umma_dev.cuh"
+
+namespace ssnb {
+namespace {
+
+using namespace umma;
+constexpr int STAGES = 4;
+constexpr int BOX_BYTES = 64 * 128;                 // [64 px][64 ch] fp16
+constexpr int A_BYTES = 2 * BOX_BYTES;              // 128 output channels
+constexpr int STAGE_BYTES = A_BYTES + 4 * BOX_BYTES;  // + up to 256 input channels
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
+                  const UmmaWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  int id = blockIdx.x;
+  const int tap = id % p.ntaps; id /= p.ntaps;
+  const int nt = id % p.n_tiles; id /= p.n_tiles;
+  const int mt = id;
+  const int split = blockIdx.y;
+  const int m0 = mt * BLOCK_M, n0 = nt * p.block_n;
+  const int ptiles = p.tiles_w * p.tiles_h * p.tiles_f;
+  const int pt0 = split * p.ptiles_per_split;
+  const int pt1 = min(pt0 + p.ptiles_per_split, ptiles);
+  const int nboxes_b = p.block_n / 64;
+  const uint32_t tmem_cols = p.block_n <= 64 ? 64 : (p.block_n <= 128 ? 128 : 256);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dz)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(2 + nboxes_b) * BOX_BYTES;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        int q = pt;
+        const int w0 = (q % p.tiles_w) * p.bw; q /= p.tiles_w;
+        const int h0 = (q % p.tiles_h) * p.bh; q /= p.tiles_h;
+        const int f0 = q * p.bf;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(&full_bar[stage], tx_bytes);
+        tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, h0, f0);
+        tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, h0, f0);
+        for (int b = 0; b < nboxes_b; ++b)
+          tma_load_4d(sb + b * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], f0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16_mn(p.block_n);
+      uint32_t stage = 0, phase = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 64 / UMMA_K; ++k) {      // 16 pixel rows (2 groups of 8) per instruction
+          const uint64_t ad = make_desc_mn_sw128(sa + k * UMMA_K * 128, BOX_BYTES);
+          const uint64_t bd = make_desc_mn_sw128(sb + k * UMMA_K * 128, BOX_BYTES);
+          umma_f16(tmem_base, ad, bd, idesc, (pt > pt0 || k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = m0 + quad * 32 + lane;            // output channel of this thread's accumulator row
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* orow = p.partial + (((long long)split * p.ntaps + tap) * p.Cout + m) * p.Cin + n0;
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c0, r);
+      tmem_ld_wait();
+      if (m < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (n0 + c0 + j < p.Cin)      // Cin is a multiple of 4
+            *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int k, int pad,
+                    float* partial, int max_splits) {
+  plan.enabled = false;
+  if (int rc = umma_resolve_encode(ctx)) return rc;
+  if (dz.H != x.H || dz.W != x.W) { set_thread_error("umma wgrad: stride-1 geometry only"); return 1; }
+  if (cin % 8 || cout % 8 || dz.pitch % 8 || dz.coff % 8 || x.pitch % 8 || x.coff % 8 || k * k > UMMA_MAX_TAPS) {
+    set_thread_error("umma wgrad: unsupported channel alignment"); return 1; }
+  UmmaWgradParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.W = x.W; p.H = x.H; p.F = F;
+  // 64-pixel boxes whose rows are all real-or-zero-filled pixels (the pixel index is the reduction dim)
+  if (x.W % 8 == 0) { p.bw = 8; p.bh = 8; p.bf = 1; }
+  else if (x.W % 4 == 0) { p.bw = 4; p.bh = 4; p.bf = 4; }
+  else if (x.W % 2 == 0) { p.bw = 2; p.bh = 2; p.bf = 16; }
+  else { p.bw = 1; p.bh = 1; p.bf = 64; }
+  p.tiles_w = (x.W + p.bw - 1) / p.bw; p.tiles_h = (x.H + p.bh - 1) / p.bh; p.tiles_f = (F + p.bf - 1) / p.bf;
+  p.ntaps = k * k;
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s) { p.tap_dy[r * k + s] = r - pad; p.tap_dx[r * k + s] = s - pad; }
+  p.Cout = cout; p.Cin = cin;
+  p.m_tiles = (cout + BLOCK_M - 1) / BLOCK_M;
+  const int chunks = (cin + 63) / 64;
+  p.n_tiles = (chunks + 3) / 4;
+  p.block_n = ((chunks + p.n_tiles - 1) / p.n_tiles) * 64;
+  const int ptiles = p.tiles_w * p.tiles_h * p.tiles_f;
+  const int ctas = p.m_tiles * p.n_tiles * p.ntaps;
+  int splits = (2 * ctx.num_sms + ctas - 1) / ctas;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > ptiles) splits = ptiles;
+  if (splits < 1) splits = 1;
+  p.ptiles_per_split = (ptiles + splits - 1) / splits;
+  p.splits = (ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+  p.partial = partial;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)dz.W, (cuuint64_t)dz.H, (cuuint64_t)F};
+    cuuint64_t str[3] = {(cuuint64_t)dz.pitch * 2, (cuuint64_t)dz.W * dz.pitch * 2, (cuuint64_t)dz.H * dz.W * dz.pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
+    if (int rc = umma_encode_f16(ctx, &plan.tmap_dz, 4, reinterpret_cast<__half*>(dz.base) + dz.coff, dims, str, box)) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)x.W, (cuuint64_t)x.H, (cuuint64_t)F};
+    cuuint64_t str[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.W * x.pitch * 2, (cuuint64_t)x.H * x.W * x.pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
+    if (int rc = umma_encode_f16(ctx, &plan.tmap_x, 4, reinterpret_cast<__half*>(x.base) + x.coff, dims, str, box)) return rc;
+  }
+  plan.enabled = true;
+  return 0;
+}
+
+int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s) {
+  if (!plan.enabled) { set_thread_error("umma wgrad: plan not bound"); return 3; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      set_thread_error("umma wgrad: cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
+    attr_set = true;
+  }
+  const UmmaWgradParams& p = plan.p;
+  dim3 grid((unsigned)(p.m_tiles * p.n_tiles * p.ntaps), (unsigned)p.splits);
+  umma_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_dz, plan.tmap_x, p);
+  SSNB_LAUNCH_CHECK("umma_wgrad_kernel");
+  return 0;
+}
+
+}  // namespace ssnb

@@ -32,6 +32,12 @@ def main():
         return e
 
     simt, umma = make(True), make(False)
+    grads = {}
+    for e in (simt, umma):
+        dw = [torch.zeros(bb[n + ".weight"].shape, device=dev) for n in names]
+        db = [torch.zeros(bb[n + ".bias"].shape, device=dev) for n in names]
+        e.bind_grads(dw, db)
+        grads[id(e)] = (dw, db)
     g = torch.Generator().manual_seed(1)
     bad = 0
     for i, (kind, iname, oname) in enumerate(umma.ops()):
@@ -66,7 +72,6 @@ def main():
         gy = torch.randn(Fn, co_, ho, wo, generator=g).to(dev) * 0.01
         y = torch.rand(Fn, co_, ho, wo, generator=g).to(dev)
         for e in (simt, umma):
-            e.bind_grads([None] * 69, [None] * 69)
             e.write(oname, y)
             e.write(oname, gy, grad=True)
             e.write(iname, torch.zeros(Fn, c, h, w, device=dev), grad=True)
@@ -81,6 +86,17 @@ def main():
         print("%s dgrad %-34s rel %.3e" % (tag, oname, r))
         if r >= 2e-3:
             bad += 1
+        ci_ = names.index(oname[:-3])
+        a, b = grads[id(umma)][0][ci_], grads[id(simt)][0][ci_]
+        r = rel(a, b)
+        tag = "ok " if r < 2e-3 else "BAD"
+        print("%s wgrad %-34s rel %.3e  |ref| %.3e |got| %.3e" % (tag, oname, r, float(b.abs().mean()), float(a.abs().mean())))
+        if r >= 2e-3:
+            bad += 1
+            d = (a - b).abs()
+            print("    err by tap:", [round(float(d[:, :, t // k, t % k].mean() / (b.abs().mean() + 1e-30)), 3) for t in range(k * k)])
+            print("    err by co/16:", [round(float(d[j:j + 16].mean() / (b.abs().mean() + 1e-30)), 3) for j in range(0, co, 16)][:24])
+            print("    err by ci/16:", [round(float(d[:, j:j + 16].mean() / (b.abs().mean() + 1e-30)), 3) for j in range(0, ci, 16)][:40])
     print("umma_diag: %d mismatching launches" % bad)
 
 
