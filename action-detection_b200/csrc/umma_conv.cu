@@ -75,7 +75,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+      // bytes the two TMA boxes deliver (zero-filled out-of-bounds elements count; a 7x1x18 box has 126 rows)
+      const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bf + p.block_n) * BLOCK_K * 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         for (int tap = 0; tap < p.ntaps; ++tap) {
