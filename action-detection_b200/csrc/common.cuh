@@ -80,4 +80,11 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
                      const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
                      cudaStream_t s);
 
+// FAST-mode layout helpers (s2d_glue.cu)
+int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
+int launch_pack_conv1_s2d(const __half* wd, int Cout, int Cin, int Cs, __half* ws, cudaStream_t s);
+int launch_wgrad_finalize_s2d(const float* partial, int splits, int Cout, int Cin, int Cs, const float* mult, float out_scale,
+                              float* dw_ref, cudaStream_t s);
+int launch_upsample2_zero(View src, __half* dst, int H, int W, int F, cudaStream_t s);
+
 }  // namespace ssnb

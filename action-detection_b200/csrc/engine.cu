@@ -4,6 +4,7 @@
 // bn_inception.yaml) and the autograd graph PyTorch builds from it.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -84,6 +85,8 @@ struct ssnb_engine {
   std::vector<Op> ops;
   std::vector<PackedConv> packed;
   size_t ws_bytes = 0, partial_off = 0, partial_bytes = 0, bpartial_off = 0;
+  size_t s2d_off = 0, s2d_w_off = 0, up_off = 0;   // FAST mode: space-to-depth input + weights, zero-upsampled dz
+  int Cs = 0;                                        // channels of the space-to-depth input (4*Cin rounded up to 8)
   char* ws = nullptr;
   bool weights_ready = false;
   std::vector<float*> dw, db;
@@ -223,6 +226,21 @@ static void plan(ssnb_engine* e) {
       }
     }
   }
+  if (e->fp16) {
+    e->Cs = (4 * e->cfg.in_channels + 7) / 8 * 8;
+    e->s2d_off = off; off = align_up(off + F * 112 * 112 * e->Cs * 2, 1024);
+    e->s2d_w_off = off; off = align_up(off + (size_t)16 * 64 * e->Cs * 2, 1024);
+    if (e->cfg.training) {
+      size_t up = 0;
+      for (const Op& o : e->ops)
+        if (o.kind == OP_CONV && o.stride == 2 && o.conv != 0) {
+          const Buffer& ib = e->bufs[e->vals[o.in_val].buf];
+          up = std::max(up, F * ib.H * ib.W * (size_t)e->convs[o.conv].cout * 2);
+        }
+      e->up_off = off; off = align_up(off + up, 1024);
+      pmax = std::max(pmax, (size_t)128 * 16 * 64 * e->Cs * 4);
+    }
+  }
   e->partial_off = off; e->partial_bytes = pmax; off = align_up(off + pmax, 1024);
   e->bpartial_off = off; off = align_up(off + 64 * 512 * 4, 1024);
   e->ws_bytes = off;
@@ -236,7 +254,11 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
   if (o.kind == OP_CONV) {
     const ConvSpec& c = e->convs[o.conv];
     const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
-    if (e->fp16 && o.umma.enabled) return umma_conv_launch(e->umma_ctx, o.umma, s);
+    if (e->fp16 && o.umma.enabled) {
+      if (o.conv == 0)   // conv1 runs as a 4x4 stride-1 convolution over the space-to-depth input
+        if (int rc = launch_nhwc_to_s2d(in, F, (__half*)(e->ws + e->s2d_off), e->Cs, s)) return rc;
+      return umma_conv_launch(e->umma_ctx, o.umma, s);
+    }
     ConvArgs a;
     a.src = in.base; a.SH = in.H; a.SW = in.W; a.Csrc = in.C; a.src_pitch = in.pitch; a.src_coff = in.coff;
     a.dst = out.base; a.DH = out.H; a.DW = out.W; a.Cdst = out.C; a.dst_pitch = out.pitch; a.dst_coff = out.coff;
@@ -297,9 +319,13 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
                   launch_bias_grad<__half>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, e->db[o.conv], s));
     if (rc) return rc;
   }
+  if (e->fp16 && c.stride == 2 && o.conv != 0 && (o.umma_wgrad.enabled || o.umma_dgrad.enabled))
+    if ((rc = launch_upsample2_zero(dy, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;   // dz at input resolution
   if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
     if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s))) return rc;
-    if ((rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s))) return rc;
+    if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], s);
+    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s);
+    if (rc) return rc;
   } else if (e->dw.size() && e->dw[o.conv]) {
     WgradArgs w;
     w.dz = dy.base; w.OH = y.H; w.OW = y.W; w.Cout = y.C; w.dz_pitch = dy.pitch; w.dz_coff = dy.coff;
@@ -389,19 +415,38 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     o.umma.enabled = false; o.umma_dgrad.enabled = false; o.umma_wgrad.enabled = false;
     if (o.kind != OP_CONV || !use_umma) continue;
     const ConvSpec& c = h->convs[o.conv];
-    if (c.stride != 1 || c.cin % 8 != 0) continue;      // conv1 and the four stride-2 convs stay on the SIMT kernel
-    int rc = umma_conv_bind_fwd(h->umma_ctx, o.umma, h->view(o.in_val, false), h->view(o.out_val, false), h->F, c.cin, c.cout,
-                                c.k, c.pad, (const __half*)(h->ws + h->packed[o.conv].wd), (const float*)(h->ws + h->packed[o.conv].bias));
-    if (rc) return h->fail(rc, "umma_conv_bind_fwd(" + c.id + "): " + ssnb::thread_error());
-    if (h->cfg.training && h->vals[o.in_val].name != "data") {
-      rc = umma_conv_bind_dgrad(h->umma_ctx, o.umma_dgrad, h->view(o.out_val, true), h->view(o.in_val, true), h->F, c.cin, c.cout,
-                                c.k, c.pad, (const __half*)(h->ws + h->packed[o.conv].wf), o.grad_accumulate);
-      if (rc) return h->fail(rc, "umma_conv_bind_dgrad(" + c.id + "): " + ssnb::thread_error());
-    }
     const char* disw = getenv("SSNB_DISABLE_UMMA_WGRAD");
-    if (h->cfg.training && !(disw && disw[0] == '1')) {
-      rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), h->view(o.in_val, false), h->F, c.cin, c.cout,
-                           c.k, c.pad, (float*)(h->ws + h->partial_off), o.wsplits);
+    const bool use_wgrad = h->cfg.training && !(disw && disw[0] == '1');
+    const View in = h->view(o.in_val, false), out = h->view(o.out_val, false);
+    int rc = 0;
+    if (o.conv == 0) {
+      // conv1 7x7/2: 4x4 stride-1 convolution over the space-to-depth input (r = 2*dr + a - 1)
+      View xs; xs.base = h->ws + h->s2d_off; xs.H = 112; xs.W = 112; xs.C = h->Cs; xs.pitch = h->Cs; xs.coff = 0;
+      int dy[16], dx[16];
+      for (int t = 0; t < 16; ++t) { dy[t] = t / 4 - 2; dx[t] = t % 4 - 2; }
+      rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, out, h->F, h->Cs, c.cout, 16, dy, dx, (const __half*)(h->ws + h->s2d_w_off),
+                               (const float*)(h->ws + h->packed[0].bias), 1);
+      if (rc) { o.umma.enabled = false; continue; }     // stays on the SIMT kernel
+      if (use_wgrad) {
+        rc = umma_wgrad_bind_taps(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), xs, h->F, h->Cs, c.cout, 16, dy, dx,
+                                  (float*)(h->ws + h->partial_off), 128);
+        if (rc) o.umma_wgrad.enabled = false;
+      }
+      continue;
+    }
+    if (c.cin % 8 != 0 || c.k * c.k > UMMA_MAX_TAPS) continue;
+    rc = umma_conv_bind_fwd(h->umma_ctx, o.umma, in, out, h->F, c.cin, c.cout, c.k, c.pad, c.stride,
+                            (const __half*)(h->ws + h->packed[o.conv].wd), (const float*)(h->ws + h->packed[o.conv].bias));
+    if (rc) return h->fail(rc, "umma_conv_bind_fwd(" + c.id + "): " + ssnb::thread_error());
+    if (!h->cfg.training) continue;
+    // backward operands: the output gradient (stride-2 layers: its zero-upsampled copy at input resolution)
+    View dz = h->view(o.out_val, true);
+    if (c.stride == 2) { dz.base = h->ws + h->up_off; dz.H = in.H; dz.W = in.W; dz.C = c.cout; dz.pitch = c.cout; dz.coff = 0; }
+    rc = umma_conv_bind_dgrad(h->umma_ctx, o.umma_dgrad, dz, h->view(o.in_val, true), h->F, c.cin, c.cout, c.k, c.pad,
+                              (const __half*)(h->ws + h->packed[o.conv].wf), o.grad_accumulate);
+    if (rc) return h->fail(rc, "umma_conv_bind_dgrad(" + c.id + "): " + ssnb::thread_error());
+    if (use_wgrad) {
+      rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, dz, in, h->F, c.cin, c.cout, c.k, c.pad, (float*)(h->ws + h->partial_off), o.wsplits);
       if (rc) return h->fail(rc, "umma_wgrad_bind(" + c.id + "): " + ssnb::thread_error());
     }
   }
@@ -422,6 +467,11 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                                                (float*)(h->ws + p.wf), (float*)(h->ws + p.wd), (float*)(h->ws + p.bias),
                                                (float*)(h->ws + p.scale), s);
     if (rc) return h->fail(rc, "pack_weights(" + c.id + "): " + ssnb::thread_error());
+  }
+  if (h->fp16 && h->ops.size() && h->ops[0].umma.enabled) {
+    int rc = launch_pack_conv1_s2d((const __half*)(h->ws + h->packed[0].wd), h->convs[0].cout, h->convs[0].cin, h->Cs,
+                                   (__half*)(h->ws + h->s2d_w_off), s);
+    if (rc) return h->fail(rc, "pack conv1 s2d: " + ssnb::thread_error());
   }
   h->weights_ready = true;
   return SSNB_OK;

@@ -1,0 +1,105 @@
+// FAST-mode helpers that let every convolution of BNInception run on the stride-1 tcgen05 kernels:
+//  * conv1 (7x7 stride 2 pad 3, bn_inception.yaml:3-5) as a 4x4 stride-1 convolution over the
+//    space-to-depth input  xs[f, i, j, (a*2+b)*Cin + c] = x[f, 2i+a, 2j+b, c]   (r = 2*dr + a - 1)
+//  * stride-2 3x3 layers (inception_3c/4e): backward through a zero-upsampled output gradient.
+#include "common.cuh"
+
+namespace ssnb {
+namespace {
+
+__global__ void nhwc_to_s2d_kernel(const __half* __restrict__ src, int F, int H, int W, int Cin, int spitch, int scoff,
+                                   __half* __restrict__ dst, int Cs) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)F * H2 * W2 * Cs;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % Cs);
+  const long long p = i / Cs;
+  const int x2 = (int)(p % W2), y2 = (int)((p / W2) % H2);
+  const long long f = p / ((long long)W2 * H2);
+  __half v = __float2half_rn(0.f);
+  if (ch < 4 * Cin) {
+    const int ab = ch / Cin, c = ch % Cin;
+    const int a = ab / 2, b = ab % 2;
+    v = src[((f * H + 2 * y2 + a) * W + 2 * x2 + b) * spitch + scoff + c];
+  }
+  dst[i] = v;
+}
+
+// ws[(dr*4+ds)][co][(a*2+b)*Cin + c] = wd[(r*7+s)][co][c],  r = 2*dr+a-1, s = 2*ds+b-1 (0 outside 0..6)
+__global__ void pack_conv1_s2d_kernel(const __half* __restrict__ wd, int Cout, int Cin, int Cs, __half* __restrict__ ws) {
+  const long long total = (long long)16 * Cout * Cs;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % Cs);
+  const int co = (int)((i / Cs) % Cout);
+  const int tap = (int)(i / ((long long)Cs * Cout));
+  const int dr = tap / 4, ds = tap % 4;
+  __half v = __float2half_rn(0.f);
+  if (ch < 4 * Cin) {
+    const int ab = ch / Cin, c = ch % Cin;
+    const int r = 2 * dr + ab / 2 - 1, s = 2 * ds + ab % 2 - 1;
+    if (r >= 0 && r < 7 && s >= 0 && s < 7) v = wd[((long long)(r * 7 + s) * Cout + co) * Cin + c];
+  }
+  ws[i] = v;
+}
+
+// dw_ref[co][c][r][s] = mult[co]*out_scale * sum_splits partial[sp][tap(dr,ds)][co][(a*2+b)*Cin + c]
+__global__ void wgrad_finalize_s2d_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int Cs,
+                                          const float* __restrict__ mult, float out_scale, float* __restrict__ dw) {
+  const long long total = (long long)Cout * Cin * 49;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int s = (int)(i % 7), r = (int)((i / 7) % 7);
+  const int c = (int)((i / 49) % Cin), co = (int)(i / (49LL * Cin));
+  const int dr = (r + 1) / 2, a = (r + 1) % 2, ds = (s + 1) / 2, b = (s + 1) % 2;
+  const int tap = dr * 4 + ds, ch = (a * 2 + b) * Cin + c;
+  float acc = 0.f;
+  for (int sp = 0; sp < splits; ++sp) acc += partial[(((long long)sp * 16 + tap) * Cout + co) * Cs + ch];
+  dw[i] = acc * mult[co] * out_scale;
+}
+
+// dst[f, y, x, c] = (y, x both even) ? src[f, y/2, x/2, c] : 0
+__global__ void upsample2_zero_kernel(const __half* __restrict__ src, int OH, int OW, int C, int spitch, int scoff,
+                                      __half* __restrict__ dst, int H, int W, int F) {
+  const long long total = (long long)F * H * W * C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long p = i / C;
+  const int x = (int)(p % W), y = (int)((p / W) % H);
+  const long long f = p / ((long long)W * H);
+  __half v = __float2half_rn(0.f);
+  if (!(x & 1) && !(y & 1) && y / 2 < OH && x / 2 < OW) v = src[((f * OH + y / 2) * OW + x / 2) * spitch + scoff + c];
+  dst[i] = v;
+}
+
+}  // namespace
+
+int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s) {
+  const long long n = (long long)F * (src.H / 2) * (src.W / 2) * Cs;
+  nhwc_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __half*)src.base, F, src.H, src.W, src.C, src.pitch, src.coff, dst, Cs);
+  SSNB_LAUNCH_CHECK("nhwc_to_s2d_kernel");
+  return 0;
+}
+int launch_pack_conv1_s2d(const __half* wd, int Cout, int Cin, int Cs, __half* ws, cudaStream_t s) {
+  const long long n = 16LL * Cout * Cs;
+  pack_conv1_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wd, Cout, Cin, Cs, ws);
+  SSNB_LAUNCH_CHECK("pack_conv1_s2d_kernel");
+  return 0;
+}
+int launch_wgrad_finalize_s2d(const float* partial, int splits, int Cout, int Cin, int Cs, const float* mult, float out_scale,
+                              float* dw_ref, cudaStream_t s) {
+  const long long n = (long long)Cout * Cin * 49;
+  wgrad_finalize_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(partial, splits, Cout, Cin, Cs, mult, out_scale, dw_ref);
+  SSNB_LAUNCH_CHECK("wgrad_finalize_s2d_kernel");
+  return 0;
+}
+int launch_upsample2_zero(View src, __half* dst, int H, int W, int F, cudaStream_t s) {
+  const long long n = (long long)F * H * W * src.C;
+  upsample2_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __half*)src.base, src.H, src.W, src.C, src.pitch, src.coff, dst, H, W, F);
+  SSNB_LAUNCH_CHECK("upsample2_zero_kernel");
+  return 0;
+}
+
+}  // namespace ssnb

@@ -128,8 +128,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
-      const bool valid = (rf < p.bf) && (w < p.W) && (h < p.H) && (f < p.F);
-      __half* orow = p.out + ((long long)(f * p.H + h) * p.W + w) * p.out_pitch + p.out_coff + t.n0;
+      const int os = p.out_stride;
+      const bool valid = (rf < p.bf) && (w < p.W) && (h < p.H) && (f < p.F) && (w % os == 0) && (h % os == 0);
+      __half* orow = p.out + ((long long)(f * p.OH + h / os) * p.OW + w / os) * p.out_pitch + p.out_coff + t.n0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -227,11 +228,11 @@ void pick_box(int W, int& bw, int& bh, int& bf) {
   else { bw = 1; bh = 1; bf = 128; }
 }
 
-int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int K, int N, int k, const __half* w) {
+int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int K, int N, int ntaps, int out_stride, const __half* w) {
   plan.enabled = false;
   if (int rc = resolve_encode(ctx)) return rc;
-  if (a.H != o.H || a.W != o.W) { set_thread_error("umma conv: stride-1 geometry only"); return 1; }
-  if (K % 8 || N % 16 || a.pitch % 8 || a.coff % 8 || o.pitch % 8 || o.coff % 8 || k * k > UMMA_MAX_TAPS) {
+  if ((a.H + out_stride - 1) / out_stride != o.H || (a.W + out_stride - 1) / out_stride != o.W) { set_thread_error("umma conv: geometry mismatch"); return 1; }
+  if (K % 8 || N % 16 || a.pitch % 8 || a.coff % 8 || o.pitch % 8 || o.coff % 8 || ntaps > UMMA_MAX_TAPS) {
     set_thread_error("umma conv: unsupported channel alignment"); return 1; }
   UmmaConvParams& p = plan.p;
   memset(&p, 0, sizeof(p));
@@ -243,8 +244,9 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.n_tiles = (N + 255) / 256;
   p.block_n = (((N + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
   p.kchunks = (K + BLOCK_K - 1) / BLOCK_K;
-  p.ntaps = k * k;
+  p.ntaps = ntaps;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
+  p.out_stride = out_stride; p.OH = o.H; p.OW = o.W;
   {
     cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)F};
     cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2};
@@ -252,7 +254,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
     if (int rc = encode(ctx, &plan.tmap_a, 4, reinterpret_cast<__half*>(a.base) + a.coff, dims, str, box)) return rc;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)(k * k)};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)ntaps};
     cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
     cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n, 1};
     if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(w), dims, str, box)) return rc;
@@ -272,9 +274,18 @@ int umma_encode_f16(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, cons
 void umma_context_init(UmmaContext& ctx, bool fp16) { ctx.active = fp16; }
 void umma_context_destroy(UmmaContext&) {}
 
+int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int ntaps,
+                        const int* dy, const int* dx, const __half* w_tap_n_k, const float* bias, int relu) {
+  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, ntaps, 1, w_tap_n_k)) return rc;
+  for (int t = 0; t < ntaps; ++t) { plan.p.tap_dy[t] = dy[t]; plan.p.tap_dx[t] = dx[t]; }
+  plan.p.bias = bias; plan.p.relu = relu; plan.p.accumulate = 0;
+  return 0;
+}
+
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
-                       const __half* w_tap_n_k, const float* bias) {
-  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, k, w_tap_n_k)) return rc;
+                       int stride, const __half* w_tap_n_k, const float* bias) {
+  // a stride-2 layer (k=3, pad=1) is the stride-1 convolution sampled at even pixels
+  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, k * k, stride, w_tap_n_k)) return rc;
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = r - pad; plan.p.tap_dx[r * k + s] = s - pad; }
   plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;
@@ -284,7 +295,7 @@ int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, 
 int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
                          const __half* w_tap_k_n, int accumulate) {
   // dx[p, ci] = sum_{r,s,co} dz[p + (pad-r, pad-s), co] * W[co][ci][r][s] : K = cout, N = cin
-  if (int rc = bind_common(ctx, plan, dz, dx, F, cout, cin, k, w_tap_k_n)) return rc;
+  if (int rc = bind_common(ctx, plan, dz, dx, F, cout, cin, k * k, 1, w_tap_k_n)) return rc;
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = pad - r; plan.p.tap_dx[r * k + s] = pad - s; }
   plan.p.bias = nullptr; plan.p.relu = 0; plan.p.accumulate = accumulate;

@@ -30,6 +30,7 @@ struct UmmaConvParams {
   int kchunks, ntaps;             // ceil(Cin/64), filter taps
   int tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   __half* out; int out_pitch, out_coff, Cout;
+  int out_stride, OH, OW;         // stride-2 layers: tiles run at input resolution, only even pixels are stored
   const float* bias;              // [Cout] or nullptr
   int relu, accumulate;
 };
@@ -44,7 +45,10 @@ void umma_context_init(UmmaContext& ctx, bool fp16);
 void umma_context_destroy(UmmaContext& ctx);
 // forward convolution plan (stride 1): in/out views, weights wd = [tap][cout][cin] fp16
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
-                       const __half* w_tap_n_k, const float* bias);
+                       int stride, const __half* w_tap_n_k, const float* bias);
+// generic tap table variant (conv1 in space-to-depth form: 16 taps of a 4x4 stride-1 convolution)
+int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int ntaps,
+                        const int* dy, const int* dx, const __half* w_tap_n_k, const float* bias, int relu);
 // data-gradient plan (stride 1): dz/dx gradient views, weights wf = [tap][cin][cout] fp16
 int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
                          const __half* w_tap_k_n, int accumulate);
@@ -75,6 +79,8 @@ struct UmmaWgradPlan {
 // returns the number of splits chosen through *splits (the caller sizes `partial` from it)
 int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int k, int pad,
                     float* partial, int max_splits);
+int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int ntaps,
+                         const int* dy, const int* dx, float* partial, int max_splits);
 int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s);
 
 }  // namespace ssnb

@@ -137,10 +137,19 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
 
 int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int k, int pad,
                     float* partial, int max_splits) {
+  int dy[UMMA_MAX_TAPS], dx[UMMA_MAX_TAPS];
+  if (k * k > UMMA_MAX_TAPS) { set_thread_error("umma wgrad: too many taps"); return 1; }
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s) { dy[r * k + s] = r - pad; dx[r * k + s] = s - pad; }
+  return umma_wgrad_bind_taps(ctx, plan, dz, x, F, cin, cout, k * k, dy, dx, partial, max_splits);
+}
+
+int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int ntaps,
+                         const int* tdy, const int* tdx, float* partial, int max_splits) {
   plan.enabled = false;
   if (int rc = umma_resolve_encode(ctx)) return rc;
   if (dz.H != x.H || dz.W != x.W) { set_thread_error("umma wgrad: stride-1 geometry only"); return 1; }
-  if (cin % 8 || cout % 8 || dz.pitch % 8 || dz.coff % 8 || x.pitch % 8 || x.coff % 8 || k * k > UMMA_MAX_TAPS) {
+  if (cin % 8 || cout % 8 || dz.pitch % 8 || dz.coff % 8 || x.pitch % 8 || x.coff % 8 || ntaps > UMMA_MAX_TAPS) {
     set_thread_error("umma wgrad: unsupported channel alignment"); return 1; }
   UmmaWgradParams& p = plan.p;
   memset(&p, 0, sizeof(p));
@@ -151,9 +160,8 @@ int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int 
   else if (x.W % 2 == 0) { p.bw = 2; p.bh = 2; p.bf = 16; }
   else { p.bw = 1; p.bh = 1; p.bf = 64; }
   p.tiles_w = (x.W + p.bw - 1) / p.bw; p.tiles_h = (x.H + p.bh - 1) / p.bh; p.tiles_f = (F + p.bf - 1) / p.bf;
-  p.ntaps = k * k;
-  for (int r = 0; r < k; ++r)
-    for (int s = 0; s < k; ++s) { p.tap_dy[r * k + s] = r - pad; p.tap_dx[r * k + s] = s - pad; }
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { p.tap_dy[t] = tdy[t]; p.tap_dx[t] = tdx[t]; }
   p.Cout = cout; p.Cin = cin;
   p.m_tiles = (cout + BLOCK_M - 1) / BLOCK_M;
   const int chunks = (cin + 63) / 64;

@@ -282,7 +282,10 @@ def test_backbone_per_layer(backbone_rgb, precision):
         if kind == "gpool" or iname == "data":
             continue
         gout = taps[oname].grad
-        xin = taps[iname].detach().clone().requires_grad_(True)
+        xin = taps[iname].detach().clone()
+        if precision == "fast" and kind == "maxpool":
+            xin = xin.half().float()     # fp16 storage creates ties the fp32 oracle would route differently
+        xin.requires_grad_(True)
         ref_in = _oracle_single_op(bb, kind, oname, xin)
         (gref,) = torch.autograd.grad(ref_in, xin, gout)
         eng.write(iname, taps[iname].detach().to(dev))
@@ -371,6 +374,7 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
         errs[n_] = rel_l2(p.grad, ref)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
     print("e2e exact grad rel-L2 vs live oracle, worst:", worst)
+    print("e2e exact grad rel-L2 in graph order:", [(k.replace("base_model.", "").replace("inception_", ""), "%.1e" % v) for k, v in errs.items() if k.endswith(".weight")])
     print("e2e exact conv1 grad vs golden:", rel_l2(model.base_model.conv1_7x7_s2.weight.grad, torch.tensor(z["rgb_g_conv1_w"])))
     assert worst[0][1] < 1e-3, worst
 
