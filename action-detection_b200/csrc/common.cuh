@@ -80,8 +80,16 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
                      const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
                      cudaStream_t s);
 
+// FAST-mode vectorised glue (glue_fp16.cu)
+int launch_maxpool_fwd_h8(View src, View dst, int F, int k, int stride, int pad, uint8_t* argmax, cudaStream_t s);
+int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pad, const uint8_t* argmax, int accumulate,
+                          cudaStream_t s);
+int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s);
+int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_scale, float* partial, int max_ctas, float* db,
+                        cudaStream_t s);
 // FAST-mode layout helpers (s2d_glue.cu)
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
+int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s);
 int launch_pack_conv1_s2d(const __half* wd, int Cout, int Cin, int Cs, __half* ws, cudaStream_t s);
 int launch_wgrad_finalize_s2d(const float* partial, int splits, int Cout, int Cin, int Cs, const float* mult, float out_scale,
                               float* dw_ref, cudaStream_t s);

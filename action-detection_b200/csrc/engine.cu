@@ -86,6 +86,7 @@ struct ssnb_engine {
   std::vector<PackedConv> packed;
   size_t ws_bytes = 0, partial_off = 0, partial_bytes = 0, bpartial_off = 0;
   size_t s2d_off = 0, s2d_w_off = 0, up_off = 0;   // FAST mode: space-to-depth input + weights, zero-upsampled dz
+  bool s2d_ready = false;                            // backbone_fwd converted the input directly
   int Cs = 0;                                        // channels of the space-to-depth input (4*Cin rounded up to 8)
   char* ws = nullptr;
   bool weights_ready = false;
@@ -242,7 +243,7 @@ static void plan(ssnb_engine* e) {
     }
   }
   e->partial_off = off; e->partial_bytes = pmax; off = align_up(off + pmax, 1024);
-  e->bpartial_off = off; off = align_up(off + 64 * 512 * 4, 1024);
+  e->bpartial_off = off; off = align_up(off + (size_t)1024 * 512 * 4, 1024);   // column-sum partials: <= 1024 CTAs x 512 channels
   e->ws_bytes = off;
 }
 
@@ -255,7 +256,7 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
     const ConvSpec& c = e->convs[o.conv];
     const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
     if (e->fp16 && o.umma.enabled) {
-      if (o.conv == 0)   // conv1 runs as a 4x4 stride-1 convolution over the space-to-depth input
+      if (o.conv == 0 && !e->s2d_ready)   // conv1 runs as a 4x4 stride-1 convolution over the space-to-depth input
         if (int rc = launch_nhwc_to_s2d(in, F, (__half*)(e->ws + e->s2d_off), e->Cs, s)) return rc;
       return umma_conv_launch(e->umma_ctx, o.umma, s);
     }
@@ -269,11 +270,13 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
   if (o.kind == OP_MAXPOOL) {
     const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
     uint8_t* am = (uint8_t*)(e->ws + o.argmax_off);
+    if (e->fp16 && in.C % 8 == 0) return launch_maxpool_fwd_h8(in, out, F, o.k, o.stride, o.pad, am, s);
     return DISPATCH(e, launch_maxpool_fwd<float>(in, out, F, o.k, o.stride, o.pad, am, s),
                     launch_maxpool_fwd<__half>(in, out, F, o.k, o.stride, o.pad, am, s));
   }
   if (o.kind == OP_AVGPOOL) {
     const View in = e->view(o.in_val, false), out = e->view(o.out_val, false);
+    if (e->fp16 && in.C % 8 == 0) return launch_avgpool3_h8(in, out, F, 0, s);
     return DISPATCH(e, launch_avgpool3_fwd<float>(in, out, F, 0, s), launch_avgpool3_fwd<__half>(in, out, F, 0, s));
   }
   if (o.kind == OP_GPOOL) {
@@ -296,11 +299,13 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   if (o.kind == OP_MAXPOOL) {
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
     const uint8_t* am = (const uint8_t*)(e->ws + o.argmax_off);
+    if (e->fp16 && din.C % 8 == 0) return launch_maxpool_bwd_h8(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s);
     return DISPATCH(e, launch_maxpool_bwd<float>(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s),
                     launch_maxpool_bwd<__half>(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s));
   }
   if (o.kind == OP_AVGPOOL) {
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
+    if (e->fp16 && din.C % 8 == 0) return launch_avgpool3_h8(dout, din, F, o.grad_accumulate, s);
     return DISPATCH(e, launch_avgpool3_fwd<float>(dout, din, F, o.grad_accumulate, s),
                     launch_avgpool3_fwd<__half>(dout, din, F, o.grad_accumulate, s));
   }
@@ -308,16 +313,20 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   const ConvSpec& c = e->convs[o.conv];
   const View x = e->view(o.in_val, false), y = e->view(o.out_val, false);
   const View dx = e->view(o.in_val, true), dy = e->view(o.out_val, true);
-  if ((rc = DISPATCH(e, launch_relu_mask<float>(dy, y, F, s), launch_relu_mask<__half>(dy, y, F, s)))) return rc;
   const float* scale = (const float*)(e->ws + e->packed[o.conv].scale);
   float* partial = (float*)(e->ws + e->partial_off);
   float* bpartial = (float*)(e->ws + e->bpartial_off);
   const long long M = (long long)F * y.H * y.W;
-  if (e->db.size() && e->db[o.conv]) {
-    int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
-    rc = DISPATCH(e, launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, e->db[o.conv], s),
-                  launch_bias_grad<__half>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, e->db[o.conv], s));
-    if (rc) return rc;
+  float* dbp = (e->db.size() && e->db[o.conv]) ? e->db[o.conv] : nullptr;
+  if (e->fp16) {
+    // one pass: ReLU gradient mask in place + bias-gradient column sums
+    if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, 1024 * 512 / y.C, dbp, s))) return rc;
+  } else {
+    if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
+    if (dbp) {
+      int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
+      if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, dbp, s))) return rc;
+    }
   }
   if (e->fp16 && c.stride == 2 && o.conv != 0 && (o.umma_wgrad.enabled || o.umma_dgrad.enabled))
     if ((rc = launch_upsample2_zero(dy, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;   // dz at input resolution
@@ -482,11 +491,15 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
   if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
   cudaStream_t s = (cudaStream_t)stream;
   const View d = h->view(h->val_by_name["data"], false);
-  int rc = h->fp16 ? launch_nchw_to_nhwc<__half>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s)
-                   : launch_nchw_to_nhwc<float>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s);
-  if (rc) return h->fail(rc, "input layout: " + ssnb::thread_error());
+  int rc;
+  h->s2d_ready = h->fp16 && h->ops[0].umma.enabled;
+  if (h->s2d_ready) rc = launch_nchw_to_s2d(input_nchw, h->F, d.C, d.H, d.W, (__half*)(h->ws + h->s2d_off), h->Cs, s);
+  else rc = h->fp16 ? launch_nchw_to_nhwc<__half>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s)
+                    : launch_nchw_to_nhwc<float>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s);
+  if (rc) { h->s2d_ready = false; return h->fail(rc, "input layout: " + ssnb::thread_error()); }
   for (const Op& o : h->ops)
-    if ((rc = run_fwd(h, o, input_nchw, feat, s))) return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error());
+    if ((rc = run_fwd(h, o, input_nchw, feat, s))) { h->s2d_ready = false; return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error()); }
+  h->s2d_ready = false;
   return SSNB_OK;
 }
 

@@ -1,0 +1,234 @@
+// FAST-mode (fp16 NHWC) memory-bound glue, vectorised: every thread moves 8 channels (16 bytes) so a
+// warp covers 256 contiguous channels / 512 bytes per pixel row.  Same semantics as the generic
+// kernels in simt_glue.cu (Caffe ceil-mode pooling, layer_factory.py:41-53; first-max-wins argmax).
+#include "common.cuh"
+
+namespace ssnb {
+namespace {
+
+struct H8 { uint4 v; };
+__device__ __forceinline__ void unpack8(const uint4& r, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 r;
+  __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+__device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__global__ void maxpool_fwd_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
+                               __half* __restrict__ dst, int OH, int OW, int dpitch, int dcoff, int F, int k, int stride,
+                               int pad, uint8_t* __restrict__ argmax) {
+  const int G = C / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)F * OH * OW * G) return;
+  const int g = (int)(i % G);
+  const long long p = i / G;
+  const int ox = (int)(p % OW), oy = (int)((p / OW) % OH);
+  const long long f = p / ((long long)OW * OH);
+  float best[8];
+  int bi[8];
+  bool first = true;
+  for (int r = 0; r < k; ++r) {
+    const int iy = oy * stride + r - pad;
+    if (iy < 0 || iy >= H) continue;
+    for (int s = 0; s < k; ++s) {
+      const int ix = ox * stride + s - pad;
+      if (ix < 0 || ix >= W) continue;
+      float v[8];
+      unpack8(ldg16(src + ((f * H + iy) * W + ix) * spitch + scoff + g * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (first || v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; bi[j] = r * k + s; }
+      first = false;
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + p * dpitch + dcoff + g * 8) = pack8(best);
+  uint2 a;
+  a.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+  a.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+  *reinterpret_cast<uint2*>(argmax + p * C + g * 8) = a;
+}
+
+__global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, int spitch, int scoff,
+                               const __half* __restrict__ ddst, int OH, int OW, int dpitch, int dcoff, int F, int k,
+                               int stride, int pad, const uint8_t* __restrict__ argmax, int accumulate) {
+  const int G = C / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)F * H * W * G) return;
+  const int g = (int)(i % G);
+  const long long p = i / G;
+  const int ix = (int)(p % W), iy = (int)((p / W) % H);
+  const long long f = p / ((long long)W * H);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < k; ++r) {
+    const int ty = iy + pad - r;
+    if (ty < 0 || ty % stride) continue;
+    const int oy = ty / stride;
+    if (oy >= OH) continue;
+    for (int s = 0; s < k; ++s) {
+      const int tx = ix + pad - s;
+      if (tx < 0 || tx % stride) continue;
+      const int ox = tx / stride;
+      if (ox >= OW) continue;
+      const long long op = (f * OH + oy) * OW + ox;
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(argmax + op * C + g * 8));
+      const uint32_t tag = (uint32_t)(r * k + s);
+      // any lane of this window pointing here?
+      const uint32_t t4 = tag * 0x01010101u;
+      if (((a.x ^ t4) & 0xFFu) && ((a.x ^ t4) & 0xFF00u) && ((a.x ^ t4) & 0xFF0000u) && ((a.x ^ t4) & 0xFF000000u) &&
+          ((a.y ^ t4) & 0xFFu) && ((a.y ^ t4) & 0xFF00u) && ((a.y ^ t4) & 0xFF0000u) && ((a.y ^ t4) & 0xFF000000u))
+        continue;
+      float v[8];
+      unpack8(ldg16(ddst + op * dpitch + dcoff + g * 8), v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (((a.x >> (8 * j)) & 0xFFu) == tag) acc[j] += v[j];
+        if (((a.y >> (8 * j)) & 0xFFu) == tag) acc[4 + j] += v[4 + j];
+      }
+    }
+  }
+  __half* q = dsrc + p * spitch + scoff + g * 8;
+  if (accumulate) {
+    float o[8];
+    unpack8(*reinterpret_cast<const uint4*>(q), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += o[j];
+  }
+  *reinterpret_cast<uint4*>(q) = pack8(acc);
+}
+
+__global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
+                            __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
+  const int G = C / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)F * H * W * G) return;
+  const int g = (int)(i % G);
+  const long long p = i / G;
+  const int x = (int)(p % W), y = (int)((p / W) % H);
+  const long long f = p / ((long long)W * H);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = -1; r <= 1; ++r) {
+    const int yy = y + r;
+    if (yy < 0 || yy >= H) continue;
+    for (int q = -1; q <= 1; ++q) {
+      const int xx = x + q;
+      if (xx < 0 || xx >= W) continue;
+      float v[8];
+      unpack8(ldg16(src + ((f * H + yy) * W + xx) * spitch + scoff + g * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = s[j] / 9.0f;
+  __half* o = dst + p * dpitch + dcoff + g * 8;
+  if (accumulate) {
+    float old[8];
+    unpack8(*reinterpret_cast<const uint4*>(o), old);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += old[j];
+  }
+  *reinterpret_cast<uint4*>(o) = pack8(s);
+}
+
+// fused ReLU gradient mask + bias-gradient column sums: dz = dy * (y > 0) in place; partial[cta][c] = sum_rows dz
+constexpr int MB_THREADS = 256;
+__global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ dy, int dpitch, int dcoff,
+                                                           const __half* __restrict__ y, int ypitch, int ycoff,
+                                                           long long rows, int C, long long rows_per_cta,
+                                                           float* __restrict__ partial) {
+  extern __shared__ float red[];                 // [lanes][C]
+  const int G = C / 8;
+  const int lanes = MB_THREADS / G;               // row lanes per CTA (G <= 64)
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      __half* pd = dy + r * dpitch + dcoff + g * 8;
+      float d[8], a[8];
+      unpack8(*reinterpret_cast<const uint4*>(pd), d);
+      unpack8(ldg16(y + r * ypitch + ycoff + g * 8), a);
+      bool changed = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
+        acc[j] += d[j];
+      }
+      if (changed) *reinterpret_cast<uint4*>(pd) = pack8(d);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * C + g * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += MB_THREADS) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + c];
+    partial[(long long)blockIdx.x * C + c] = s;
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int n, int C, const float* __restrict__ mult,
+                                    float out_scale, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += partial[(long long)i * C + c];
+  if (db) db[c] = s * mult[c] * out_scale;
+}
+
+}  // namespace
+
+#define HP(v) reinterpret_cast<__half*>((v).base)
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+int launch_maxpool_fwd_h8(View src, View dst, int F, int k, int stride, int pad, uint8_t* argmax, cudaStream_t s) {
+  const long long n = (long long)F * dst.H * dst.W * (src.C / 8);
+  maxpool_fwd_h8<<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.H, dst.W, dst.pitch,
+                                             dst.coff, F, k, stride, pad, argmax);
+  SSNB_LAUNCH_CHECK("maxpool_fwd_h8");
+  return 0;
+}
+int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pad, const uint8_t* argmax, int accumulate,
+                          cudaStream_t s) {
+  const long long n = (long long)F * dsrc.H * dsrc.W * (dsrc.C / 8);
+  maxpool_bwd_h8<<<nblk(n, 256), 256, 0, s>>>(HP(dsrc), dsrc.H, dsrc.W, dsrc.C, dsrc.pitch, dsrc.coff, HP(ddst), ddst.H, ddst.W,
+                                             ddst.pitch, ddst.coff, F, k, stride, pad, argmax, accumulate);
+  SSNB_LAUNCH_CHECK("maxpool_bwd_h8");
+  return 0;
+}
+int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s) {
+  const long long n = (long long)F * src.H * src.W * (src.C / 8);
+  avgpool3_h8<<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
+  SSNB_LAUNCH_CHECK("avgpool3_h8");
+  return 0;
+}
+// partial must hold max_ctas * C floats; db may be nullptr (mask only)
+int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_scale, float* partial, int max_ctas, float* db,
+                        cudaStream_t s) {
+  const long long rows = (long long)F * dy.H * dy.W;
+  const int C = dy.C;
+  if (C % 8 || C / 8 > 64) { set_thread_error("mask_bias: C must be a multiple of 8 and <= 512"); return 1; }
+  int ctas = (int)((rows + 255) / 256);
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  const long long rpc = (rows + ctas - 1) / ctas;
+  ctas = (int)((rows + rpc - 1) / rpc);
+  const int lanes = MB_THREADS / (C / 8);
+  mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dy), dy.pitch, dy.coff, HP(y), y.pitch, y.coff, rows, C, rpc, partial);
+  SSNB_LAUNCH_CHECK("mask_bias_h8");
+  if (db) {
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, ctas, C, mult, out_scale, db);
+    SSNB_LAUNCH_CHECK("colsum_final_kernel");
+  }
+  return 0;
+}
+
+}  // namespace ssnb

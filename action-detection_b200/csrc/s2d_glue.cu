@@ -59,6 +59,25 @@ __global__ void wgrad_finalize_s2d_kernel(const float* __restrict__ partial, int
   dw[i] = acc * mult[co] * out_scale;
 }
 
+// fused input conversion: NCHW fp32 frames -> space-to-depth NHWC fp16, one thread per s2d pixel
+// (reads are float2, coalesced along x; writes are Cs*2 contiguous bytes)
+__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin, int H, int W, __half* __restrict__ dst, int Cs) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)F * H2 * W2) return;
+  const int x2 = (int)(i % W2), y2 = (int)((i / W2) % H2);
+  const long long f = i / ((long long)W2 * H2);
+  __half* o = dst + i * Cs;
+  for (int c = 0; c < Cin; ++c) {
+    const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * x2;
+    const float2 r0 = *reinterpret_cast<const float2*>(pl);
+    const float2 r1 = *reinterpret_cast<const float2*>(pl + W);
+    o[0 * Cin + c] = __float2half_rn(r0.x); o[1 * Cin + c] = __float2half_rn(r0.y);
+    o[2 * Cin + c] = __float2half_rn(r1.x); o[3 * Cin + c] = __float2half_rn(r1.y);
+  }
+  for (int c = 4 * Cin; c < Cs; ++c) o[c] = __float2half_rn(0.f);
+}
+
 // dst[f, y, x, c] = (y, x both even) ? src[f, y/2, x/2, c] : 0
 __global__ void upsample2_zero_kernel(const __half* __restrict__ src, int OH, int OW, int C, int spitch, int scoff,
                                       __half* __restrict__ dst, int H, int W, int F) {
@@ -80,6 +99,12 @@ int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s) {
   const long long n = (long long)F * (src.H / 2) * (src.W / 2) * Cs;
   nhwc_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __half*)src.base, F, src.H, src.W, src.C, src.pitch, src.coff, dst, Cs);
   SSNB_LAUNCH_CHECK("nhwc_to_s2d_kernel");
+  return 0;
+}
+int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s) {
+  const long long n = (long long)F * (H / 2) * (W / 2);
+  nchw_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst, Cs);
+  SSNB_LAUNCH_CHECK("nchw_to_s2d_kernel");
   return 0;
 }
 int launch_pack_conv1_s2d(const __half* wd, int Cout, int Cin, int Cs, __half* ws, cudaStream_t s) {
