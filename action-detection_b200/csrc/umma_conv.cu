@@ -106,8 +106,11 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K chunks whose tail is TMA zero fill (Cin % 64 != 0, conv1's 16-channel taps) skip the all-zero MMAs
+          const int kc = ks % p.kchunks;
+          const int kvalid = min(BLOCK_K, p.K - kc * BLOCK_K);
+          const int nk = (kvalid + UMMA_K - 1) / UMMA_K;
+          for (int k = 0; k < nk; ++k) {
             const uint64_t ad = make_desc_k_sw128(sa + k * UMMA_K * 2);
             const uint64_t bd = make_desc_k_sw128(sb + k * UMMA_K * 2);
             umma_f16(d_tmem, ad, bd, idesc, (ks | k) ? 1u : 0u);
@@ -244,6 +247,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.n_tiles = (N + 255) / 256;
   p.block_n = (((N + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
   p.kchunks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.K = K;
   p.ntaps = ntaps;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
   p.out_stride = out_stride; p.OH = o.H; p.OW = o.W;

@@ -27,7 +27,7 @@ struct UmmaConvParams {
   int bw, bh, bf;                 // TMA box in pixels; bw*bh*bf <= 128 rows of the M tile
   int tiles_w, tiles_h, tiles_f;
   int n_tiles, block_n;           // N split of Cout
-  int kchunks, ntaps;             // ceil(Cin/64), filter taps
+  int kchunks, ntaps, K;          // ceil(K/64), filter taps, reduction channels per tap
   int tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   __half* out; int out_pitch, out_coff, Cout;
   int out_stride, OH, OW;         // stride-2 layers: tiles run at input resolution, only even pixels are stored
@@ -69,6 +69,7 @@ struct UmmaWgradParams {
   int ptiles_per_split, splits;
   int ntaps, tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   int Cout, Cin, m_tiles, n_tiles, block_n;
+  int taps_per_cta, tap_groups, mma_n;   // taps sharing one dz tile per CTA; N of each tap's MMA
   float* partial;
 };
 struct UmmaWgradPlan {

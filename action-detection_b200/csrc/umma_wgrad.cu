@@ -36,16 +36,19 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   int id = blockIdx.x;
-  const int tap = id % p.ntaps; id /= p.ntaps;
+  const int tgrp = id % p.tap_groups; id /= p.tap_groups;
   const int nt = id % p.n_tiles; id /= p.n_tiles;
   const int mt = id;
+  const int tap0 = tgrp * p.taps_per_cta;
+  const int ntap = min(p.taps_per_cta, p.ntaps - tap0);        // taps handled by this CTA (share the dz tile)
   const int split = blockIdx.y;
   const int m0 = mt * BLOCK_M, n0 = nt * p.block_n;
   const int ptiles = p.tiles_w * p.tiles_h * p.tiles_f;
   const int pt0 = split * p.ptiles_per_split;
   const int pt1 = min(pt0 + p.ptiles_per_split, ptiles);
   const int nboxes_b = p.block_n / 64;
-  const uint32_t tmem_cols = p.block_n <= 64 ? 64 : (p.block_n <= 128 ? 128 : 256);
+  const int acc_cols = p.taps_per_cta * p.mma_n;
+  const uint32_t tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dz)) : "memory");
@@ -66,7 +69,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(2 + nboxes_b) * BOX_BYTES;
+      const uint32_t tx_bytes = (uint32_t)(2 + nboxes_b * ntap) * BOX_BYTES;
       for (int pt = pt0; pt < pt1; ++pt) {
         int q = pt;
         const int w0 = (q % p.tiles_w) * p.bw; q /= p.tiles_w;
@@ -78,25 +81,29 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         mbar_expect_tx(&full_bar[stage], tx_bytes);
         tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, h0, f0);
         tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, h0, f0);
-        for (int b = 0; b < nboxes_b; ++b)
-          tma_load_4d(sb + b * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], f0);
+        for (int t = 0; t < ntap; ++t)
+          for (int b = 0; b < nboxes_b; ++b)
+            tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64,
+                        w0 + p.tap_dx[tap0 + t], h0 + p.tap_dy[tap0 + t], f0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16_mn(p.block_n);
+      const uint32_t idesc = make_idesc_f16_mn(p.mma_n);
       uint32_t stage = 0, phase = 0;
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t sb = sa + A_BYTES;
+        for (int t = 0; t < ntap; ++t) {
 #pragma unroll
-        for (int k = 0; k < 64 / UMMA_K; ++k) {      // 16 pixel rows (2 groups of 8) per instruction
-          const uint64_t ad = make_desc_mn_sw128(sa + k * UMMA_K * 128, BOX_BYTES);
-          const uint64_t bd = make_desc_mn_sw128(sb + k * UMMA_K * 128, BOX_BYTES);
-          umma_f16(tmem_base, ad, bd, idesc, (pt > pt0 || k) ? 1u : 0u);
+          for (int k = 0; k < 64 / UMMA_K; ++k) {      // 16 pixel rows (2 groups of 8) per instruction
+            const uint64_t ad = make_desc_mn_sw128(sa + k * UMMA_K * 128, BOX_BYTES);
+            const uint64_t bd = make_desc_mn_sw128(sb + t * nboxes_b * BOX_BYTES + k * UMMA_K * 128, BOX_BYTES);
+            umma_f16(tmem_base + t * p.mma_n, ad, bd, idesc, (pt > pt0 || k) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -109,17 +116,19 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float* orow = p.partial + (((long long)split * p.ntaps + tap) * p.Cout + m) * p.Cin + n0;
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr + c0, r);
-      tmem_ld_wait();
-      if (m < p.Cout) {
+    for (int t = 0; t < ntap; ++t) {
+      float* orow = p.partial + (((long long)split * p.ntaps + tap0 + t) * p.Cout + m) * p.Cin + n0;
+      for (int c0 = 0; c0 < p.mma_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + t * p.mma_n + c0, r);
+        tmem_ld_wait();
+        if (m < p.Cout) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          if (n0 + c0 + j < p.Cin)      // Cin is a multiple of 4
-            *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 16; j += 4) {
+            if (n0 + c0 + j < p.Cin)      // Cin is a multiple of 4
+              *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
         }
       }
     }
@@ -167,8 +176,17 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   const int chunks = (cin + 63) / 64;
   p.n_tiles = (chunks + 3) / 4;
   p.block_n = ((chunks + p.n_tiles - 1) / p.n_tiles) * 64;
+  // several taps per CTA share one dz tile: stage = 2 dz boxes + taps * (block_n/64) x boxes <= 6 boxes, and
+  // the accumulators (taps * mma_n fp32 columns) must fit the 512 TMEM columns
+  p.mma_n = p.block_n;
+  if (p.n_tiles == 1 && cin < p.block_n) p.mma_n = (cin + 15) / 16 * 16;     // narrow inputs (conv1 space-to-depth: 16)
+  p.taps_per_cta = 4 / (p.block_n / 64);
+  if (p.taps_per_cta < 1) p.taps_per_cta = 1;
+  while (p.taps_per_cta > 1 && p.taps_per_cta * p.mma_n > 512) --p.taps_per_cta;
+  if (p.taps_per_cta > ntaps) p.taps_per_cta = ntaps;
+  p.tap_groups = (ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
   const int ptiles = p.tiles_w * p.tiles_h * p.tiles_f;
-  const int ctas = p.m_tiles * p.n_tiles * p.ntaps;
+  const int ctas = p.m_tiles * p.n_tiles * p.tap_groups;
   int splits = (2 * ctx.num_sms + ctas - 1) / ctas;
   if (splits > max_splits) splits = max_splits;
   if (splits > ptiles) splits = ptiles;
@@ -201,7 +219,7 @@ int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t 
     attr_set = true;
   }
   const UmmaWgradParams& p = plan.p;
-  dim3 grid((unsigned)(p.m_tiles * p.n_tiles * p.ntaps), (unsigned)p.splits);
+  dim3 grid((unsigned)(p.m_tiles * p.n_tiles * p.tap_groups), (unsigned)p.splits);
   umma_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_dz, plan.tmap_x, p);
   SSNB_LAUNCH_CHECK("umma_wgrad_kernel");
   return 0;
