@@ -175,13 +175,16 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
   }
 }
 
+// one warp per channel: lanes stride over the CTA partials (fixed order per lane + fixed shuffle tree = deterministic)
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int n, int C, const float* __restrict__ mult,
                                     float out_scale, float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (c >= C) return;
   float s = 0.f;
-  for (int i = 0; i < n; ++i) s += partial[(long long)i * C + c];
-  if (db) db[c] = s * mult[c] * out_scale;
+  for (int i = lane; i < n; i += 32) s += partial[(long long)i * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0 && db) db[c] = s * mult[c] * out_scale;
 }
 
 }  // namespace
@@ -225,7 +228,7 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
   mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dy), dy.pitch, dy.coff, HP(y), y.pitch, y.coff, rows, C, rpc, partial);
   SSNB_LAUNCH_CHECK("mask_bias_h8");
   if (db) {
-    colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, ctas, C, mult, out_scale, db);
+    colsum_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(partial, ctas, C, mult, out_scale, db);
     SSNB_LAUNCH_CHECK("colsum_final_kernel");
   }
   return 0;

@@ -19,7 +19,7 @@ def load(path):
 
 
 def short(name):
-    n = name.replace("ssnb::<unnamed>::", "").replace("ssnb::", "").replace("void ", "")
+    n = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "").replace("ssnb::", "").replace("void ", "")
     m = re.match(r"([\w:]+)(<[^(]*>)?\(", n)
     if not m:
         return n[:50]
