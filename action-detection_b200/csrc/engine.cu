@@ -66,8 +66,18 @@ struct Op {
   UmmaConvPlan umma;        // tcgen05 forward plan (FAST mode, stride-1 layers)
   UmmaConvPlan umma_dgrad;  // tcgen05 data-gradient plan
   UmmaWgradPlan umma_wgrad; // tcgen05 weight-gradient plan
+  int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
+  int fuse_block = -1;
 };
 struct PackedConv { size_t wf, wd, bias, scale; };
+// the 1x1 convolutions of one inception block that read the block input (1x1, 3x3_reduce, double_3x3_reduce)
+struct FusedBlock {
+  int op1 = -1, op_r3 = -1, op_rd = -1;   // op indices (op1 = -1 for 3c/4e)
+  int c1 = 0, c3r = 0, cdr = 0, cx = 0;
+  size_t w_fwd = 0, bias = 0, w_dg = 0;   // stacked forward weights/bias, K-concatenated data-gradient weights
+  UmmaConvPlan fwd, dgrad;
+  bool enabled = false;
+};
 
 }  // namespace ssnb
 
@@ -84,6 +94,7 @@ struct ssnb_engine {
   std::map<std::string, int> val_by_name;
   std::vector<Op> ops;
   std::vector<PackedConv> packed;
+  std::vector<FusedBlock> fused;
   size_t ws_bytes = 0, partial_off = 0, partial_bytes = 0, bpartial_off = 0;
   size_t s2d_off = 0, s2d_w_off = 0, up_off = 0;   // FAST mode: space-to-depth input + weights, zero-upsampled dz
   bool s2d_ready = false;                            // backbone_fwd converted the input directly
@@ -228,8 +239,29 @@ static void plan(ssnb_engine* e) {
     }
   }
   if (e->fp16) {
+    for (int i = 0; i < (int)e->ops.size(); ++i) {
+      const Op& o = e->ops[i];
+      if (o.kind != OP_CONV || o.k != 1) continue;
+      const std::string& id = o.id;
+      const std::string suf = "_3x3_reduce";
+      if (id.size() < suf.size() || id.compare(id.size() - suf.size(), suf.size(), suf) != 0 || id.find("double") != std::string::npos) continue;
+      const std::string pre = id.substr(0, id.size() - suf.size() + 1);      // "inception_3a_"
+      FusedBlock fb; fb.op_r3 = i;
+      for (int j = 0; j < (int)e->ops.size(); ++j) {
+        if (e->ops[j].id == pre + "1x1") fb.op1 = j;
+        if (e->ops[j].id == pre + "double_3x3_reduce") fb.op_rd = j;
+      }
+      if (fb.op_rd < 0) continue;
+      fb.cx = e->convs[o.conv].cin; fb.c3r = e->convs[o.conv].cout; fb.cdr = e->convs[e->ops[fb.op_rd].conv].cout;
+      fb.c1 = fb.op1 >= 0 ? e->convs[e->ops[fb.op1].conv].cout : 0;
+      const int n = fb.c1 + fb.c3r + fb.cdr, kf = (fb.c1 + 63) / 64 * 64 + fb.c3r + fb.cdr;
+      fb.w_fwd = off; off = align_up(off + (size_t)n * fb.cx * 2, 1024);
+      fb.bias = off; off = align_up(off + (size_t)n * 4, 256);
+      fb.w_dg = off; off = align_up(off + (size_t)fb.cx * kf * 2, 1024);
+      e->fused.push_back(fb);
+    }
     e->Cs = (4 * e->cfg.in_channels + 7) / 8 * 8;
-    e->s2d_off = off; off = align_up(off + F * 112 * 112 * e->Cs * 2, 1024);
+    e->s2d_off = off; off = align_up(off + F * 112 * 112 * 4 * e->Cs * 2, 1024);   // packed: 4 horizontal neighbours per pixel
     e->s2d_w_off = off; off = align_up(off + (size_t)16 * 64 * e->Cs * 2, 1024);
     if (e->cfg.training) {
       size_t up = 0;
@@ -287,7 +319,7 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
   return SSNB_EINVAL;
 }
 
-static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t s) {
+static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t s, bool skip_dgrad = false) {
   const int F = e->F;
   const float gs = e->fp16 ? e->cfg.grad_scale : 1.0f;
   int rc = 0;
@@ -344,7 +376,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if ((rc = DISPATCH(e, launch_wgrad<float>(w, s), launch_wgrad<__half>(w, s)))) return rc;
     if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s))) return rc;
   }
-  if (e->vals[o.in_val].name != "data") {
+  if (e->vals[o.in_val].name != "data" && !skip_dgrad) {
     if (e->fp16 && o.umma_dgrad.enabled) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s);
     ConvArgs a;
     a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
@@ -429,15 +461,16 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     const View in = h->view(o.in_val, false), out = h->view(o.out_val, false);
     int rc = 0;
     if (o.conv == 0) {
-      // conv1 7x7/2: 4x4 stride-1 convolution over the space-to-depth input (r = 2*dr + a - 1)
-      View xs; xs.base = h->ws + h->s2d_off; xs.H = 112; xs.W = 112; xs.C = h->Cs; xs.pitch = h->Cs; xs.coff = 0;
-      int dy[16], dx[16];
-      for (int t = 0; t < 16; ++t) { dy[t] = t / 4 - 2; dx[t] = t % 4 - 2; }
-      rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, out, h->F, h->Cs, c.cout, 16, dy, dx, (const __half*)(h->ws + h->s2d_w_off),
+      // conv1 7x7/2: four vertical taps over the packed space-to-depth input (r = 2*dr + a - 1, s = 2*ds + b - 1)
+      const int Ck = 4 * h->Cs;
+      View xs; xs.base = h->ws + h->s2d_off; xs.H = 112; xs.W = 112; xs.C = Ck; xs.pitch = Ck; xs.coff = 0;
+      int dy[4], dx[4];
+      for (int t = 0; t < 4; ++t) { dy[t] = t - 2; dx[t] = 0; }
+      rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, out, h->F, Ck, c.cout, 4, dy, dx, (const __half*)(h->ws + h->s2d_w_off),
                                (const float*)(h->ws + h->packed[0].bias), 1);
       if (rc) { o.umma.enabled = false; continue; }     // stays on the SIMT kernel
       if (use_wgrad) {
-        rc = umma_wgrad_bind_taps(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), xs, h->F, h->Cs, c.cout, 16, dy, dx,
+        rc = umma_wgrad_bind_taps(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), xs, h->F, Ck, c.cout, 4, dy, dx,
                                   (float*)(h->ws + h->partial_off), 128);
         if (rc) o.umma_wgrad.enabled = false;
       }
@@ -458,6 +491,34 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, dz, in, h->F, c.cin, c.cout, c.k, c.pad, (float*)(h->ws + h->partial_off), o.wsplits);
       if (rc) return h->fail(rc, "umma_wgrad_bind(" + c.id + "): " + ssnb::thread_error());
     }
+  }
+  // horizontal fusion of the sibling 1x1 convolutions of each inception block (SSNB_DISABLE_FUSION=1 turns it off)
+  const char* disf = getenv("SSNB_DISABLE_FUSION");
+  for (Op& o : h->ops) { o.fuse_role = 0; o.fuse_block = -1; }
+  for (size_t bi = 0; bi < h->fused.size(); ++bi) {
+    FusedBlock& fb = h->fused[bi];
+    fb.enabled = false;
+    if (!use_umma || (disf && disf[0] == '1')) continue;
+    Op& o3 = h->ops[fb.op_r3]; Op& od = h->ops[fb.op_rd];
+    const View x = h->view(o3.in_val, false);
+    View red = h->view(o3.out_val, false); red.C = fb.c3r + fb.cdr;          // both reduce outputs: adjacent slices of one buffer
+    int rc;
+    if (fb.op1 >= 0) rc = umma_conv_bind_fused_fwd(h->umma_ctx, fb.fwd, x, h->view(h->ops[fb.op1].out_val, false), red, h->F, fb.cx, fb.c1,
+                                                  fb.c3r + fb.cdr, (const __half*)(h->ws + fb.w_fwd), (const float*)(h->ws + fb.bias));
+    else rc = umma_conv_bind_fwd(h->umma_ctx, fb.fwd, x, red, h->F, fb.cx, fb.c3r + fb.cdr, 1, 0, 1, (const __half*)(h->ws + fb.w_fwd),
+                                 (const float*)(h->ws + fb.bias));
+    if (rc) return h->fail(rc, "fused fwd bind(" + o3.id + "): " + ssnb::thread_error());
+    if (h->cfg.training) {
+      View dred = h->view(o3.out_val, true); dred.C = fb.c3r + fb.cdr;
+      View d1 = fb.op1 >= 0 ? h->view(h->ops[fb.op1].out_val, true) : dred;
+      rc = umma_conv_bind_fused_dgrad(h->umma_ctx, fb.dgrad, d1, dred, h->view(o3.in_val, true), h->F, fb.cx, fb.c1, fb.c3r + fb.cdr,
+                                      (const __half*)(h->ws + fb.w_dg), od.grad_accumulate);
+      if (rc) return h->fail(rc, "fused dgrad bind(" + o3.id + "): " + ssnb::thread_error());
+    }
+    fb.enabled = true;
+    const int leader = fb.op1 >= 0 ? fb.op1 : fb.op_r3;
+    for (int j : {fb.op1, fb.op_r3, fb.op_rd})
+      if (j >= 0) { h->ops[j].fuse_block = (int)bi; h->ops[j].fuse_role = (j == leader) ? 1 : 2; }
   }
   return SSNB_OK;
 }
@@ -482,6 +543,26 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                                    (__half*)(h->ws + h->s2d_w_off), s);
     if (rc) return h->fail(rc, "pack conv1 s2d: " + ssnb::thread_error());
   }
+  for (FusedBlock& fb : h->fused) {
+    if (!fb.enabled) continue;
+    // forward: rows of wd ([co][ci]) stacked; bias stacked.  data gradient: wf ([ci][co]) concatenated along K,
+    // the 1x1 part padded to a multiple of 64 so each K chunk has a single activation source.
+    const int k1p = (fb.c1 + 63) / 64 * 64, kf = k1p + fb.c3r + fb.cdr;
+    __half* wfwd = (__half*)(h->ws + fb.w_fwd); float* bias = (float*)(h->ws + fb.bias); __half* wdg = (__half*)(h->ws + fb.w_dg);
+    if (cudaMemsetAsync(wdg, 0, (size_t)fb.cx * kf * 2, s) != cudaSuccess) return h->fail(SSNB_ECUDA, "fused pack: memset");
+    int row = 0, col = 0;
+    for (int j : {fb.op1, fb.op_r3, fb.op_rd}) {
+      if (j < 0) { continue; }
+      const int ci = h->ops[j].conv, co = h->convs[ci].cout;
+      cudaError_t e1 = cudaMemcpyAsync(wfwd + (size_t)row * fb.cx, h->ws + h->packed[ci].wd, (size_t)co * fb.cx * 2, cudaMemcpyDeviceToDevice, s);
+      cudaError_t e2 = cudaMemcpyAsync(bias + row, h->ws + h->packed[ci].bias, (size_t)co * 4, cudaMemcpyDeviceToDevice, s);
+      cudaError_t e3 = cudaMemcpy2DAsync(wdg + col, (size_t)kf * 2, h->ws + h->packed[ci].wf, (size_t)co * 2, (size_t)co * 2, fb.cx,
+                                         cudaMemcpyDeviceToDevice, s);
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return h->fail(SSNB_ECUDA, "fused pack: copy failed");
+      row += co;
+      col += (j == fb.op1) ? k1p : co;
+    }
+  }
   h->weights_ready = true;
   return SSNB_OK;
 }
@@ -497,8 +578,12 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
   else rc = h->fp16 ? launch_nchw_to_nhwc<__half>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s)
                     : launch_nchw_to_nhwc<float>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s);
   if (rc) { h->s2d_ready = false; return h->fail(rc, "input layout: " + ssnb::thread_error()); }
-  for (const Op& o : h->ops)
-    if ((rc = run_fwd(h, o, input_nchw, feat, s))) { h->s2d_ready = false; return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error()); }
+  for (const Op& o : h->ops) {
+    if (o.fuse_role == 2) continue;                       // computed by its block's fused launch
+    if (o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].fwd, s);
+    else rc = run_fwd(h, o, input_nchw, feat, s);
+    if (rc) { h->s2d_ready = false; return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error()); }
+  }
   h->s2d_ready = false;
   return SSNB_OK;
 }
@@ -517,8 +602,10 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   ssnb_bind_grads(h, dw, db);
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
-    int rc = run_bwd(h, h->ops[i], dfeat, s);
-    if (rc) return h->fail(rc, "bwd " + h->ops[i].id + ": " + ssnb::thread_error());
+    const Op& o = h->ops[i];
+    int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0);   // siblings: mask/bias/wgrad only ...
+    if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s);   // ... one fused data gradient
+    if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
   }
   return SSNB_OK;
 }

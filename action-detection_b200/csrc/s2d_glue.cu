@@ -7,69 +7,82 @@
 namespace ssnb {
 namespace {
 
+// Packed layout: Ck = 4*Cs channels per pixel, channel = ds*Cs + (a*2+b)*Cin + c holds
+//   x[f, 2*i + a, 2*(j + ds - 2) + b, c]      (zero outside the image / for the pad channels)
+// so the 7x7/2 convolution becomes FOUR vertical taps (dr = 0..3, dy = dr - 2) with K = 4*Cs each:
+//   r = 2*dr + a - 1,  s = 2*ds + b - 1.
 __global__ void nhwc_to_s2d_kernel(const __half* __restrict__ src, int F, int H, int W, int Cin, int spitch, int scoff,
                                    __half* __restrict__ dst, int Cs) {
-  const int H2 = H / 2, W2 = W / 2;
-  const long long total = (long long)F * H2 * W2 * Cs;
+  const int H2 = H / 2, W2 = W / 2, Ck = 4 * Cs;
+  const long long total = (long long)F * H2 * W2 * Ck;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int ch = (int)(i % Cs);
-  const long long p = i / Cs;
+  const int ch = (int)(i % Ck);
+  const long long p = i / Ck;
   const int x2 = (int)(p % W2), y2 = (int)((p / W2) % H2);
   const long long f = p / ((long long)W2 * H2);
+  const int ds = ch / Cs, q = ch % Cs;
   __half v = __float2half_rn(0.f);
-  if (ch < 4 * Cin) {
-    const int ab = ch / Cin, c = ch % Cin;
-    const int a = ab / 2, b = ab % 2;
-    v = src[((f * H + 2 * y2 + a) * W + 2 * x2 + b) * spitch + scoff + c];
+  const int xs = x2 + ds - 2;
+  if (q < 4 * Cin && xs >= 0 && xs < W2) {
+    const int ab = q / Cin, c = q % Cin;
+    v = src[((f * H + 2 * y2 + ab / 2) * W + 2 * xs + ab % 2) * spitch + scoff + c];
   }
   dst[i] = v;
 }
 
-// ws[(dr*4+ds)][co][(a*2+b)*Cin + c] = wd[(r*7+s)][co][c],  r = 2*dr+a-1, s = 2*ds+b-1 (0 outside 0..6)
+// ws[dr][co][ds*Cs + (a*2+b)*Cin + c] = wd[(r*7+s)][co][c],  r = 2*dr+a-1, s = 2*ds+b-1 (0 outside 0..6)
 __global__ void pack_conv1_s2d_kernel(const __half* __restrict__ wd, int Cout, int Cin, int Cs, __half* __restrict__ ws) {
-  const long long total = (long long)16 * Cout * Cs;
+  const int Ck = 4 * Cs;
+  const long long total = (long long)4 * Cout * Ck;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int ch = (int)(i % Cs);
-  const int co = (int)((i / Cs) % Cout);
-  const int tap = (int)(i / ((long long)Cs * Cout));
-  const int dr = tap / 4, ds = tap % 4;
+  const int ch = (int)(i % Ck);
+  const int co = (int)((i / Ck) % Cout);
+  const int dr = (int)(i / ((long long)Ck * Cout));
+  const int ds = ch / Cs, q = ch % Cs;
   __half v = __float2half_rn(0.f);
-  if (ch < 4 * Cin) {
-    const int ab = ch / Cin, c = ch % Cin;
+  if (q < 4 * Cin) {
+    const int ab = q / Cin, c = q % Cin;
     const int r = 2 * dr + ab / 2 - 1, s = 2 * ds + ab % 2 - 1;
     if (r >= 0 && r < 7 && s >= 0 && s < 7) v = wd[((long long)(r * 7 + s) * Cout + co) * Cin + c];
   }
   ws[i] = v;
 }
 
-// dw_ref[co][c][r][s] = mult[co]*out_scale * sum_splits partial[sp][tap(dr,ds)][co][(a*2+b)*Cin + c]
+// dw_ref[co][c][r][s] = mult[co]*out_scale * sum_splits partial[sp][dr][co][ds*Cs + (a*2+b)*Cin + c]
 __global__ void wgrad_finalize_s2d_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int Cs,
                                           const float* __restrict__ mult, float out_scale, float* __restrict__ dw) {
+  const int Ck = 4 * Cs;
   const long long total = (long long)Cout * Cin * 49;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int s = (int)(i % 7), r = (int)((i / 7) % 7);
   const int c = (int)((i / 49) % Cin), co = (int)(i / (49LL * Cin));
   const int dr = (r + 1) / 2, a = (r + 1) % 2, ds = (s + 1) / 2, b = (s + 1) % 2;
-  const int tap = dr * 4 + ds, ch = (a * 2 + b) * Cin + c;
+  const int ch = ds * Cs + (a * 2 + b) * Cin + c;
   float acc = 0.f;
-  for (int sp = 0; sp < splits; ++sp) acc += partial[(((long long)sp * 16 + tap) * Cout + co) * Cs + ch];
+  for (int sp = 0; sp < splits; ++sp) acc += partial[(((long long)sp * 4 + dr) * Cout + co) * Ck + ch];
   dw[i] = acc * mult[co] * out_scale;
 }
 
-// fused input conversion: NCHW fp32 frames -> space-to-depth NHWC fp16, one thread per s2d pixel
-// (reads are float2, coalesced along x; writes are Cs*2 contiguous bytes)
+// fused input conversion: NCHW fp32 frames -> packed space-to-depth fp16; one thread per (pixel, ds block)
 __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin, int H, int W, __half* __restrict__ dst, int Cs) {
   const int H2 = H / 2, W2 = W / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)F * H2 * W2) return;
-  const int x2 = (int)(i % W2), y2 = (int)((i / W2) % H2);
-  const long long f = i / ((long long)W2 * H2);
-  __half* o = dst + i * Cs;
+  if (i >= (long long)F * H2 * W2 * 4) return;
+  const int ds = (int)(i % 4);
+  const long long p = i / 4;
+  const int x2 = (int)(p % W2), y2 = (int)((p / W2) % H2);
+  const long long f = p / ((long long)W2 * H2);
+  __half* o = dst + p * (4 * Cs) + ds * Cs;
+  const int xs = x2 + ds - 2;
+  if (xs < 0 || xs >= W2) {
+    for (int c = 0; c < Cs; ++c) o[c] = __float2half_rn(0.f);
+    return;
+  }
   for (int c = 0; c < Cin; ++c) {
-    const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * x2;
+    const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * xs;
     const float2 r0 = *reinterpret_cast<const float2*>(pl);
     const float2 r1 = *reinterpret_cast<const float2*>(pl + W);
     o[0 * Cin + c] = __float2half_rn(r0.x); o[1 * Cin + c] = __float2half_rn(r0.y);
@@ -96,19 +109,19 @@ __global__ void upsample2_zero_kernel(const __half* __restrict__ src, int OH, in
 }  // namespace
 
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s) {
-  const long long n = (long long)F * (src.H / 2) * (src.W / 2) * Cs;
+  const long long n = (long long)F * (src.H / 2) * (src.W / 2) * 4 * Cs;
   nhwc_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __half*)src.base, F, src.H, src.W, src.C, src.pitch, src.coff, dst, Cs);
   SSNB_LAUNCH_CHECK("nhwc_to_s2d_kernel");
   return 0;
 }
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s) {
-  const long long n = (long long)F * (H / 2) * (W / 2);
+  const long long n = (long long)F * (H / 2) * (W / 2) * 4;
   nchw_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst, Cs);
   SSNB_LAUNCH_CHECK("nchw_to_s2d_kernel");
   return 0;
 }
 int launch_pack_conv1_s2d(const __half* wd, int Cout, int Cin, int Cs, __half* ws, cudaStream_t s) {
-  const long long n = 16LL * Cout * Cs;
+  const long long n = 16LL * Cout * Cs;   // 4 taps x Cout x 4*Cs
   pack_conv1_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wd, Cout, Cin, Cs, ws);
   SSNB_LAUNCH_CHECK("pack_conv1_s2d_kernel");
   return 0;

@@ -39,8 +39,8 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaConvParams& p, int ti
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const UmmaConvParams p) {
+umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                 const __grid_constant__ CUtensorMap tmap_b, const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -57,6 +57,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
@@ -85,7 +86,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
+            if (kc < p.kchunks_a1) tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
+            else tma_load_4d(sa, &tmap_a2, &full_bar[stage], (kc - p.kchunks_a1) * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
             tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, t.n0, tap);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -101,22 +103,26 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        int kc = 0;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          // K chunks whose tail is TMA zero fill (Cin % 64 != 0, conv1's 16-channel taps) skip the all-zero MMAs
-          const int kc = ks % p.kchunks;
-          const int kvalid = min(BLOCK_K, p.K - kc * BLOCK_K);
-          const int nk = (kvalid + UMMA_K - 1) / UMMA_K;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t ad = make_desc_k_sw128(sa + k * UMMA_K * 2);
-            const uint64_t bd = make_desc_k_sw128(sb + k * UMMA_K * 2);
-            umma_f16(d_tmem, ad, bd, idesc, (ks | k) ? 1u : 0u);
+          // K chunks whose tail is TMA zero fill (Cin % 64 != 0) skip the all-zero MMAs
+          const int kvalid = kc < p.kchunks_a1 ? p.K1 - kc * BLOCK_K : p.K - p.K1 - (kc - p.kchunks_a1) * BLOCK_K;
+          if (kvalid >= BLOCK_K) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16(d_tmem, make_desc_k_sw128(sa + k * UMMA_K * 2), make_desc_k_sw128(sb + k * UMMA_K * 2), idesc, (ks | k) ? 1u : 0u);
+          } else {
+            const int nk = (kvalid + UMMA_K - 1) / UMMA_K;
+            for (int k = 0; k < nk; ++k)
+              umma_f16(d_tmem, make_desc_k_sw128(sa + k * UMMA_K * 2), make_desc_k_sw128(sb + k * UMMA_K * 2), idesc, (ks | k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++kc == p.kchunks) kc = 0;
         }
         umma_commit(&tfull_bar[acc]);                   // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -133,7 +139,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
       const int os = p.out_stride;
       const bool valid = (rf < p.bf) && (w < p.W) && (h < p.H) && (f < p.F) && (w % os == 0) && (h % os == 0);
-      __half* orow = p.out + ((long long)(f * p.OH + h / os) * p.OW + w / os) * p.out_pitch + p.out_coff + t.n0;
+      const long long opix = (long long)(f * p.OH + h / os) * p.OW + w / os;
+      __half* orow = p.out + opix * p.out_pitch + p.out_coff;
+      __half* orow2 = p.out2 + opix * p.out2_pitch + p.out2_coff - p.n_split;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -149,7 +157,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + t.n0 + c0 + j);
           }
-          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+          const int col = t.n0 + c0;
+          uint4* dst = reinterpret_cast<uint4*>((col < p.n_split ? orow : orow2) + col);
           if (p.accumulate) {
             uint4 o0 = dst[0], o1 = dst[1];
             const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
@@ -251,6 +260,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.ntaps = ntaps;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
   p.out_stride = out_stride; p.OH = o.H; p.OW = o.W;
+  p.kchunks_a1 = (K + BLOCK_K - 1) / BLOCK_K; p.K1 = K; p.n_split = 1 << 30; p.out2 = p.out; p.out2_pitch = o.pitch; p.out2_coff = o.coff;
   {
     cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)F};
     cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2};
@@ -263,6 +273,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
     cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n, 1};
     if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(w), dims, str, box)) return rc;
   }
+  plan.tmap_a2 = plan.tmap_a;
   plan.enabled = true;
   return 0;
 }
@@ -306,6 +317,43 @@ int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx,
   return 0;
 }
 
+int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out1, View out2, int F, int cin, int n1, int n2,
+                             const __half* w_n_k, const float* bias) {
+  // bind as one convolution with N = n1 + n2 writing to out1's geometry, then redirect columns >= n1
+  View o = out1; o.C = n1 + n2;
+  if (out1.H != out2.H || out1.W != out2.W || n1 % 16 || n2 % 16 || out2.pitch % 8 || out2.coff % 8) { set_thread_error("fused fwd: bad views"); return 1; }
+  if (int rc = bind_common(ctx, plan, in, o, F, cin, n1 + n2, 1, 1, w_n_k)) return rc;
+  plan.p.tap_dy[0] = 0; plan.p.tap_dx[0] = 0;
+  plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;
+  plan.p.n_split = n1; plan.p.out2 = reinterpret_cast<__half*>(out2.base); plan.p.out2_pitch = out2.pitch; plan.p.out2_coff = out2.coff;
+  return 0;
+}
+
+int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, View dz2, View dx, int F, int cin, int k1, int k2,
+                               const __half* w_n_k, int accumulate) {
+  const int k1p = (k1 + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  // bind with the first source as the A view and the full fused K; then attach the second source
+  View a = k1 ? dz1 : dz2;
+  if (int rc = bind_common(ctx, plan, a, dx, F, k1 ? k1 : k2, cin, 1, 1, w_n_k)) return rc;
+  UmmaConvParams& p = plan.p;
+  p.tap_dy[0] = 0; p.tap_dx[0] = 0; p.bias = nullptr; p.relu = 0; p.accumulate = accumulate;
+  if (k1) {
+    if (dz2.H != dz1.H || dz2.W != dz1.W || dz2.pitch % 8 || dz2.coff % 8 || k2 % 8) { set_thread_error("fused dgrad: bad views"); return 1; }
+    cuuint64_t dims[4] = {(cuuint64_t)k2, (cuuint64_t)dz2.W, (cuuint64_t)dz2.H, (cuuint64_t)F};
+    cuuint64_t str[3] = {(cuuint64_t)dz2.pitch * 2, (cuuint64_t)dz2.W * dz2.pitch * 2, (cuuint64_t)dz2.H * dz2.W * dz2.pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
+    if (int rc = encode(ctx, &plan.tmap_a2, 4, reinterpret_cast<__half*>(dz2.base) + dz2.coff, dims, str, box)) { plan.enabled = false; return rc; }
+    p.kchunks_a1 = k1p / BLOCK_K; p.K1 = k1; p.K = k1 + k2;
+    p.kchunks = p.kchunks_a1 + (k2 + BLOCK_K - 1) / BLOCK_K;
+    // the weight map covers the padded fused K
+    cuuint64_t bd[3] = {(cuuint64_t)(k1p + k2), (cuuint64_t)cin, 1};
+    cuuint64_t bs[2] = {(cuuint64_t)(k1p + k2) * 2, (cuuint64_t)cin * (k1p + k2) * 2};
+    cuuint32_t bb[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n, 1};
+    if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(w_n_k), bd, bs, bb)) { plan.enabled = false; return rc; }
+  }
+  return 0;
+}
+
 int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s) {
   if (!plan.enabled) { set_thread_error("umma conv: plan not bound"); return 3; }
   if (!ctx.attr_set) {
@@ -316,7 +364,7 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s)
   const UmmaConvParams& p = plan.p;
   const int total = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
   const int grid = total < ctx.num_sms ? total : ctx.num_sms;
-  umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_b, p);
+  umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, p);
   SSNB_LAUNCH_CHECK("umma_conv_kernel");
   return 0;
 }

@@ -33,11 +33,15 @@ struct UmmaConvParams {
   int out_stride, OH, OW;         // stride-2 layers: tiles run at input resolution, only even pixels are stored
   const float* bias;              // [Cout] or nullptr
   int relu, accumulate;
+  // horizontal fusion of sibling 1x1 convolutions (same input):
+  int kchunks_a1, K1;             // K chunks [0, kchunks_a1) come from tmap_a (K1 real channels), the rest from tmap_a2
+  int n_split;                    // output columns >= n_split go to out2 (second destination), else to out
+  __half* out2; int out2_pitch, out2_coff;
 };
 
 struct UmmaConvPlan {
   bool enabled = false;
-  CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a, tmap_a2, tmap_b;
   UmmaConvParams p;
 };
 
@@ -52,6 +56,12 @@ int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out,
 // data-gradient plan (stride 1): dz/dx gradient views, weights wf = [tap][cin][cout] fp16
 int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
                          const __half* w_tap_k_n, int accumulate);
+// fused forward of sibling 1x1 convs: one input view, weights [n1+n2][cin] (rows stacked), columns [0,n1) -> out1, rest -> out2
+int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out1, View out2, int F, int cin, int n1, int n2,
+                             const __half* w_n_k, const float* bias);
+// fused data gradient of sibling 1x1 convs: dx (+)= [dz1 | dz2] * W, weights [cin][pad64(k1) + k2]; dz1 may be empty (k1 = 0)
+int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, View dz2, View dx, int F, int cin, int k1, int k2,
+                               const __half* w_n_k, int accumulate);
 int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s);
 
 // host helpers shared by the tensor-core kernels

@@ -461,3 +461,55 @@ def test_test_forward_and_prepare_test_fc(backbone_rgb):
     ref_feat = O.backbone_forward(backbone_rgb, x.cpu(), 3)
     assert rel_l2(base_out, ref_feat) < 1e-4
     assert rel_l2(scores, torch.nn.functional.linear(ref_feat, w_ref, b_ref)) < 1e-4
+
+
+def test_fast_fused_vs_unfused_and_oracle(backbone_rgb):
+    """FAST mode, whole backbone fwd+bwd on 18 frames: the fused schedule (sibling 1x1 fusion, conv1
+    space-to-depth, stride-2 sampling, tcgen05 everywhere) against the same engine with fusion and
+    tensor cores disabled (SIMT fp16 kernels), and both against the fp32 oracle."""
+    dev = _cuda()
+    from ssn_b200 import _lib
+    from ssn_b200.engine import BackboneEngine
+    Fn = 18
+    names = [n for (n, *_r) in O.conv_layers(3)]
+    x = synth.synth_frames(Fn, 3, seed=11)
+    g = torch.Generator().manual_seed(12)
+    dfeat = torch.randn(Fn, 1024, generator=g) * 0.01
+
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            eng = BackboneEngine(3, Fn, _lib.FAST_FP16, True, 4096.0, dev)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        eng.pack([backbone_rgb[n + ".weight"].to(dev) for n in names], [backbone_rgb[n + ".bias"].to(dev) for n in names],
+                 [backbone_rgb[n + "_bn.weight"].to(dev) for n in names], [backbone_rgb[n + "_bn.bias"].to(dev) for n in names],
+                 [backbone_rgb[n + "_bn.running_mean"].to(dev) for n in names], [backbone_rgb[n + "_bn.running_var"].to(dev) for n in names])
+        feat = eng.forward(x.to(dev))
+        dw = [torch.zeros_like(backbone_rgb[n + ".weight"]).to(dev) for n in names]
+        db = [torch.zeros_like(backbone_rgb[n + ".bias"]).to(dev) for n in names]
+        eng.backward(dfeat.to(dev), dw, db)
+        torch.cuda.synchronize()
+        return feat, dw, db
+
+    f_fast, dw_fast, db_fast = run({"SSNB_DISABLE_UMMA": "0", "SSNB_DISABLE_FUSION": "0"})
+    f_simt, dw_simt, db_simt = run({"SSNB_DISABLE_UMMA": "1"})
+    bb = {k: v.clone() for k, v in backbone_rgb.items()}
+    for k in bb:
+        if "_bn." not in k:
+            bb[k].requires_grad_(True)
+    ref = O.backbone_forward(bb, x, 3)
+    ref.backward(dfeat)
+    e_feat = rel_l2(f_fast, f_simt)
+    e_w = max(rel_l2(a, b) for a, b in zip(dw_fast, dw_simt))
+    e_b = max(rel_l2(a, b) for a, b in zip(db_fast, db_simt))
+    o_feat = rel_l2(f_fast, ref.detach())
+    o_w = sorted(((rel_l2(a, bb[n + ".weight"].grad), n) for a, n in zip(dw_fast, names)), reverse=True)[:3]
+    print("fast fused vs SIMT-fp16: feat %.2e  max dW %.2e  max db %.2e ; vs fp32 oracle: feat %.2e  worst dW %s" % (e_feat, e_w, e_b, o_feat, o_w))
+    assert e_feat < 5e-3 and e_w < 3e-2 and e_b < 3e-2      # same fp16 storage, different accumulation order / ReLU flips
+    assert o_feat < 5e-2                                     # fp16 operand rounding through 69 layers (DESIGN.md §2)
