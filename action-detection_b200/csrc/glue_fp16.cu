@@ -66,24 +66,21 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
   const int ix = (int)(p % W), iy = (int)((p / W) % H);
   const long long f = p / ((long long)W * H);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = 0; r < k; ++r) {
-    const int ty = iy + pad - r;
-    if (ty < 0 || ty % stride) continue;
-    const int oy = ty / stride;
-    if (oy >= OH) continue;
-    for (int s = 0; s < k; ++s) {
-      const int tx = ix + pad - s;
-      if (tx < 0 || tx % stride) continue;
-      const int ox = tx / stride;
-      if (ox >= OW) continue;
+  // windows covering this pixel: oy in [ceil((iy+pad-k+1)/stride), floor((iy+pad)/stride)] (<= 2 per axis for k3/s2)
+  const int ty0 = iy + pad - k + 1, tx0 = ix + pad - k + 1;
+  const int oy_lo = ty0 > 0 ? (ty0 + stride - 1) / stride : 0, oy_hi = min((iy + pad) / stride, OH - 1);
+  const int ox_lo = tx0 > 0 ? (tx0 + stride - 1) / stride : 0, ox_hi = min((ix + pad) / stride, OW - 1);
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    const int r = iy + pad - oy * stride;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const int s = ix + pad - ox * stride;
       const long long op = (f * OH + oy) * OW + ox;
       const uint2 a = __ldg(reinterpret_cast<const uint2*>(argmax + op * C + g * 8));
       const uint32_t tag = (uint32_t)(r * k + s);
-      // any lane of this window pointing here?
       const uint32_t t4 = tag * 0x01010101u;
-      if (((a.x ^ t4) & 0xFFu) && ((a.x ^ t4) & 0xFF00u) && ((a.x ^ t4) & 0xFF0000u) && ((a.x ^ t4) & 0xFF000000u) &&
-          ((a.y ^ t4) & 0xFFu) && ((a.y ^ t4) & 0xFF00u) && ((a.y ^ t4) & 0xFF0000u) && ((a.y ^ t4) & 0xFF000000u))
-        continue;
+      const uint32_t xa = a.x ^ t4, xb = a.y ^ t4;
+      // zero byte test: does any of the 8 channels of this window point at this pixel?
+      if (!(((xa - 0x01010101u) & ~xa & 0x80808080u) | ((xb - 0x01010101u) & ~xb & 0x80808080u))) continue;
       float v[8];
       unpack8(ldg16(ddst + op * dpitch + dcoff + g * 8), v);
 #pragma unroll

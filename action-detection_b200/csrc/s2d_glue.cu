@@ -66,8 +66,10 @@ __global__ void wgrad_finalize_s2d_kernel(const float* __restrict__ partial, int
   dw[i] = acc * mult[co] * out_scale;
 }
 
-// fused input conversion: NCHW fp32 frames -> packed space-to-depth fp16; one thread per (pixel, ds block)
-__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin, int H, int W, __half* __restrict__ dst, int Cs) {
+// fused input conversion: NCHW fp32 frames -> packed space-to-depth fp16; one thread per (pixel, ds block):
+// float2 reads coalesced along x, the Cs-channel block is assembled in registers and stored as 16-byte vectors
+template <int CS>
+__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin, int H, int W, __half* __restrict__ dst) {
   const int H2 = H / 2, W2 = W / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * H2 * W2 * 4) return;
@@ -75,20 +77,23 @@ __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin
   const long long p = i / 4;
   const int x2 = (int)(p % W2), y2 = (int)((p / W2) % H2);
   const long long f = p / ((long long)W2 * H2);
-  __half* o = dst + p * (4 * Cs) + ds * Cs;
+  __align__(16) __half v[CS];
+#pragma unroll
+  for (int c = 0; c < CS; ++c) v[c] = __float2half_rn(0.f);
   const int xs = x2 + ds - 2;
-  if (xs < 0 || xs >= W2) {
-    for (int c = 0; c < Cs; ++c) o[c] = __float2half_rn(0.f);
-    return;
+  if (xs >= 0 && xs < W2) {
+    for (int c = 0; c < Cin; ++c) {
+      const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * xs;
+      const float2 r0 = __ldg(reinterpret_cast<const float2*>(pl));
+      const float2 r1 = __ldg(reinterpret_cast<const float2*>(pl + W));
+      v[0 * Cin + c] = __float2half_rn(r0.x); v[1 * Cin + c] = __float2half_rn(r0.y);
+      v[2 * Cin + c] = __float2half_rn(r1.x); v[3 * Cin + c] = __float2half_rn(r1.y);
+    }
   }
-  for (int c = 0; c < Cin; ++c) {
-    const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * xs;
-    const float2 r0 = *reinterpret_cast<const float2*>(pl);
-    const float2 r1 = *reinterpret_cast<const float2*>(pl + W);
-    o[0 * Cin + c] = __float2half_rn(r0.x); o[1 * Cin + c] = __float2half_rn(r0.y);
-    o[2 * Cin + c] = __float2half_rn(r1.x); o[3 * Cin + c] = __float2half_rn(r1.y);
-  }
-  for (int c = 4 * Cin; c < Cs; ++c) o[c] = __float2half_rn(0.f);
+  uint4* o = reinterpret_cast<uint4*>(dst + p * (4 * CS) + ds * CS);
+  const uint4* vv = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+  for (int q = 0; q < CS / 8; ++q) o[q] = vv[q];
 }
 
 // dst[f, y, x, c] = (y, x both even) ? src[f, y/2, x/2, c] : 0
@@ -116,7 +121,9 @@ int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s) {
 }
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s) {
   const long long n = (long long)F * (H / 2) * (W / 2) * 4;
-  nchw_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst, Cs);
+  if (Cs == 16) nchw_to_s2d_kernel<16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst);
+  else if (Cs == 40) nchw_to_s2d_kernel<40><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst);
+  else { set_thread_error("nchw_to_s2d: unsupported channel count (RGB 3 or Flow 10)"); return 1; }
   SSNB_LAUNCH_CHECK("nchw_to_s2d_kernel");
   return 0;
 }

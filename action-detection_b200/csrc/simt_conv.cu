@@ -262,18 +262,19 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
   }
 }
 
+// threads enumerate the partial layout [tap][co][ci] (coalesced reads of every split), write the reference
+// layout [co][ci][tap]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin,
                                       const float* __restrict__ mult, float out_scale, float* __restrict__ dw) {
   const long long total = (long long)taps * Cout * Cin;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  // i enumerates the reference layout [co][ci][tap]
-  const int tap = (int)(i % taps);
-  const int ci = (int)((i / taps) % Cin);
-  const int co = (int)(i / ((long long)taps * Cin));
+  const int ci = (int)(i % Cin);
+  const int co = (int)((i / Cin) % Cout);
+  const int tap = (int)(i / ((long long)Cin * Cout));
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += partial[(((long long)sp * taps + tap) * Cout + co) * Cin + ci];
-  dw[i] = s * mult[co] * out_scale;
+  for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * total + i];
+  dw[((long long)co * Cin + ci) * taps + tap] = s * mult[co] * out_scale;
 }
 
 // column sums of dz: stage 1 partial[split][c], stage 2 db[c] = mult[c]*out_scale*sum
