@@ -352,7 +352,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   float* dbp = (e->db.size() && e->db[o.conv]) ? e->db[o.conv] : nullptr;
   if (e->fp16) {
     // one pass: ReLU gradient mask in place + bias-gradient column sums
-    if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, 1024 * 512 / y.C, dbp, s))) return rc;
+    if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, s))) return rc;
   } else {
     if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
     if (dbp) {
@@ -449,6 +449,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
   if (((uintptr_t)dev_ptr) % 1024) return h->fail(SSNB_EINVAL, "workspace must be 1024-byte aligned");
   h->ws = (char*)dev_ptr;
   h->weights_ready = false;
+  if (h->fp16 && cudaMemset(h->ws + h->bpartial_off, 0, 256) != cudaSuccess) { cudaGetLastError(); /* no device (CPU-only planning) */ }
   // bind tcgen05 plans (tensor maps need final addresses); SSNB_DISABLE_UMMA=1 keeps FAST mode on the SIMT kernels
   const char* dis = getenv("SSNB_DISABLE_UMMA");
   const bool use_umma = h->fp16 && !(dis && dis[0] == '1');

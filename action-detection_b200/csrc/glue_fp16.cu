@@ -100,38 +100,51 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
   *reinterpret_cast<uint4*>(q) = pack8(acc);
 }
 
+// 3x3/1 average (count_include_pad, /9): one thread per (frame, column x, 8-channel group) walks down the
+// rows keeping the horizontal 3-sums of the last three rows -> 3 loads per output instead of 9
 __global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
                             __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
   const int G = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)F * H * W * G) return;
+  if (i >= (long long)F * W * G) return;
   const int g = (int)(i % G);
-  const long long p = i / G;
-  const int x = (int)(p % W), y = (int)((p / W) % H);
-  const long long f = p / ((long long)W * H);
-  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = -1; r <= 1; ++r) {
-    const int yy = y + r;
-    if (yy < 0 || yy >= H) continue;
+  const int x = (int)((i / G) % W);
+  const long long f = i / ((long long)G * W);
+  float prev[8], cur[8], nxt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
+  auto rowsum = [&](int y, float* o) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    if (y >= H) return;
+    const __half* base = src + ((f * H + y) * W) * spitch + scoff + g * 8;
+#pragma unroll
     for (int q = -1; q <= 1; ++q) {
       const int xx = x + q;
       if (xx < 0 || xx >= W) continue;
       float v[8];
-      unpack8(ldg16(src + ((f * H + yy) * W + xx) * spitch + scoff + g * 8), v);
+      unpack8(ldg16(base + (long long)xx * spitch), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += v[j];
+      for (int j = 0; j < 8; ++j) o[j] += v[j];
     }
-  }
+  };
+  rowsum(0, cur);
+  for (int y = 0; y < H; ++y) {
+    rowsum(y + 1, nxt);
+    float s[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = s[j] / 9.0f;
-  __half* o = dst + p * dpitch + dcoff + g * 8;
-  if (accumulate) {
-    float old[8];
-    unpack8(*reinterpret_cast<const uint4*>(o), old);
+    for (int j = 0; j < 8; ++j) s[j] = (prev[j] + cur[j] + nxt[j]) / 9.0f;
+    __half* o = dst + ((f * H + y) * W + x) * dpitch + dcoff + g * 8;
+    if (accumulate) {
+      float old[8];
+      unpack8(*reinterpret_cast<const uint4*>(o), old);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] += old[j];
+      for (int j = 0; j < 8; ++j) s[j] += old[j];
+    }
+    *reinterpret_cast<uint4*>(o) = pack8(s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { prev[j] = cur[j]; cur[j] = nxt[j]; }
   }
-  *reinterpret_cast<uint4*>(o) = pack8(s);
 }
 
 // fused ReLU gradient mask + bias-gradient column sums: dz = dy * (y > 0) in place; partial[cta][c] = sum_rows dz
@@ -139,8 +152,11 @@ constexpr int MB_THREADS = 256;
 __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ dy, int dpitch, int dcoff,
                                                            const __half* __restrict__ y, int ypitch, int ycoff,
                                                            long long rows, int C, long long rows_per_cta,
-                                                           float* __restrict__ partial) {
+                                                           float* __restrict__ partial, unsigned* __restrict__ counter,
+                                                           const float* __restrict__ mult, float out_scale,
+                                                           float* __restrict__ db) {
   extern __shared__ float red[];                 // [lanes][C]
+  __shared__ bool is_last;
   const int G = C / 8;
   const int lanes = MB_THREADS / G;               // row lanes per CTA (G <= 64)
   const int g = threadIdx.x % G, rl = threadIdx.x / G;
@@ -148,18 +164,31 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
   const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < lanes) {
-    for (long long r = r0 + rl; r < r1; r += lanes) {
-      __half* pd = dy + r * dpitch + dcoff + g * 8;
-      float d[8], a[8];
-      unpack8(*reinterpret_cast<const uint4*>(pd), d);
-      unpack8(ldg16(y + r * ypitch + ycoff + g * 8), a);
-      bool changed = false;
+    constexpr int U = 4;                          // rows in flight per thread
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * U) {
+      uint4 dv[U], yv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
-        acc[j] += d[j];
+      for (int u = 0; u < U; ++u) {
+        const long long r = rb + (long long)u * lanes;
+        if (r < r1) {
+          dv[u] = *reinterpret_cast<const uint4*>(dy + r * dpitch + dcoff + g * 8);
+          yv[u] = ldg16(y + r * ypitch + ycoff + g * 8);
+        }
       }
-      if (changed) *reinterpret_cast<uint4*>(pd) = pack8(d);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = rb + (long long)u * lanes;
+        if (r >= r1) continue;
+        float d[8], a[8];
+        unpack8(dv[u], d); unpack8(yv[u], a);
+        bool changed = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
+          acc[j] += d[j];
+        }
+        if (changed) *reinterpret_cast<uint4*>(dy + r * dpitch + dcoff + g * 8) = pack8(d);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[rl * C + g * 8 + j] = acc[j];
@@ -170,18 +199,23 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
     for (int l = 0; l < lanes; ++l) s += red[l * C + c];
     partial[(long long)blockIdx.x * C + c] = s;
   }
-}
-
-// one warp per channel: lanes stride over the CTA partials (fixed order per lane + fixed shuffle tree = deterministic)
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int n, int C, const float* __restrict__ mult,
-                                    float out_scale, float* __restrict__ db) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int i = lane; i < n; i += 32) s += partial[(long long)i * C + c];
+  if (!db) return;
+  // the last CTA to finish reduces the per-CTA partials in CTA order (deterministic) into db
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int c = warp; c < C; c += MB_THREADS / 32) {
+    float s = 0.f;
+    for (int i = lane; i < (int)gridDim.x; i += 32) s += __ldcg(partial + (long long)i * C + c);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0 && db) db[c] = s * mult[c] * out_scale;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) db[c] = s * mult[c] * out_scale;
+  }
+  if (threadIdx.x == 0) *counter = 0;             // ready for the next launch on this stream
 }
 
 }  // namespace
@@ -205,8 +239,8 @@ int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pa
   return 0;
 }
 int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s) {
-  const long long n = (long long)F * src.H * src.W * (src.C / 8);
-  avgpool3_h8<<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
+  const long long n = (long long)F * src.W * (src.C / 8);
+  avgpool3_h8<<<nblk(n, 128), 128, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
   SSNB_LAUNCH_CHECK("avgpool3_h8");
   return 0;
 }
@@ -222,12 +256,11 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
   const long long rpc = (rows + ctas - 1) / ctas;
   ctas = (int)((rows + rpc - 1) / rpc);
   const int lanes = MB_THREADS / (C / 8);
-  mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dy), dy.pitch, dy.coff, HP(y), y.pitch, y.coff, rows, C, rpc, partial);
+  unsigned* counter = reinterpret_cast<unsigned*>(partial);          // first 256 bytes of the scratch: completion counter
+  float* part = partial + 64;
+  mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dy), dy.pitch, dy.coff, HP(y), y.pitch, y.coff, rows, C, rpc, part,
+                                                              counter, mult, out_scale, db);
   SSNB_LAUNCH_CHECK("mask_bias_h8");
-  if (db) {
-    colsum_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(partial, ctas, C, mult, out_scale, db);
-    SSNB_LAUNCH_CHECK("colsum_final_kernel");
-  }
   return 0;
 }
 

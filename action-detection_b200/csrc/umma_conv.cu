@@ -18,13 +18,13 @@ namespace ssnb {
 namespace {
 
 using namespace umma;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
+constexpr int PIPE_BYTES = 4 * (BLOCK_M * BLOCK_K * 2 + 256 * BLOCK_K * 2);   // 192 KiB of operand staging
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KiB
 constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct TileCoord { int w0, h0, f0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const UmmaConvParams& p, int tile) {
@@ -44,12 +44,14 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2] accumulator ready
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  // pipeline depth adapts to the tile: narrow-N layers get up to 8 stages in the same 192 KiB
+  const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES);
+  uint64_t* full_bar = bars;                     // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;       // [MAX_STAGES]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
@@ -257,6 +259,8 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.block_n = (((N + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
   p.kchunks = (K + BLOCK_K - 1) / BLOCK_K;
   p.K = K;
+  p.stage_bytes = (A_BYTES + p.block_n * BLOCK_K * 2 + 1023) / 1024 * 1024;
+  p.stages = PIPE_BYTES / p.stage_bytes; if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.ntaps = ntaps;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
   p.out_stride = out_stride; p.OH = o.H; p.OW = o.W;

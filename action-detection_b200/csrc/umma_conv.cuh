@@ -27,6 +27,7 @@ struct UmmaConvParams {
   int bw, bh, bf;                 // TMA box in pixels; bw*bh*bf <= 128 rows of the M tile
   int tiles_w, tiles_h, tiles_f;
   int n_tiles, block_n;           // N split of Cout
+  int stages, stage_bytes;        // smem pipeline depth / stride chosen from block_n
   int kchunks, ntaps, K;          // ceil(K/64), filter taps, reduction channels per tap
   int tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   __half* out; int out_pitch, out_coff, Cout;

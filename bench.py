@@ -72,12 +72,32 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def usable_cores():
+    """threads the host really grants this process: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def cpu_reference(steps, warmup, videos=2):
     """The reference's CPU PyTorch path for this workload, restated by the oracle (the reference
     scripts do not parse on py3.12), all host threads, bounded sample."""
     import torch
     from oracle import ssn_oracle as O, synth
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cores())
     bb = synth.synth_backbone(3, seed=0, calib_frames=2)
     hd = synth.synth_heads(K_CLASSES, 5, seed=0)
     for d in (bb, hd):
@@ -108,7 +128,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(max(1, min(args.steps, 3)), max(0, min(args.warmup, 1)))
+    r = cpu_reference(max(1, min(args.steps, 2)), max(0, min(args.warmup, 1)))
     line = {"impl": "reference", "metric": "proposals/sec (9-seg BNInception SSN fwd+bwd)", "value": r["value"],
             "unit": "proposals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -297,7 +317,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(2, 1)
+        r = cpu_reference(1, 1)
         cpu = {"value": r["value"], "unit": "proposals/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:

@@ -525,3 +525,45 @@ def test_fast_fused_vs_unfused_and_oracle(backbone_rgb):
     # test_ssn_train_exact_vs_oracle for a 1e-5 forward difference).  Reported, bounded loosely; the
     # per-kernel bound is test_backbone_per_layer[fast].
     assert o_feat < 5e-2 and o_w[0][0] < 1.0
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_flow_conv1_fwd_bwd(precision):
+    """Flow modality (10-channel stacked flow, ssn_models.py:318-343): the first convolution is the only
+    layer whose geometry changes; forward + weight/bias gradient per kernel boundary, and the whole
+    backbone forward in FAST mode through the packed space-to-depth input path."""
+    dev = _cuda()
+    from ssn_b200 import _lib
+    from ssn_b200.engine import BackboneEngine
+    Fn = 4
+    bb = synth.synth_backbone(10, seed=1, calib_frames=2)
+    names = [n for (n, *_r) in O.conv_layers(10)]
+    x = synth.synth_frames(Fn, 10, seed=2)
+    w = bb["conv1_7x7_s2.weight"].clone().requires_grad_(True)
+    b = bb["conv1_7x7_s2.bias"].clone().requires_grad_(True)
+    Fnn = torch.nn.functional
+    z = Fnn.conv2d(x, w, b, 2, 3)
+    y = Fnn.relu(Fnn.batch_norm(z, bb["conv1_7x7_s2_bn.running_mean"], bb["conv1_7x7_s2_bn.running_var"],
+                                bb["conv1_7x7_s2_bn.weight"], bb["conv1_7x7_s2_bn.bias"], False, 0.1, 1e-5))
+    g = torch.Generator().manual_seed(3)
+    gy = torch.randn(y.shape, generator=g) * 0.01
+    y.backward(gy)
+    prec = _lib.EXACT_FP32 if precision == "exact" else _lib.FAST_FP16
+    tol = 2e-5 if precision == "exact" else 3e-3
+    eng = BackboneEngine(10, Fn, prec, True, 1024.0, dev)
+    eng.pack([bb[n + ".weight"].to(dev) for n in names], [bb[n + ".bias"].to(dev) for n in names],
+             [bb[n + "_bn.weight"].to(dev) for n in names], [bb[n + "_bn.bias"].to(dev) for n in names],
+             [bb[n + "_bn.running_mean"].to(dev) for n in names], [bb[n + "_bn.running_var"].to(dev) for n in names])
+    dw = [torch.zeros_like(bb[n + ".weight"]).to(dev) for n in names]
+    db = [torch.zeros_like(bb[n + ".bias"]).to(dev) for n in names]
+    eng.bind_grads(dw, db)
+    eng.write("data", x.to(dev))
+    eng.run_op(0, backward=False)
+    assert rel_l2(eng.read("conv1_7x7_s2_bn"), y.detach()) < tol
+    eng.write("conv1_7x7_s2_bn", y.detach().to(dev))
+    eng.write("conv1_7x7_s2_bn", gy.to(dev), grad=True)
+    eng.run_op(0, backward=True)
+    assert rel_l2(dw[0], w.grad) < 2 * tol and rel_l2(db[0], b.grad) < 2 * tol
+    feat = eng.forward(x.to(dev))
+    ref = O.backbone_forward(bb, x, 10)
+    assert rel_l2(feat, ref) < (1e-4 if precision == "exact" else 5e-2)
