@@ -207,13 +207,16 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  for (int c = warp; c < C; c += MB_THREADS / 32) {
-    float s = 0.f;
-    for (int i = lane; i < (int)gridDim.x; i += 32) s += __ldcg(partial + (long long)i * C + c);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) db[c] = s * mult[c] * out_scale;
+  const int n = (int)gridDim.x;
+  for (int c = threadIdx.x; c < C; c += MB_THREADS) {      // coalesced across threads, 4 independent chains per thread
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+      s0 += __ldcg(partial + (long long)i * C + c);       s1 += __ldcg(partial + (long long)(i + 1) * C + c);
+      s2 += __ldcg(partial + (long long)(i + 2) * C + c); s3 += __ldcg(partial + (long long)(i + 3) * C + c);
+    }
+    for (; i < n; ++i) s0 += __ldcg(partial + (long long)i * C + c);
+    db[c] = ((s0 + s1) + (s2 + s3)) * mult[c] * out_scale;
   }
   if (threadIdx.x == 0) *counter = 0;             // ready for the next launch on this stream
 }
@@ -251,6 +254,7 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
   const int C = dy.C;
   if (C % 8 || C / 8 > 64) { set_thread_error("mask_bias: C must be a multiple of 8 and <= 512"); return 1; }
   int ctas = (int)((rows + 255) / 256);
+  if (ctas > 296) ctas = 296;                      // two CTAs per SM: enough to saturate HBM, short final reduction
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   const long long rpc = (rows + ctas - 1) / ctas;

@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grad-scale", type=float, default=4096.0)
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the training step in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,13 +195,44 @@ def main():
     host_batches = [tuple(t.pin_memory() for t in synth.synth_batch(VIDEOS_PER_GPU, K_CLASSES, 3, seed=100 * rank + i)) for i in range(nb)]
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(batch):
+    def eager_step(batch):
         flat_grad.zero_()
         losses = model.fused_step(*batch, global_videos=VIDEOS_PER_GPU * world, loss_scale=1.0 / world)
         if world > 1:
             dist.all_reduce(flat_grad)
         opt.step()
         return losses
+
+    # The whole step (~420 kernel launches + all-reduce + optimizer + weight re-pack) is captured once in a
+    # CUDA graph and replayed; the step's inputs are copied into the graph's static input tensors.
+    step, used_graph = eager_step, False
+    if not args.no_graph:
+        try:
+            static_batch = tuple(torch.empty_like(t) for t in batches[0])
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    for d_, s_ in zip(static_batch, batches[i % nb]):
+                        d_.copy_(s_)
+                    eager_step(static_batch)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_losses = eager_step(static_batch)
+
+            def graph_step(batch):
+                for d_, s_ in zip(static_batch, batch):
+                    d_.copy_(s_)
+                graph.replay()
+                return static_losses
+            step, used_graph = graph_step, True
+        except Exception as ex:          # capture not possible on this stack: stay eager, say so
+            if rank == 0:
+                print("CUDA graph capture failed, running eagerly: %r" % (ex,), file=sys.stderr)
+            torch.cuda.synchronize()
+            step, used_graph = eager_step, False
 
     def barrier():
         if world > 1:
@@ -220,6 +252,9 @@ def main():
             ev[2 * i + 1].record()
         barrier()
     launches = _lib.lib.ssnb_global_launch_count() - launches0
+    if used_graph:      # replays do not pass through the library's counter: count one eager step and scale
+        l0 = _lib.lib.ssnb_global_launch_count(); eager_step(batches[0]); torch.cuda.synchronize()
+        launches = (_lib.lib.ssnb_global_launch_count() - l0) * args.steps
     ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -329,7 +364,7 @@ def main():
                                        "fwd+bwd (+allreduce+SGD+repack), K=20, STPP (1,(1,2),1), dropout 0, frozen BN",
                            "global_batch_proposals": props_step, "frames_per_gpu": VIDEOS_PER_GPU * PROPS * SEG,
                            "parallelism": "dp%d" % world, "precision": args.precision, "l2": "flushed between timed steps (256 MiB write)",
-                           "grad_scale": args.grad_scale},
+                           "grad_scale": args.grad_scale, "cuda_graph": used_graph},
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
                 "tflops_step": FLOP_PER_FRAME_FWDBWD * VIDEOS_PER_GPU * PROPS * SEG / (ms_total / args.steps / 1e3) / 1e12,
                 "losses": [float(v) for v in losses.tolist()],
