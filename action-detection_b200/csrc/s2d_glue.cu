@@ -96,19 +96,21 @@ __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin
   for (int q = 0; q < CS / 8; ++q) o[q] = vv[q];
 }
 
-// dst[f, y, x, c] = (y, x both even) ? src[f, y/2, x/2, c] : 0
+// dst[f, y, x, c] = (y, x both even) ? src[f, y/2, x/2, c] : 0      (8 channels = 16 bytes per thread)
 __global__ void upsample2_zero_kernel(const __half* __restrict__ src, int OH, int OW, int C, int spitch, int scoff,
                                       __half* __restrict__ dst, int H, int W, int F) {
-  const long long total = (long long)F * H * W * C;
+  const int G = C / 8;
+  const long long total = (long long)F * H * W * G;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c = (int)(i % C);
-  const long long p = i / C;
+  const int g = (int)(i % G);
+  const long long p = i / G;
   const int x = (int)(p % W), y = (int)((p / W) % H);
   const long long f = p / ((long long)W * H);
-  __half v = __float2half_rn(0.f);
-  if (!(x & 1) && !(y & 1) && y / 2 < OH && x / 2 < OW) v = src[((f * OH + y / 2) * OW + x / 2) * spitch + scoff + c];
-  dst[i] = v;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (!(x & 1) && !(y & 1) && y / 2 < OH && x / 2 < OW)
+    v = __ldg(reinterpret_cast<const uint4*>(src + ((f * OH + y / 2) * OW + x / 2) * spitch + scoff + g * 8));
+  *reinterpret_cast<uint4*>(dst + p * C + g * 8) = v;
 }
 
 }  // namespace
@@ -141,7 +143,7 @@ int launch_wgrad_finalize_s2d(const float* partial, int splits, int Cout, int Ci
   return 0;
 }
 int launch_upsample2_zero(View src, __half* dst, int H, int W, int F, cudaStream_t s) {
-  const long long n = (long long)F * H * W * src.C;
+  const long long n = (long long)F * H * W * (src.C / 8);
   upsample2_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const __half*)src.base, src.H, src.W, src.C, src.pitch, src.coff, dst, H, W, F);
   SSNB_LAUNCH_CHECK("upsample2_zero_kernel");
   return 0;
