@@ -70,6 +70,30 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
   const int ty0 = iy + pad - k + 1, tx0 = ix + pad - k + 1;
   const int oy_lo = ty0 > 0 ? (ty0 + stride - 1) / stride : 0, oy_hi = min((iy + pad) / stride, OH - 1);
   const int ox_lo = tx0 > 0 ? (tx0 + stride - 1) / stride : 0, ox_hi = min((ix + pad) / stride, OW - 1);
+  if (oy_hi - oy_lo <= 1 && ox_hi - ox_lo <= 1) {
+    // stride-2 pools: at most 2x2 covering windows -> issue every load before the first use (memory-level parallelism)
+    uint2 am[4]; uint4 dv[4]; uint32_t tg[4]; bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int oy = oy_lo + (q >> 1), ox = ox_lo + (q & 1);
+      ok[q] = oy <= oy_hi && ox <= ox_hi;
+      const long long op = (f * OH + (ok[q] ? oy : oy_lo)) * OW + (ok[q] ? ox : ox_lo);
+      tg[q] = (uint32_t)((iy + pad - oy * stride) * k + (ix + pad - ox * stride));
+      am[q] = __ldg(reinterpret_cast<const uint2*>(argmax + op * C + g * 8));
+      dv[q] = ldg16(ddst + op * dpitch + dcoff + g * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!ok[q]) continue;
+      float v[8];
+      unpack8(dv[q], v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (((am[q].x >> (8 * j)) & 0xFFu) == tg[q]) acc[j] += v[j];
+        if (((am[q].y >> (8 * j)) & 0xFFu) == tg[q]) acc[4 + j] += v[4 + j];
+      }
+    }
+  } else {
   for (int oy = oy_lo; oy <= oy_hi; ++oy) {
     const int r = iy + pad - oy * stride;
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
@@ -89,6 +113,7 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
         if (((a.y >> (8 * j)) & 0xFFu) == tag) acc[4 + j] += v[4 + j];
       }
     }
+  }
   }
   __half* q = dsrc + p * spitch + scoff + g * 8;
   if (accumulate) {
@@ -164,7 +189,7 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
   const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < lanes) {
-    constexpr int U = 4;                          // rows in flight per thread
+    constexpr int U = 8;                          // rows in flight per thread
     for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * U) {
       uint4 dv[U], yv[U];
 #pragma unroll
@@ -254,7 +279,7 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
   const int C = dy.C;
   if (C % 8 || C / 8 > 64) { set_thread_error("mask_bias: C must be a multiple of 8 and <= 512"); return 1; }
   int ctas = (int)((rows + 255) / 256);
-  if (ctas > 296) ctas = 296;                      // two CTAs per SM: enough to saturate HBM, short final reduction
+  if (ctas > 444) ctas = 444;                      // three CTAs per SM: enough to saturate HBM, short final reduction
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   const long long rpc = (rows + ctas - 1) / ctas;

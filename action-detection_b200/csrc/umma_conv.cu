@@ -8,6 +8,7 @@
 // Rows of the M tile are the pixels of one TMA box (bw x bh x bf); taps shift the box origin and
 // rely on TMA's out-of-bounds zero fill for the convolution padding.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "umma_conv.cuh"
@@ -88,7 +89,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (kc < p.kchunks_a1) tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
+            if (kc < p.kchunks_a1) tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, t.w0 * p.a_stride + p.tap_dx[tap], t.h0 * p.a_stride + p.tap_dy[tap], t.f0);
             else tma_load_4d(sa, &tmap_a2, &full_bar[stage], (kc - p.kchunks_a1) * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
             tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, t.n0, tap);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -220,8 +221,9 @@ int resolve_encode(UmmaContext& ctx) {
 }
 
 int encode(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box) {
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+           const cuuint32_t* box, int spatial_stride = 1) {
+  // spatial_stride 2: the box traverses W and H with step 2 (box extents are given in un-strided elements)
+  cuuint32_t es[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx.encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, addr, dims, strides,
                                                                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -242,9 +244,25 @@ void pick_box(int W, int& bw, int& bh, int& bf) {
   else { bw = 1; bh = 1; bf = 128; }
 }
 
-int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int K, int N, int ntaps, int out_stride, const __half* w) {
+int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int K, int N, int ntaps, int out_stride, const __half* w,
+                int a_stride = 1) {
   plan.enabled = false;
   if (int rc = resolve_encode(ctx)) return rc;
+  if (a_stride == 2) {
+    // strided TMA: tiles enumerate OUTPUT pixels, the A box steps over the input with stride 2
+    View ao = a; ao.H = o.H; ao.W = o.W;
+    if (int rc = bind_common(ctx, plan, ao, o, F, K, N, ntaps, 1, w, 1)) return rc;
+    plan.enabled = false;
+    UmmaConvParams& q = plan.p;
+    q.a_stride = 2;
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)F};
+    cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(2 * q.bw), (cuuint32_t)(2 * q.bh), (cuuint32_t)q.bf};
+    if (int rc = encode(ctx, &plan.tmap_a, 4, reinterpret_cast<__half*>(a.base) + a.coff, dims, str, box, 2)) return rc;
+    plan.tmap_a2 = plan.tmap_a;
+    plan.enabled = true;
+    return 0;
+  }
   if ((a.H + out_stride - 1) / out_stride != o.H || (a.W + out_stride - 1) / out_stride != o.W) { set_thread_error("umma conv: geometry mismatch"); return 1; }
   if (K % 8 || N % 16 || a.pitch % 8 || a.coff % 8 || o.pitch % 8 || o.coff % 8 || ntaps > UMMA_MAX_TAPS) {
     set_thread_error("umma conv: unsupported channel alignment"); return 1; }
@@ -263,7 +281,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.stages = PIPE_BYTES / p.stage_bytes; if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.ntaps = ntaps;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
-  p.out_stride = out_stride; p.OH = o.H; p.OW = o.W;
+  p.out_stride = out_stride; p.OH = o.H; p.OW = o.W; p.a_stride = 1;
   p.kchunks_a1 = (K + BLOCK_K - 1) / BLOCK_K; p.K1 = K; p.n_split = 1 << 30; p.out2 = p.out; p.out2_pitch = o.pitch; p.out2_coff = o.coff;
   {
     cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)F};
@@ -286,8 +304,8 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
 
 int umma_resolve_encode(UmmaContext& ctx) { return resolve_encode(ctx); }
 int umma_encode_f16(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, const cuuint64_t* dims,
-                    const cuuint64_t* strides, const cuuint32_t* box) {
-  return encode(ctx, m, rank, addr, dims, strides, box);
+                    const cuuint64_t* strides, const cuuint32_t* box, int spatial_stride) {
+  return encode(ctx, m, rank, addr, dims, strides, box, spatial_stride);
 }
 
 void umma_context_init(UmmaContext& ctx, bool fp16) { ctx.active = fp16; }
@@ -303,8 +321,12 @@ int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out,
 
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
                        int stride, const __half* w_tap_n_k, const float* bias) {
-  // a stride-2 layer (k=3, pad=1) is the stride-1 convolution sampled at even pixels
-  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, k * k, stride, w_tap_n_k)) return rc;
+  // a stride-2 layer (k=3, pad=1): either the stride-1 convolution sampled at even pixels (4x redundant MMAs) or,
+  // with SSNB_TMA_STRIDED=1, tiles over output pixels whose A boxes step over the input with TMA element stride 2
+  const char* st = getenv("SSNB_TMA_STRIDED");
+  const bool strided = stride == 2 && st && st[0] == '1';
+  if (int rc = strided ? bind_common(ctx, plan, in, out, F, cin, cout, k * k, 1, w_tap_n_k, 2)
+                       : bind_common(ctx, plan, in, out, F, cin, cout, k * k, stride, w_tap_n_k)) return rc;
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = r - pad; plan.p.tap_dx[r * k + s] = s - pad; }
   plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;

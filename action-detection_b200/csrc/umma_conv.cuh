@@ -32,6 +32,7 @@ struct UmmaConvParams {
   int tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   __half* out; int out_pitch, out_coff, Cout;
   int out_stride, OH, OW;         // stride-2 layers: tiles run at input resolution, only even pixels are stored
+  int a_stride;                   // 2: tiles run at OUTPUT resolution and the A box uses TMA element stride 2
   const float* bias;              // [Cout] or nullptr
   int relu, accumulate;
   // horizontal fusion of sibling 1x1 convolutions (same input):
@@ -68,7 +69,7 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s)
 // host helpers shared by the tensor-core kernels
 int umma_resolve_encode(UmmaContext& ctx);
 int umma_encode_f16(UmmaContext& ctx, CUtensorMap* m, int rank, void* addr, const cuuint64_t* dims,
-                    const cuuint64_t* strides, const cuuint32_t* box);
+                    const cuuint64_t* strides, const cuuint32_t* box, int spatial_stride = 1);
 
 // ---- weight gradient on tcgen05 (umma_wgrad.cu) -------------------------------------------------------
 // partial[split][tap][co][ci] = sum over the split's pixels of dz[p, co] * x[p + (r-pad, s-pad), ci]

@@ -371,9 +371,14 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                         "steps": e2e_steps, "path": "SSN.forward + CrossEntropy/CompletenessLoss/ClassWiseRegressionLoss + backward + SGD from pinned host tensors, H2D double-buffered on a copy stream, loss.item() every step"},
                 "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # all ranks leave together; skip NCCL/graph teardown (it can block when a captured graph holds the
+        # communicator) — the process is done
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
