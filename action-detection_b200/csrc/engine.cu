@@ -66,6 +66,8 @@ struct Op {
   UmmaConvPlan umma;        // tcgen05 forward plan (FAST mode, stride-1 layers)
   UmmaConvPlan umma_dgrad;  // tcgen05 data-gradient plan
   UmmaWgradPlan umma_wgrad; // tcgen05 weight-gradient plan
+  int pool_consumer = -1;   // conv whose only consumer is a k3/s2 max pool: that pool's op index (backward gather is folded in)
+  bool folded_into_conv = false;   // max pool whose backward runs inside its producer conv's mask+bias pass
   int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
   int fuse_block = -1;
 };
@@ -97,6 +99,7 @@ struct ssnb_engine {
   std::vector<FusedBlock> fused;
   size_t ws_bytes = 0, partial_off = 0, partial_bytes = 0, bpartial_off = 0;
   size_t s2d_off = 0, s2d_w_off = 0, up_off = 0;   // FAST mode: space-to-depth input + weights, zero-upsampled dz
+  bool fold_pools = true;                            // SSNB_DISABLE_FUSION=1 also keeps the max-pool backward separate
   bool s2d_ready = false;                            // backbone_fwd converted the input directly
   int Cs = 0;                                        // channels of the space-to-depth input (4*Cin rounded up to 8)
   char* ws = nullptr;
@@ -260,6 +263,16 @@ static void plan(ssnb_engine* e) {
       fb.w_dg = off; off = align_up(off + (size_t)fb.cx * kf * 2, 1024);
       e->fused.push_back(fb);
     }
+    for (int i = 0; i < (int)e->ops.size(); ++i) {
+      Op& po = e->ops[i];
+      if (po.kind != OP_MAXPOOL || po.k != 3 || po.stride != 2) continue;
+      int producer = -1, consumers = 0;
+      for (int j = 0; j < (int)e->ops.size(); ++j) {
+        if (e->ops[j].out_val == po.in_val && e->ops[j].kind == OP_CONV) producer = j;
+        if (e->ops[j].in_val == po.in_val) ++consumers;
+      }
+      if (producer >= 0 && consumers == 1 && e->vals[po.in_val].C % 8 == 0) { e->ops[producer].pool_consumer = i; po.folded_into_conv = true; }
+    }
     e->Cs = (4 * e->cfg.in_channels + 7) / 8 * 8;
     e->s2d_off = off; off = align_up(off + F * 112 * 112 * 4 * e->Cs * 2, 1024);   // packed: 4 horizontal neighbours per pixel
     e->s2d_w_off = off; off = align_up(off + (size_t)16 * 64 * e->Cs * 2, 1024);
@@ -319,7 +332,7 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
   return SSNB_EINVAL;
 }
 
-static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t s, bool skip_dgrad = false) {
+static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t s, bool skip_dgrad = false, bool full = false) {
   const int F = e->F;
   const float gs = e->fp16 ? e->cfg.grad_scale : 1.0f;
   int rc = 0;
@@ -329,6 +342,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     return DISPATCH(e, launch_gpool_bwd<float>(dfeat, gs, din, F, s), launch_gpool_bwd<__half>(dfeat, gs, din, F, s));
   }
   if (o.kind == OP_MAXPOOL) {
+    if (full && e->fp16 && e->fold_pools && o.folded_into_conv) return 0;      // gathered by the producer conv's mask+bias pass
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
     const uint8_t* am = (const uint8_t*)(e->ws + o.argmax_off);
     if (e->fp16 && din.C % 8 == 0) return launch_maxpool_bwd_h8(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s);
@@ -350,7 +364,12 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   float* bpartial = (float*)(e->ws + e->bpartial_off);
   const long long M = (long long)F * y.H * y.W;
   float* dbp = (e->db.size() && e->db[o.conv]) ? e->db[o.conv] : nullptr;
-  if (e->fp16) {
+  if (e->fp16 && full && e->fold_pools && o.pool_consumer >= 0) {
+    // max-pool backward gather + ReLU mask + bias-gradient column sums in one pass (dy is never materialised)
+    const Op& po = e->ops[o.pool_consumer];
+    if ((rc = launch_pool_mask_bias_h8(dy, y, e->view(po.out_val, true), F, po.k, po.stride, po.pad, (const uint8_t*)(e->ws + po.argmax_off),
+                                       scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, s))) return rc;
+  } else if (e->fp16) {
     // one pass: ReLU gradient mask in place + bias-gradient column sums
     if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, s))) return rc;
   } else {
@@ -360,7 +379,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
       if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, dbp, s))) return rc;
     }
   }
-  if (e->fp16 && c.stride == 2 && o.conv != 0 && (o.umma_wgrad.enabled || o.umma_dgrad.enabled))
+  if (e->fp16 && c.stride == 2 && o.conv != 0 && o.umma_dgrad.enabled && !skip_dgrad)
     if ((rc = launch_upsample2_zero(dy, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;   // dz at input resolution
   if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
     if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s))) return rc;
@@ -489,12 +508,15 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
                               (const __half*)(h->ws + h->packed[o.conv].wf), o.grad_accumulate);
     if (rc) return h->fail(rc, "umma_conv_bind_dgrad(" + c.id + "): " + ssnb::thread_error());
     if (use_wgrad) {
-      rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, dz, in, h->F, c.cin, c.cout, c.k, c.pad, (float*)(h->ws + h->partial_off), o.wsplits);
+      // stride-2 layers: dz at its own (output) resolution, the x boxes step over the input with element stride 2
+      rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), in, h->F, c.cin, c.cout, c.k, c.pad,
+                           (float*)(h->ws + h->partial_off), o.wsplits, c.stride);
       if (rc) return h->fail(rc, "umma_wgrad_bind(" + c.id + "): " + ssnb::thread_error());
     }
   }
   // horizontal fusion of the sibling 1x1 convolutions of each inception block (SSNB_DISABLE_FUSION=1 turns it off)
   const char* disf = getenv("SSNB_DISABLE_FUSION");
+  h->fold_pools = !(disf && disf[0] == '1');
   for (Op& o : h->ops) { o.fuse_role = 0; o.fuse_block = -1; }
   for (size_t bi = 0; bi < h->fused.size(); ++bi) {
     FusedBlock& fb = h->fused[bi];
@@ -604,7 +626,7 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
     const Op& o = h->ops[i];
-    int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0);   // siblings: mask/bias/wgrad only ...
+    int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
     if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s);   // ... one fused data gradient
     if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
   }

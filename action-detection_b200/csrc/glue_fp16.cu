@@ -174,6 +174,30 @@ __global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C,
 
 // fused ReLU gradient mask + bias-gradient column sums: dz = dy * (y > 0) in place; partial[cta][c] = sum_rows dz
 constexpr int MB_THREADS = 256;
+// the last CTA to finish reduces the per-CTA partials in CTA order (deterministic) into db
+__device__ __forceinline__ void colsum_tail(float* __restrict__ partial, unsigned* __restrict__ counter, int C,
+                                            const float* __restrict__ mult, float out_scale, float* __restrict__ db,
+                                            bool* is_last) {
+  if (!db) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!*is_last) return;
+  __threadfence();
+  const int n = (int)gridDim.x;
+  for (int c = threadIdx.x; c < C; c += MB_THREADS) {      // coalesced across threads, 4 independent chains per thread
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+      s0 += __ldcg(partial + (long long)i * C + c);       s1 += __ldcg(partial + (long long)(i + 1) * C + c);
+      s2 += __ldcg(partial + (long long)(i + 2) * C + c); s3 += __ldcg(partial + (long long)(i + 3) * C + c);
+    }
+    for (; i < n; ++i) s0 += __ldcg(partial + (long long)i * C + c);
+    db[c] = ((s0 + s1) + (s2 + s3)) * mult[c] * out_scale;
+  }
+  if (threadIdx.x == 0) *counter = 0;             // ready for the next launch on this stream
+}
 __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ dy, int dpitch, int dcoff,
                                                            const __half* __restrict__ y, int ypitch, int ycoff,
                                                            long long rows, int C, long long rows_per_cta,
@@ -224,26 +248,78 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
     for (int l = 0; l < lanes; ++l) s += red[l * C + c];
     partial[(long long)blockIdx.x * C + c] = s;
   }
-  if (!db) return;
-  // the last CTA to finish reduces the per-CTA partials in CTA order (deterministic) into db
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const int n = (int)gridDim.x;
-  for (int c = threadIdx.x; c < C; c += MB_THREADS) {      // coalesced across threads, 4 independent chains per thread
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int i = 0;
-    for (; i + 3 < n; i += 4) {
-      s0 += __ldcg(partial + (long long)i * C + c);       s1 += __ldcg(partial + (long long)(i + 1) * C + c);
-      s2 += __ldcg(partial + (long long)(i + 2) * C + c); s3 += __ldcg(partial + (long long)(i + 3) * C + c);
+  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last);
+}
+
+// Same pass for a convolution whose only consumer is a stride-2 max pool (conv1 -> pool1, conv2_3x3 -> pool2):
+// the pool's backward gather is folded in, so the full-resolution dy tensor is never written or re-read:
+//   dz[p] = (sum over covering windows whose arg-max is p of dpool) * (y[p] > 0);  partial = column sums of dz
+__global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_h8(__half* __restrict__ dz, int dpitch, int dcoff,
+                                                                const __half* __restrict__ y, int ypitch, int ycoff, int H,
+                                                                int W, const __half* __restrict__ dpool, int OH, int OW,
+                                                                int ppitch, int pcoff, const uint8_t* __restrict__ argmax,
+                                                                int k, int stride, int pad, long long rows, int C,
+                                                                long long rows_per_cta, float* __restrict__ partial,
+                                                                unsigned* __restrict__ counter, const float* __restrict__ mult,
+                                                                float out_scale, float* __restrict__ db) {
+  extern __shared__ float red[];
+  __shared__ bool is_last;
+  const int G = C / 8;
+  const int lanes = MB_THREADS / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = (r0 + rows_per_cta < rows) ? r0 + rows_per_cta : rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const int ix = (int)(r % W), iy = (int)((r / W) % H);
+      const long long f = r / ((long long)W * H);
+      const int ty0 = iy + pad - k + 1, tx0 = ix + pad - k + 1;
+      const int oy_lo = ty0 > 0 ? (ty0 + stride - 1) / stride : 0, oy_hi = min((iy + pad) / stride, OH - 1);
+      const int ox_lo = tx0 > 0 ? (tx0 + stride - 1) / stride : 0, ox_hi = min((ix + pad) / stride, OW - 1);
+      uint2 am[4]; uint4 dv[4]; uint32_t tg[4]; bool ok[4];
+      const uint4 yv = ldg16(y + r * ypitch + ycoff + g * 8);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int oy = oy_lo + (q >> 1), ox = ox_lo + (q & 1);
+        ok[q] = oy <= oy_hi && ox <= ox_hi;
+        const long long op = (f * OH + (ok[q] ? oy : oy_lo)) * OW + (ok[q] ? ox : ox_lo);
+        tg[q] = (uint32_t)((iy + pad - oy * stride) * k + (ix + pad - ox * stride));
+        am[q] = __ldg(reinterpret_cast<const uint2*>(argmax + op * C + g * 8));
+        dv[q] = ldg16(dpool + op * ppitch + pcoff + g * 8);
+      }
+      float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!ok[q]) continue;
+        float v[8];
+        unpack8(dv[q], v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (((am[q].x >> (8 * j)) & 0xFFu) == tg[q]) d[j] += v[j];
+          if (((am[q].y >> (8 * j)) & 0xFFu) == tg[q]) d[4 + j] += v[4 + j];
+        }
+      }
+      unpack8(yv, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!(a[j] > 0.f)) d[j] = 0.f;
+        // round to storage precision first so the bias gradient sums exactly what the weight gradient reads
+        d[j] = __half2float(__float2half_rn(d[j]));
+        acc[j] += d[j];
+      }
+      *reinterpret_cast<uint4*>(dz + r * dpitch + dcoff + g * 8) = pack8(d);
     }
-    for (; i < n; ++i) s0 += __ldcg(partial + (long long)i * C + c);
-    db[c] = ((s0 + s1) + (s2 + s3)) * mult[c] * out_scale;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * C + g * 8 + j] = acc[j];
   }
-  if (threadIdx.x == 0) *counter = 0;             // ready for the next launch on this stream
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += MB_THREADS) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + c];
+    partial[(long long)blockIdx.x * C + c] = s;
+  }
+  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last);
 }
 
 }  // namespace
@@ -290,6 +366,29 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
   mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dy), dy.pitch, dy.coff, HP(y), y.pitch, y.coff, rows, C, rpc, part,
                                                               counter, mult, out_scale, db);
   SSNB_LAUNCH_CHECK("mask_bias_h8");
+  return 0;
+}
+
+
+// conv output y/dz views at full resolution; dpool = gradient of the max pool's output, argmax from its forward
+int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stride, int pad, const uint8_t* argmax,
+                             const float* mult, float out_scale, float* partial, int max_ctas, float* db, cudaStream_t s) {
+  const long long rows = (long long)F * dz.H * dz.W;
+  const int C = dz.C;
+  if (C % 8 || C / 8 > 64 || stride != 2 || k != 3) { set_thread_error("pool_mask_bias: k3/s2 pools, C multiple of 8 and <= 512"); return 1; }
+  int ctas = (int)((rows + 255) / 256);
+  if (ctas > 888) ctas = 888;
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  const long long rpc = (rows + ctas - 1) / ctas;
+  ctas = (int)((rows + rpc - 1) / rpc);
+  const int lanes = MB_THREADS / (C / 8);
+  unsigned* counter = reinterpret_cast<unsigned*>(partial);
+  float* part = partial + 64;
+  pool_mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dz), dz.pitch, dz.coff, HP(y), y.pitch, y.coff, dz.H, dz.W, HP(dpool),
+                                                                   dpool.H, dpool.W, dpool.pitch, dpool.coff, argmax, k, stride, pad, rows, C,
+                                                                   rpc, part, counter, mult, out_scale, db);
+  SSNB_LAUNCH_CHECK("pool_mask_bias_h8");
   return 0;
 }
 

@@ -321,10 +321,10 @@ int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out,
 
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
                        int stride, const __half* w_tap_n_k, const float* bias) {
-  // a stride-2 layer (k=3, pad=1): either the stride-1 convolution sampled at even pixels (4x redundant MMAs) or,
-  // with SSNB_TMA_STRIDED=1, tiles over output pixels whose A boxes step over the input with TMA element stride 2
-  const char* st = getenv("SSNB_TMA_STRIDED");
-  const bool strided = stride == 2 && st && st[0] == '1';
+  // a stride-2 layer (k=3, pad=1): tiles over OUTPUT pixels whose A boxes step over the input with TMA element
+  // stride 2 (default), or the stride-1 convolution sampled at even pixels (4x redundant MMAs, SSNB_TMA_STRIDED=0)
+  const char* st = getenv("SSNB_TMA_STRIDED");           // default on; "0" falls back to the sampled-epilogue variant
+  const bool strided = stride == 2 && !(st && st[0] == '0');
   if (int rc = strided ? bind_common(ctx, plan, in, out, F, cin, cout, k * k, 1, w_tap_n_k, 2)
                        : bind_common(ctx, plan, in, out, F, cin, cout, k * k, stride, w_tap_n_k)) return rc;
   for (int r = 0; r < k; ++r)

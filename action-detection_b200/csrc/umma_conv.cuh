@@ -81,6 +81,7 @@ struct UmmaWgradParams {
   int ptiles_per_split, splits;
   int ntaps, tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   int Cout, Cin, m_tiles, n_tiles, block_n;
+  int x_stride;                   // 2: stride-2 layers, the x box steps over the input with TMA element stride 2
   int taps_per_cta, tap_groups, mma_n;   // taps sharing one dz tile per CTA; N of each tap's MMA
   float* partial;
 };
@@ -91,9 +92,9 @@ struct UmmaWgradPlan {
 };
 // returns the number of splits chosen through *splits (the caller sizes `partial` from it)
 int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int k, int pad,
-                    float* partial, int max_splits);
+                    float* partial, int max_splits, int x_stride = 1);
 int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int ntaps,
-                         const int* dy, const int* dx, float* partial, int max_splits);
+                         const int* dy, const int* dx, float* partial, int max_splits, int x_stride = 1);
 int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s);
 
 }  // namespace ssnb

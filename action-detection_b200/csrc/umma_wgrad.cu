@@ -84,7 +84,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         for (int t = 0; t < ntap; ++t)
           for (int b = 0; b < nboxes_b; ++b)
             tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64,
-                        w0 + p.tap_dx[tap0 + t], h0 + p.tap_dy[tap0 + t], f0);
+                        w0 * p.x_stride + p.tap_dx[tap0 + t], h0 * p.x_stride + p.tap_dy[tap0 + t], f0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -145,30 +145,30 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
 }  // namespace
 
 int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int k, int pad,
-                    float* partial, int max_splits) {
+                    float* partial, int max_splits, int x_stride) {
   int dy[UMMA_MAX_TAPS], dx[UMMA_MAX_TAPS];
   if (k * k > UMMA_MAX_TAPS) { set_thread_error("umma wgrad: too many taps"); return 1; }
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { dy[r * k + s] = r - pad; dx[r * k + s] = s - pad; }
-  return umma_wgrad_bind_taps(ctx, plan, dz, x, F, cin, cout, k * k, dy, dx, partial, max_splits);
+  return umma_wgrad_bind_taps(ctx, plan, dz, x, F, cin, cout, k * k, dy, dx, partial, max_splits, x_stride);
 }
 
 int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int ntaps,
-                         const int* tdy, const int* tdx, float* partial, int max_splits) {
+                         const int* tdy, const int* tdx, float* partial, int max_splits, int x_stride) {
   plan.enabled = false;
   if (int rc = umma_resolve_encode(ctx)) return rc;
-  if (dz.H != x.H || dz.W != x.W) { set_thread_error("umma wgrad: stride-1 geometry only"); return 1; }
+  if (dz.H != (x.H + x_stride - 1) / x_stride || dz.W != (x.W + x_stride - 1) / x_stride) { set_thread_error("umma wgrad: geometry mismatch"); return 1; }
   if (cin % 8 || cout % 8 || dz.pitch % 8 || dz.coff % 8 || x.pitch % 8 || x.coff % 8 || ntaps > UMMA_MAX_TAPS) {
     set_thread_error("umma wgrad: unsupported channel alignment"); return 1; }
   UmmaWgradParams& p = plan.p;
   memset(&p, 0, sizeof(p));
-  p.W = x.W; p.H = x.H; p.F = F;
+  p.W = dz.W; p.H = dz.H; p.F = F; p.x_stride = x_stride;     // tiles enumerate dz (output) pixels
   // 64-pixel boxes whose rows are all real-or-zero-filled pixels (the pixel index is the reduction dim)
-  if (x.W % 8 == 0) { p.bw = 8; p.bh = 8; p.bf = 1; }
-  else if (x.W % 4 == 0) { p.bw = 4; p.bh = 4; p.bf = 4; }
-  else if (x.W % 2 == 0) { p.bw = 2; p.bh = 2; p.bf = 16; }
+  if (dz.W % 8 == 0) { p.bw = 8; p.bh = 8; p.bf = 1; }
+  else if (dz.W % 4 == 0) { p.bw = 4; p.bh = 4; p.bf = 4; }
+  else if (dz.W % 2 == 0) { p.bw = 2; p.bh = 2; p.bf = 16; }
   else { p.bw = 1; p.bh = 1; p.bf = 64; }
-  p.tiles_w = (x.W + p.bw - 1) / p.bw; p.tiles_h = (x.H + p.bh - 1) / p.bh; p.tiles_f = (F + p.bf - 1) / p.bf;
+  p.tiles_w = (dz.W + p.bw - 1) / p.bw; p.tiles_h = (dz.H + p.bh - 1) / p.bh; p.tiles_f = (F + p.bf - 1) / p.bf;
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) { p.tap_dy[t] = tdy[t]; p.tap_dx[t] = tdx[t]; }
   p.Cout = cout; p.Cin = cin;
@@ -203,8 +203,8 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)x.W, (cuuint64_t)x.H, (cuuint64_t)F};
     cuuint64_t str[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.W * x.pitch * 2, (cuuint64_t)x.H * x.W * x.pitch * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
-    if (int rc = umma_encode_f16(ctx, &plan.tmap_x, 4, reinterpret_cast<__half*>(x.base) + x.coff, dims, str, box)) return rc;
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * x_stride), (cuuint32_t)(p.bh * x_stride), (cuuint32_t)p.bf};
+    if (int rc = umma_encode_f16(ctx, &plan.tmap_x, 4, reinterpret_cast<__half*>(x.base) + x.coff, dims, str, box, x_stride)) return rc;
   }
   plan.enabled = true;
   return 0;

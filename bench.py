@@ -124,6 +124,10 @@ def cpu_reference(steps, warmup, videos=2):
             "sample": "%d videos = %d proposals x 9 seg fwd+bwd per step, %d steps" % (videos, props, len(times))}
 
 
+WORKLOAD = ("THUMOS14-shape synthetic: batch 32 proposals x 9 segments RGB 224x224 per GPU, BNInception SSN "
+            "fwd+bwd (+allreduce+SGD+repack), K=20, STPP (1,(1,2),1), dropout 0, frozen BN")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,8 +137,10 @@ def run_reference(args):
             "unit": "proposals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "THUMOS14-shape synthetic: 9-seg RGB 224x224 BNInception SSN fwd+bwd, K=20, STPP (1,(1,2),1)",
-                       "note": "reference CPU PyTorch path (oracle restatement, kind=port), bounded sample"},
+            "config": {"workload": WORKLOAD, "global_batch_proposals": 32 * args.gpus, "frames_per_gpu": 288,
+                       "parallelism": "dp%d" % args.gpus, "precision": "f32 CPU",
+                       "note": "reference CPU PyTorch path (oracle restatement, kind=port) timed on a bounded sample "
+                               "(16 proposals per step) of the same workload; rank 0 only"},
             "cpu_baseline": {"value": r["value"], "unit": "proposals/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -360,8 +366,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 operands / f32 accumulate" if prec == _lib.FAST_FP16 else "f32", "data": "synthetic",
-                "config": {"workload": "THUMOS14-shape synthetic: batch 32 proposals x 9 segments RGB 224x224 per GPU, BNInception SSN "
-                                       "fwd+bwd (+allreduce+SGD+repack), K=20, STPP (1,(1,2),1), dropout 0, frozen BN",
+                "config": {"workload": WORKLOAD,
                            "global_batch_proposals": props_step, "frames_per_gpu": VIDEOS_PER_GPU * PROPS * SEG,
                            "parallelism": "dp%d" % world, "precision": args.precision, "l2": "flushed between timed steps (256 MiB write)",
                            "grad_scale": args.grad_scale, "cuda_graph": used_graph},
