@@ -54,10 +54,10 @@ template <typename T> int launch_conv(const ConvArgs& a, cudaStream_t s);
 template <typename T> int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 // dW_ref[co][ci][r][s] = mult[co] * sum_splits partial ; mult = bn_scale * 1/loss_scale
 int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
-                          float out_scale, float* dw_ref, cudaStream_t s);
+                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s);
 template <typename T>
 int launch_bias_grad(const void* dz, int rows, int C, int pitch, int coff, const float* mult, float out_scale,
-                     float* partial, int splits, float* db, cudaStream_t s);
+                     float* partial, int splits, float* db, int accumulate, cudaStream_t s);
 
 // ---- glue (simt_glue.cu) ------------------------------------------------------------------------
 template <typename T> int launch_nchw_to_nhwc(const float* src, int F, int C, int H, int W, View dst, float scale, cudaStream_t s);
@@ -86,15 +86,15 @@ int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pa
                           cudaStream_t s);
 int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s);
 int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_scale, float* partial, int max_ctas, float* db,
-                        cudaStream_t s);
+                        int accumulate, cudaStream_t s);
 int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stride, int pad, const uint8_t* argmax,
-                             const float* mult, float out_scale, float* partial, int max_ctas, float* db, cudaStream_t s);
+                             const float* mult, float out_scale, float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
 // FAST-mode layout helpers (s2d_glue.cu)
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s);
 int launch_pack_conv1_s2d(const __half* wd, int Cout, int Cin, int Cs, __half* ws, cudaStream_t s);
 int launch_wgrad_finalize_s2d(const float* partial, int splits, int Cout, int Cin, int Cs, const float* mult, float out_scale,
-                              float* dw_ref, cudaStream_t s);
+                              float* dw_ref, int accumulate, cudaStream_t s);
 int launch_upsample2_zero(View src, __half* dst, int H, int W, int F, cudaStream_t s);
 
 }  // namespace ssnb

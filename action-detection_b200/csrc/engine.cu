@@ -105,6 +105,7 @@ struct ssnb_engine {
   char* ws = nullptr;
   bool weights_ready = false;
   std::vector<float*> dw, db;
+  int grad_accumulate = 0;          // 1: dw/db += (autograd-style accumulation into existing .grad), 0: overwrite
   std::string error;
   long long launches0 = 0;
   UmmaContext umma_ctx;
@@ -368,23 +369,23 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     // max-pool backward gather + ReLU mask + bias-gradient column sums in one pass (dy is never materialised)
     const Op& po = e->ops[o.pool_consumer];
     if ((rc = launch_pool_mask_bias_h8(dy, y, e->view(po.out_val, true), F, po.k, po.stride, po.pad, (const uint8_t*)(e->ws + po.argmax_off),
-                                       scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, s))) return rc;
+                                       scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
   } else if (e->fp16) {
     // one pass: ReLU gradient mask in place + bias-gradient column sums
-    if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, s))) return rc;
+    if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
   } else {
     if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
     if (dbp) {
       int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
-      if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, dbp, s))) return rc;
+      if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, dbp, e->grad_accumulate, s))) return rc;
     }
   }
   if (e->fp16 && c.stride == 2 && o.conv != 0 && o.umma_dgrad.enabled && !skip_dgrad)
     if ((rc = launch_upsample2_zero(dy, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;   // dz at input resolution
   if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
     if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s))) return rc;
-    if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], s);
-    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s);
+    if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
+    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
     if (rc) return rc;
   } else if (e->dw.size() && e->dw[o.conv]) {
     WgradArgs w;
@@ -393,7 +394,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     w.partial = partial; w.F = F; w.k = c.k; w.stride = c.stride; w.pad = c.pad;
     w.rows_per_split = o.wrows; w.splits = o.wsplits;
     if ((rc = DISPATCH(e, launch_wgrad<float>(w, s), launch_wgrad<__half>(w, s)))) return rc;
-    if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], s))) return rc;
+    if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s))) return rc;
   }
   if (e->vals[o.in_val].name != "data" && !skip_dgrad) {
     if (e->fp16 && o.umma_dgrad.enabled) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s);
@@ -488,11 +489,11 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       for (int t = 0; t < 4; ++t) { dy[t] = t - 2; dx[t] = 0; }
       rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, out, h->F, Ck, c.cout, 4, dy, dx, (const __half*)(h->ws + h->s2d_w_off),
                                (const float*)(h->ws + h->packed[0].bias), 1);
-      if (rc) { o.umma.enabled = false; continue; }     // stays on the SIMT kernel
+      if (rc) return h->fail(rc, "umma conv1 bind: " + ssnb::thread_error());
       if (use_wgrad) {
         rc = umma_wgrad_bind_taps(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), xs, h->F, Ck, c.cout, 4, dy, dx,
                                   (float*)(h->ws + h->partial_off), 128);
-        if (rc) o.umma_wgrad.enabled = false;
+        if (rc) return h->fail(rc, "umma conv1 wgrad bind: " + ssnb::thread_error());
       }
       continue;
     }
@@ -630,6 +631,12 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
     if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s);   // ... one fused data gradient
     if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
   }
+  return SSNB_OK;
+}
+
+int ssnb_set_grad_accumulate(ssnb_handle h, int accumulate) {
+  if (!h) return SSNB_EINVAL;
+  h->grad_accumulate = accumulate ? 1 : 0;
   return SSNB_OK;
 }
 

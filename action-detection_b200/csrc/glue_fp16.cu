@@ -177,7 +177,7 @@ constexpr int MB_THREADS = 256;
 // the last CTA to finish reduces the per-CTA partials in CTA order (deterministic) into db
 __device__ __forceinline__ void colsum_tail(float* __restrict__ partial, unsigned* __restrict__ counter, int C,
                                             const float* __restrict__ mult, float out_scale, float* __restrict__ db,
-                                            bool* is_last) {
+                                            bool* is_last, int accumulate) {
   if (!db) return;
   __threadfence();
   __syncthreads();
@@ -194,7 +194,7 @@ __device__ __forceinline__ void colsum_tail(float* __restrict__ partial, unsigne
       s2 += __ldcg(partial + (long long)(i + 2) * C + c); s3 += __ldcg(partial + (long long)(i + 3) * C + c);
     }
     for (; i < n; ++i) s0 += __ldcg(partial + (long long)i * C + c);
-    db[c] = ((s0 + s1) + (s2 + s3)) * mult[c] * out_scale;
+    db[c] = (accumulate ? db[c] : 0.f) + ((s0 + s1) + (s2 + s3)) * mult[c] * out_scale;
   }
   if (threadIdx.x == 0) *counter = 0;             // ready for the next launch on this stream
 }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
                                                            long long rows, int C, long long rows_per_cta,
                                                            float* __restrict__ partial, unsigned* __restrict__ counter,
                                                            const float* __restrict__ mult, float out_scale,
-                                                           float* __restrict__ db) {
+                                                           float* __restrict__ db, int accumulate) {
   extern __shared__ float red[];                 // [lanes][C]
   __shared__ bool is_last;
   const int G = C / 8;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
     for (int l = 0; l < lanes; ++l) s += red[l * C + c];
     partial[(long long)blockIdx.x * C + c] = s;
   }
-  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last);
+  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last, accumulate);
 }
 
 // Same pass for a convolution whose only consumer is a stride-2 max pool (conv1 -> pool1, conv2_3x3 -> pool2):
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_h8(__half* __restri
                                                                 int k, int stride, int pad, long long rows, int C,
                                                                 long long rows_per_cta, float* __restrict__ partial,
                                                                 unsigned* __restrict__ counter, const float* __restrict__ mult,
-                                                                float out_scale, float* __restrict__ db) {
+                                                                float out_scale, float* __restrict__ db, int accumulate) {
   extern __shared__ float red[];
   __shared__ bool is_last;
   const int G = C / 8;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_h8(__half* __restri
     for (int l = 0; l < lanes; ++l) s += red[l * C + c];
     partial[(long long)blockIdx.x * C + c] = s;
   }
-  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last);
+  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last, accumulate);
 }
 
 }  // namespace
@@ -350,7 +350,7 @@ int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s
 }
 // partial must hold max_ctas * C floats; db may be nullptr (mask only)
 int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_scale, float* partial, int max_ctas, float* db,
-                        cudaStream_t s) {
+                        int accumulate, cudaStream_t s) {
   const long long rows = (long long)F * dy.H * dy.W;
   const int C = dy.C;
   if (C % 8 || C / 8 > 64) { set_thread_error("mask_bias: C must be a multiple of 8 and <= 512"); return 1; }
@@ -364,7 +364,7 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
   unsigned* counter = reinterpret_cast<unsigned*>(partial);          // first 256 bytes of the scratch: completion counter
   float* part = partial + 64;
   mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dy), dy.pitch, dy.coff, HP(y), y.pitch, y.coff, rows, C, rpc, part,
-                                                              counter, mult, out_scale, db);
+                                                              counter, mult, out_scale, db, accumulate);
   SSNB_LAUNCH_CHECK("mask_bias_h8");
   return 0;
 }
@@ -372,7 +372,7 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
 
 // conv output y/dz views at full resolution; dpool = gradient of the max pool's output, argmax from its forward
 int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stride, int pad, const uint8_t* argmax,
-                             const float* mult, float out_scale, float* partial, int max_ctas, float* db, cudaStream_t s) {
+                             const float* mult, float out_scale, float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s) {
   const long long rows = (long long)F * dz.H * dz.W;
   const int C = dz.C;
   if (C % 8 || C / 8 > 64 || stride != 2 || k != 3) { set_thread_error("pool_mask_bias: k3/s2 pools, C multiple of 8 and <= 512"); return 1; }
@@ -387,7 +387,7 @@ int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stri
   float* part = partial + 64;
   pool_mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dz), dz.pitch, dz.coff, HP(y), y.pitch, y.coff, dz.H, dz.W, HP(dpool),
                                                                    dpool.H, dpool.W, dpool.pitch, dpool.coff, argmax, k, stride, pad, rows, C,
-                                                                   rpc, part, counter, mult, out_scale, db);
+                                                                   rpc, part, counter, mult, out_scale, db, accumulate);
   SSNB_LAUNCH_CHECK("pool_mask_bias_h8");
   return 0;
 }

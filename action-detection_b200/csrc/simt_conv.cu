@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
 // threads enumerate the partial layout [tap][co][ci] (coalesced reads of every split), write the reference
 // layout [co][ci][tap]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin,
-                                      const float* __restrict__ mult, float out_scale, float* __restrict__ dw) {
+                                      const float* __restrict__ mult, float out_scale, float* __restrict__ dw, int accumulate) {
   const long long total = (long long)taps * Cout * Cin;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -274,7 +274,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
   const int tap = (int)(i / ((long long)Cin * Cout));
   float s = 0.f;
   for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * total + i];
-  dw[((long long)co * Cin + ci) * taps + tap] = s * mult[co] * out_scale;
+  float* o = dw + ((long long)co * Cin + ci) * taps + tap;
+  *o = (accumulate ? *o : 0.f) + s * mult[co] * out_scale;
 }
 
 // column sums of dz: stage 1 partial[split][c], stage 2 db[c] = mult[c]*out_scale*sum
@@ -298,12 +299,12 @@ __global__ void bias_grad_partial_kernel(const T* __restrict__ dz, long long row
   }
 }
 __global__ void bias_grad_final_kernel(const float* __restrict__ partial, int splits, int C,
-                                       const float* __restrict__ mult, float out_scale, float* __restrict__ db) {
+                                       const float* __restrict__ mult, float out_scale, float* __restrict__ db, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
   for (int i = 0; i < splits; ++i) s += partial[(long long)i * C + c];
-  db[c] = s * mult[c] * out_scale;
+  db[c] = (accumulate ? db[c] : 0.f) + s * mult[c] * out_scale;
 }
 
 }  // namespace
@@ -338,26 +339,26 @@ template int launch_wgrad<float>(const WgradArgs&, cudaStream_t);
 template int launch_wgrad<__half>(const WgradArgs&, cudaStream_t);
 
 int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
-                          float out_scale, float* dw_ref, cudaStream_t s) {
+                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s) {
   const long long total = (long long)taps * Cout * Cin;
   wgrad_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, taps, Cout, Cin, mult,
-                                                                       out_scale, dw_ref);
+                                                                       out_scale, dw_ref, accumulate);
   SSNB_LAUNCH_CHECK("wgrad_finalize_kernel");
   return 0;
 }
 
 template <typename T>
 int launch_bias_grad(const void* dz, int rows, int C, int pitch, int coff, const float* mult, float out_scale,
-                     float* partial, int splits, float* db, cudaStream_t s) {
+                     float* partial, int splits, float* db, int accumulate, cudaStream_t s) {
   const long long rps = ((long long)rows + splits - 1) / splits;
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)splits), block(32, 8);
   bias_grad_partial_kernel<T><<<grid, block, 0, s>>>(reinterpret_cast<const T*>(dz), rows, C, pitch, coff, rps, partial);
   SSNB_LAUNCH_CHECK("bias_grad_partial_kernel");
-  bias_grad_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, splits, C, mult, out_scale, db);
+  bias_grad_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, splits, C, mult, out_scale, db, accumulate);
   SSNB_LAUNCH_CHECK("bias_grad_final_kernel");
   return 0;
 }
-template int launch_bias_grad<float>(const void*, int, int, int, int, const float*, float, float*, int, float*, cudaStream_t);
-template int launch_bias_grad<__half>(const void*, int, int, int, int, const float*, float, float*, int, float*, cudaStream_t);
+template int launch_bias_grad<float>(const void*, int, int, int, int, const float*, float, float*, int, float*, int, cudaStream_t);
+template int launch_bias_grad<__half>(const void*, int, int, int, int, const float*, float, float*, int, float*, int, cudaStream_t);
 
 }  // namespace ssnb

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ssnb_backbone_fwd": (_i, [_vp, _vp, _vp, _vp]),
     "ssnb_backbone_bwd": (_i, [_vp, _vp, _pp, _pp, _vp]),
     "ssnb_bind_grads": (_i, [_vp, _pp, _pp]),
+    "ssnb_set_grad_accumulate": (_i, [_vp, _i]),
     "ssnb_num_ops": (_i, [_vp]),
     "ssnb_op_info": (_i, [_vp, _i, C.c_char_p, _i, C.c_char_p, _i, C.c_char_p, _i]),
     "ssnb_value_shape": (_i, [_vp, C.c_char_p, _ip, _ip, _ip]),

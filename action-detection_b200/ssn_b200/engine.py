@@ -72,8 +72,9 @@ class BackboneEngine:
                   self.h, "backbone_fwd")
         return feat
 
-    def backward(self, dfeat, dw, db):
+    def backward(self, dfeat, dw, db, accumulate=False):
         dfeat = dfeat.contiguous().float()
+        check(lib.ssnb_set_grad_accumulate(self.h, int(accumulate)), self.h, "set_grad_accumulate")
         with torch.cuda.device(self.device):
             check(lib.ssnb_backbone_bwd(self.h, C.c_void_p(dfeat.data_ptr()), _lib.ptr_array(dw), _lib.ptr_array(db),
                                         _stream()), self.h, "backbone_bwd")
@@ -118,21 +119,38 @@ class BackboneEngine:
 
 
 class BackboneFunction(torch.autograd.Function):
-    """autograd bridge: feat = BNInception(x); backward fills Conv2d weight/bias grads
-    (BatchNorm2d is frozen, ssn_models.py:156-174, so it gets none)."""
+    """autograd bridge: feat = BNInception(x); backward produces the Conv2d weight/bias gradients
+    (BatchNorm2d is frozen, ssn_models.py:156-174, so it gets none).
+
+    With direct_grad (default) the kernels add straight into each parameter's .grad (allocating it
+    when it is None), exactly what autograd's AccumulateGrad would do with returned gradients, but
+    without 138 temporary tensors and 138 tiny add kernels per step; the Function then returns None
+    for the parameters.  Set BackboneFunction.direct_grad = False to get ordinary returned gradients
+    (needed for torch.autograd.grad or parameter hooks)."""
+    direct_grad = True
 
     @staticmethod
     def forward(ctx, x, engine, n_conv, *wb):
         ctx.engine, ctx.n_conv = engine, n_conv
-        ctx.shapes = [t.shape for t in wb]
-        ctx.needs = [t.requires_grad for t in wb]
+        ctx.params = wb
         return engine.forward(x)
 
     @staticmethod
     def backward(ctx, dfeat):
         eng, n = ctx.engine, ctx.n_conv
         dev = dfeat.device
-        grads = [torch.empty(s, dtype=torch.float32, device=dev) if need else None for s, need in zip(ctx.shapes, ctx.needs)]
+        if BackboneFunction.direct_grad:
+            grads = []
+            for p in ctx.params:
+                if not p.requires_grad:
+                    grads.append(None)
+                    continue
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                grads.append(p.grad)
+            eng.backward(dfeat, grads[:n], grads[n:], accumulate=True)
+            return (None, None, None) + (None,) * len(ctx.params)
+        grads = [torch.empty(p.shape, dtype=torch.float32, device=dev) if p.requires_grad else None for p in ctx.params]
         eng.backward(dfeat, grads[:n], grads[n:])
         return (None, None, None) + tuple(grads)
 

@@ -259,17 +259,17 @@ class SSN(torch.nn.Module):
         if mask is not None:
             dft = dft * mask
         cs = bm._convs()
-        dw = [torch.empty_like(c.weight) for c in cs]
-        db = [torch.empty_like(c.bias) for c in cs]
-        eng.backward(dft, dw, db)
+        params = [c.weight for c in cs] + [c.bias for c in cs]
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        eng.backward(dft, [c.weight.grad for c in cs], [c.bias.grad for c in cs], accumulate=True)   # straight into .grad
 
         def acc(p, g):
             if p.grad is None:
                 p.grad = g
             else:
                 p.grad.add_(g)
-        for c, gw, gb in zip(cs, dw, db):
-            acc(c.weight, gw); acc(c.bias, gb)
         for fc, k in ((self.activity_fc, "act"), (self.completeness_fc, "comp"), (self.regressor_fc, "reg")):
             acc(fc.weight, out["d_%s_w" % k]); acc(fc.bias, out["d_%s_b" % k])
         self.last_fused = dict(out, feat=feat, course=course, stpp=stpp)

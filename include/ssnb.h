@@ -63,6 +63,9 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
 /* dfeat [F,1024] fp32 -> dw[i] [cout,cin,k,k], db[i] [cout] fp32 in reference layout (what autograd
  * leaves in Conv2d.weight.grad / .bias.grad; BN params are frozen and get none).  Overwrites. */
 int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float* const* db, void* stream);
+/* 0 (default): ssnb_backbone_bwd overwrites dw/db; 1: it adds to them (what autograd's AccumulateGrad does
+ * with Conv2d.weight.grad), so the caller can hand in the live .grad tensors */
+int ssnb_set_grad_accumulate(ssnb_handle h, int accumulate);
 /* bind the gradient outputs used by ssnb_run_op(backward=1) without running the whole backward */
 int ssnb_bind_grads(ssnb_handle h, float* const* dw, float* const* db);
 
