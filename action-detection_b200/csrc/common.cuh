@@ -69,7 +69,7 @@ int launch_maxpool_bwd(View dsrc, View ddst, int F, int k, int stride, int pad, 
                        cudaStream_t s);
 template <typename T> int launch_avgpool3_fwd(View src, View dst, int F, int accumulate, cudaStream_t s);
 template <typename T> int launch_gpool_fwd(View src, int F, float* feat, cudaStream_t s);
-template <typename T> int launch_gpool_bwd(const float* dfeat, float scale, View ddst, int F, cudaStream_t s);
+template <typename T> int launch_gpool_bwd(const float* dfeat, float scale, View ddst, int F, const void* y, cudaStream_t s);
 template <typename T> int launch_relu_mask(View dy, View y, int F, cudaStream_t s);
 template <typename T> int launch_fill_zero(View v, int F, cudaStream_t s);
 

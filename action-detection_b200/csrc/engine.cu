@@ -68,6 +68,8 @@ struct Op {
   UmmaWgradPlan umma_wgrad; // tcgen05 weight-gradient plan
   int pool_consumer = -1;   // conv whose only consumer is a k3/s2 max pool: that pool's op index (backward gather is folded in)
   bool folded_into_conv = false;   // max pool whose backward runs inside its producer conv's mask+bias pass
+  bool dgrad_masks = false; // this op's data gradient is the LAST writer of d(in_val): it applies the ReLU mask of in_val
+  bool dy_premasked = false;// conv: d(out) arrives already masked, the backward pass only needs the bias column sums
   int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
   int fuse_block = -1;
 };
@@ -340,7 +342,8 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   if (o.kind == OP_GPOOL) {
     if (!dfeat) return e->fail(SSNB_EINVAL, "global_pool backward needs dfeat");
     const View din = e->view(o.in_val, true);
-    return DISPATCH(e, launch_gpool_bwd<float>(dfeat, gs, din, F, s), launch_gpool_bwd<__half>(dfeat, gs, din, F, s));
+    const void* ym = (full && e->fold_pools && o.dgrad_masks) ? e->view(o.in_val, false).base : nullptr;
+    return DISPATCH(e, launch_gpool_bwd<float>(dfeat, gs, din, F, ym, s), launch_gpool_bwd<__half>(dfeat, gs, din, F, ym, s));
   }
   if (o.kind == OP_MAXPOOL) {
     if (full && e->fp16 && e->fold_pools && o.folded_into_conv) return 0;      // gathered by the producer conv's mask+bias pass
@@ -371,8 +374,9 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if ((rc = launch_pool_mask_bias_h8(dy, y, e->view(po.out_val, true), F, po.k, po.stride, po.pad, (const uint8_t*)(e->ws + po.argmax_off),
                                        scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
   } else if (e->fp16) {
-    // one pass: ReLU gradient mask in place + bias-gradient column sums
-    if ((rc = launch_mask_bias_h8(dy, y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
+    // one pass: ReLU gradient mask in place + bias-gradient column sums (mask skipped when the producer of dy applied it)
+    const bool pre = full && e->fold_pools && o.dy_premasked;
+    if ((rc = launch_mask_bias_h8(dy, pre ? View() : y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
   } else {
     if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
     if (dbp) {
@@ -397,7 +401,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s))) return rc;
   }
   if (e->vals[o.in_val].name != "data" && !skip_dgrad) {
-    if (e->fp16 && o.umma_dgrad.enabled) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s);
+    if (e->fp16 && o.umma_dgrad.enabled) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s, full && e->fold_pools && o.dgrad_masks);
     ConvArgs a;
     a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
     a.dst = dx.base; a.DH = dx.H; a.DW = dx.W; a.Cdst = dx.C; a.dst_pitch = dx.pitch; a.dst_coff = dx.coff;
@@ -544,6 +548,39 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     for (int j : {fb.op1, fb.op_r3, fb.op_rd})
       if (j >= 0) { h->ops[j].fuse_block = (int)bi; h->ops[j].fuse_role = (j == leader) ? 1 : 2; }
   }
+  // ReLU-mask fusion: the consumer with the smallest forward index is the last writer of a value's gradient in the
+  // reverse schedule (sibling followers are folded into their leader); if that writer is a tcgen05 data gradient or the
+  // global pool, it applies dz = dy * (y > 0) in its epilogue and the producing conv skips its own mask pass.
+  for (Op& o : h->ops) { o.dgrad_masks = false; o.dy_premasked = false; }
+  if (use_umma && h->cfg.training) {
+    std::vector<int> first_consumer(h->vals.size(), -1);
+    for (int i = 0; i < (int)h->ops.size(); ++i)
+      if (first_consumer[h->ops[i].in_val] < 0) first_consumer[h->ops[i].in_val] = i;
+    for (size_t v = 0; v < h->vals.size(); ++v) {
+      const int fc = first_consumer[v];
+      if (fc < 0 || h->vals[v].name == "data") continue;
+      bool conv_made = false;                    // only buffers that hold convolution outputs have a ReLU to differentiate
+      for (const Op& q : h->ops) conv_made = conv_made || (q.kind == OP_CONV && h->vals[q.out_val].buf == h->vals[v].buf);
+      if (!conv_made) continue;
+      Op& c = h->ops[fc];
+      if (c.kind == OP_GPOOL) c.dgrad_masks = true;
+      else if (c.kind == OP_CONV && (c.fuse_role == 1 ? h->fused[c.fuse_block].enabled : (c.fuse_role == 0 && c.umma_dgrad.enabled))) {
+        c.dgrad_masks = true;
+        const View yv = h->view((int)v, false);
+        if (c.fuse_role == 1) umma_conv_set_mask(h->fused[c.fuse_block].dgrad, yv); else umma_conv_set_mask(c.umma_dgrad, yv);
+      }
+    }
+    for (Op& o : h->ops) {
+      if (o.kind != OP_CONV) continue;
+      int w = o.out_val;
+      if (first_consumer[w] < 0) {               // a slice of a concat buffer: gradients are written through the whole-buffer value
+        const Value& ov = h->vals[o.out_val];
+        for (size_t v = 0; v < h->vals.size(); ++v)
+          if (h->vals[v].buf == ov.buf && h->vals[v].coff == 0 && h->vals[v].C == h->bufs[ov.buf].C && first_consumer[v] >= 0) { w = (int)v; break; }
+      }
+      if (first_consumer[w] >= 0 && h->ops[first_consumer[w]].dgrad_masks) o.dy_premasked = true;
+    }
+  }
   return SSNB_OK;
 }
 
@@ -628,7 +665,7 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
     const Op& o = h->ops[i];
     int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
-    if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s);   // ... one fused data gradient
+    if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s, h->fold_pools && o.dgrad_masks);   // ... one fused data gradient
     if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
   }
   return SSNB_OK;

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
         const long long r = rb + (long long)u * lanes;
         if (r < r1) {
           dv[u] = *reinterpret_cast<const uint4*>(dy + r * dpitch + dcoff + g * 8);
-          yv[u] = ldg16(y + r * ypitch + ycoff + g * 8);
+          if (y) yv[u] = ldg16(y + r * ypitch + ycoff + g * 8);
         }
       }
 #pragma unroll
@@ -229,13 +229,16 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_h8(__half* __restrict__ 
         const long long r = rb + (long long)u * lanes;
         if (r >= r1) continue;
         float d[8], a[8];
-        unpack8(dv[u], d); unpack8(yv[u], a);
+        unpack8(dv[u], d);
         bool changed = false;
+        if (y) {                                  // y == nullptr: the producer already masked dy (column sums only)
+          unpack8(yv[u], a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
-          acc[j] += d[j];
+          for (int j = 0; j < 8; ++j)
+            if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += d[j];
         if (changed) *reinterpret_cast<uint4*>(dy + r * dpitch + dcoff + g * 8) = pack8(d);
       }
     }

@@ -136,13 +136,15 @@ __global__ void gpool_fwd_kernel(const T* __restrict__ src, int HW, int C, int p
 
 template <typename T>
 __global__ void gpool_bwd_kernel(const float* __restrict__ dfeat, float scale, int HW, int C, int pitch, int coff, int F,
-                                 T* __restrict__ ddst) {
+                                 T* __restrict__ ddst, const T* __restrict__ y) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * HW * C) return;
   const int c = (int)(i % C);
   const long long p = i / C;
   const long long f = p / HW;
-  ddst[p * pitch + coff + c] = from_f<T>(dfeat[f * C + c] / (float)HW * scale);
+  float g = dfeat[f * C + c] / (float)HW * scale;
+  if (y && !(to_f<T>(y[p * pitch + coff + c]) > 0.f)) g = 0.f;     // fused ReLU gradient mask (same view geometry)
+  ddst[p * pitch + coff + c] = from_f<T>(g);
 }
 
 template <typename T>
@@ -234,9 +236,9 @@ template <typename T> int launch_gpool_fwd(View src, int F, float* feat, cudaStr
   SSNB_LAUNCH_CHECK("gpool_fwd_kernel");
   return 0;
 }
-template <typename T> int launch_gpool_bwd(const float* dfeat, float scale, View ddst, int F, cudaStream_t s) {
+template <typename T> int launch_gpool_bwd(const float* dfeat, float scale, View ddst, int F, const void* y, cudaStream_t s) {
   const long long n = (long long)F * ddst.H * ddst.W * ddst.C;
-  gpool_bwd_kernel<T><<<blocks_for(n), TPB, 0, s>>>(dfeat, scale, ddst.H * ddst.W, ddst.C, ddst.pitch, ddst.coff, F, V(T, ddst));
+  gpool_bwd_kernel<T><<<blocks_for(n), TPB, 0, s>>>(dfeat, scale, ddst.H * ddst.W, ddst.C, ddst.pitch, ddst.coff, F, V(T, ddst), reinterpret_cast<const T*>(y));
   SSNB_LAUNCH_CHECK("gpool_bwd_kernel");
   return 0;
 }
@@ -269,7 +271,7 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
   template int launch_maxpool_bwd<T>(View, View, int, int, int, int, const uint8_t*, int, cudaStream_t);     \
   template int launch_avgpool3_fwd<T>(View, View, int, int, cudaStream_t);                                   \
   template int launch_gpool_fwd<T>(View, int, float*, cudaStream_t);                                         \
-  template int launch_gpool_bwd<T>(const float*, float, View, int, cudaStream_t);                            \
+  template int launch_gpool_bwd<T>(const float*, float, View, int, const void*, cudaStream_t);                            \
   template int launch_relu_mask<T>(View, View, int, cudaStream_t);                                           \
   template int launch_fill_zero<T>(View, int, cudaStream_t);                                                 \
   template int launch_pack_conv<T>(const float*, const float*, const float*, const float*, const float*,     \

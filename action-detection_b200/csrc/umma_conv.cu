@@ -176,6 +176,20 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          if (p.mask_y) {
+            const uint4* my = reinterpret_cast<const uint4*>(p.mask_y + opix * p.mask_pitch + p.mask_coff + col);
+            const uint4 y0 = __ldg(my), y1 = __ldg(my + 1);
+            const __half2* a0 = reinterpret_cast<const __half2*>(&y0);
+            const __half2* a1 = reinterpret_cast<const __half2*>(&y1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 ya = __half22float2(a0[j]), yb = __half22float2(a1[j]);
+              if (!(ya.x > 0.f)) v[2 * j] = 0.f;
+              if (!(ya.y > 0.f)) v[2 * j + 1] = 0.f;
+              if (!(yb.x > 0.f)) v[8 + 2 * j] = 0.f;
+              if (!(yb.y > 0.f)) v[8 + 2 * j + 1] = 0.f;
+            }
+          }
           uint4 q0, q1;
           __half2* g0 = reinterpret_cast<__half2*>(&q0);
           __half2* g1 = reinterpret_cast<__half2*>(&q1);
@@ -281,7 +295,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.stages = PIPE_BYTES / p.stage_bytes; if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.ntaps = ntaps;
   p.out = reinterpret_cast<__half*>(o.base); p.out_pitch = o.pitch; p.out_coff = o.coff; p.Cout = N;
-  p.out_stride = out_stride; p.OH = o.H; p.OW = o.W; p.a_stride = 1;
+  p.out_stride = out_stride; p.OH = o.H; p.OW = o.W; p.a_stride = 1; p.mask_y = nullptr; p.mask_pitch = 0; p.mask_coff = 0;
   p.kchunks_a1 = (K + BLOCK_K - 1) / BLOCK_K; p.K1 = K; p.n_split = 1 << 30; p.out2 = p.out; p.out2_pitch = o.pitch; p.out2_coff = o.coff;
   {
     cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)F};
@@ -380,14 +394,19 @@ int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, V
   return 0;
 }
 
-int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s) {
+void umma_conv_set_mask(UmmaConvPlan& plan, View y) {
+  plan.mask_y = reinterpret_cast<const __half*>(y.base); plan.mask_pitch = y.pitch; plan.mask_coff = y.coff;
+}
+
+int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s, bool mask) {
   if (!plan.enabled) { set_thread_error("umma conv: plan not bound"); return 3; }
   if (!ctx.attr_set) {
     if (cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       set_thread_error("umma conv: cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
     ctx.attr_set = true;
   }
-  const UmmaConvParams& p = plan.p;
+  UmmaConvParams p = plan.p;
+  if (mask && plan.mask_y) { p.mask_y = plan.mask_y; p.mask_pitch = plan.mask_pitch; p.mask_coff = plan.mask_coff; }
   const int total = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
   const int grid = total < ctx.num_sms ? total : ctx.num_sms;
   umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, p);

@@ -39,10 +39,13 @@ struct UmmaConvParams {
   int kchunks_a1, K1;             // K chunks [0, kchunks_a1) come from tmap_a (K1 real channels), the rest from tmap_a2
   int n_split;                    // output columns >= n_split go to out2 (second destination), else to out
   __half* out2; int out2_pitch, out2_coff;
+  // data gradient that is the LAST writer of its output: fuse dz = dy * (y > 0), y = activation of the same value
+  const __half* mask_y; int mask_pitch, mask_coff;
 };
 
 struct UmmaConvPlan {
   bool enabled = false;
+  const __half* mask_y = nullptr; int mask_pitch = 0, mask_coff = 0;   // applied only when launched with mask=true
   CUtensorMap tmap_a, tmap_a2, tmap_b;
   UmmaConvParams p;
 };
@@ -64,7 +67,8 @@ int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View
 // fused data gradient of sibling 1x1 convs: dx (+)= [dz1 | dz2] * W, weights [cin][pad64(k1) + k2]; dz1 may be empty (k1 = 0)
 int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, View dz2, View dx, int F, int cin, int k1, int k2,
                                const __half* w_n_k, int accumulate);
-int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s);
+int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s, bool mask = false);
+void umma_conv_set_mask(UmmaConvPlan& plan, View y);
 
 // host helpers shared by the tensor-core kernels
 int umma_resolve_encode(UmmaContext& ctx);

@@ -333,28 +333,41 @@ def main():
         eng = model.base_model.engine_for(VIDEOS_PER_GPU * PROPS * SEG, True, dev)
         table = {n: (ci, co, k, s, p) for (n, ci, co, k, s, p) in __import__("ssn_b200.engine", fromlist=["conv_table"]).conv_table(3)}
         tot_ms, tot_flop, n_l = 0.0, 0.0, 0
+        big = None
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i, (kind, iname, oname) in enumerate(eng.ops()):
             if kind != "conv":
                 continue
             ci, co, k, s, p = table[oname[:-3]]
             if s != 1 or ci % 8:
-                continue                           # conv1 / stride-2 layers run on the SIMT kernel
+                continue                           # conv1 / stride-2 layers use other plans of the same kernel
             _c, hh, ww = eng.value_shape(oname)
             best = 1e9
             for _ in range(3):
                 l2_flush.zero_()
                 a.record(); eng.run_op(i, False); b.record(); b.synchronize()
                 best = min(best, a.elapsed_time(b))
+            flop = 2.0 * eng.frames * hh * ww * co * ci * k * k
             tot_ms += best
-            tot_flop += 2.0 * eng.frames * hh * ww * co * ci * k * k
+            tot_flop += flop
             n_l += 1
-        achieved = tot_flop / (tot_ms / 1e3) / 1e12
+            if big is None or flop > big[1]:
+                big = (oname[:-3], flop, best)
         peak = peaks.get("bf16_tflops", 1590.0)
-        roof = {"bound": "tensor", "kernel": "umma_conv_kernel (forward launches, 64 stride-1 layers)" if prec == _lib.FAST_FP16 else "conv_kernel<float> (SIMT)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src + " bf16 burst (kernel timed alone)", "launches_timed": n_l,
-                "flop_per_launch_avg": tot_flop / n_l, "ms_per_launch_avg": tot_ms / n_l}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("umma_conv_kernel:%s_fwd" % big[0], {}).get("dram_bytes")
+        except Exception:
+            traffic = None
+        achieved = big[1] / (big[2] / 1e3) / 1e12
+        fam = tot_flop / (tot_ms / 1e3) / 1e12
+        roof = {"bound": "tensor",
+                "kernel": ("umma_conv_kernel" if prec == _lib.FAST_FP16 else "conv_kernel<float> (SIMT)") + ", largest launch: %s forward" % big[0],
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu --set full dram read+write, profiles/r01_ncu_full_tensor_kernels.txt)",
+                "peak_source": peak_src + " bf16 burst (kernel timed alone, L2 flushed before each launch)",
+                "flop_per_launch": big[1], "ms_per_launch": big[2],
+                "family_average": {"launches_timed": n_l, "achieved": fam, "frac": fam / peak,
+                                   "note": "all %d stride-1 forward launches of the kernel, sum(flop)/sum(time)" % n_l}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
