@@ -54,7 +54,8 @@ template <typename T> int launch_conv(const ConvArgs& a, cudaStream_t s);
 template <typename T> int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 // dW_ref[co][ci][r][s] = mult[co] * sum_splits partial ; mult = bn_scale * 1/loss_scale
 int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
-                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s);
+                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s, const float* bias_partial = nullptr,
+                          float* db = nullptr);
 template <typename T>
 int launch_bias_grad(const void* dz, int rows, int C, int pitch, int coff, const float* mult, float out_scale,
                      float* partial, int splits, float* db, int accumulate, cudaStream_t s);

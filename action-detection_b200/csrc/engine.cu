@@ -69,6 +69,7 @@ struct Op {
   int pool_consumer = -1;   // conv whose only consumer is a k3/s2 max pool: that pool's op index (backward gather is folded in)
   bool folded_into_conv = false;   // max pool whose backward runs inside its producer conv's mask+bias pass
   bool dgrad_masks = false; // this op's data gradient is the LAST writer of d(in_val): it applies the ReLU mask of in_val
+  bool bias_in_wgrad = false;// conv: bias gradient comes out of the tcgen05 weight-gradient kernel (ones operand)
   bool dy_premasked = false;// conv: d(out) arrives already masked, the backward pass only needs the bias column sums
   int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
   int fuse_block = -1;
@@ -376,7 +377,9 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   } else if (e->fp16) {
     // one pass: ReLU gradient mask in place + bias-gradient column sums (mask skipped when the producer of dy applied it)
     const bool pre = full && e->fold_pools && o.dy_premasked;
-    if ((rc = launch_mask_bias_h8(dy, pre ? View() : y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
+    const bool bias_w = pre && o.bias_in_wgrad && dbp && e->dw.size() && e->dw[o.conv] && o.umma_wgrad.enabled;
+    if (bias_w) { /* no pass at all: dy is already masked and the column sums ride on the weight-gradient MMAs */ }
+    else if ((rc = launch_mask_bias_h8(dy, pre ? View() : y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
   } else {
     if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
     if (dbp) {
@@ -387,9 +390,11 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   if (e->fp16 && c.stride == 2 && o.conv != 0 && o.umma_dgrad.enabled && !skip_dgrad)
     if ((rc = launch_upsample2_zero(dy, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;   // dz at input resolution
   if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
-    if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s))) return rc;
+    const bool bias_w = full && e->fold_pools && o.dy_premasked && o.bias_in_wgrad && dbp;
+    float* bp = bias_w ? bpartial + 64 : nullptr;
+    if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, bp))) return rc;
     if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
-    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
+    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s, bp, dbp);
     if (rc) return rc;
   } else if (e->dw.size() && e->dw[o.conv]) {
     WgradArgs w;
@@ -579,6 +584,8 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
           if (h->vals[v].buf == ov.buf && h->vals[v].coff == 0 && h->vals[v].C == h->bufs[ov.buf].C && first_consumer[v] >= 0) { w = (int)v; break; }
       }
       if (first_consumer[w] >= 0 && h->ops[first_consumer[w]].dgrad_masks) o.dy_premasked = true;
+      o.bias_in_wgrad = o.dy_premasked && o.conv != 0 && o.umma_wgrad.enabled && o.umma_wgrad.p.taps_per_cta * o.umma_wgrad.p.mma_n + 16 <= 512 &&
+                        o.umma_wgrad.p.splits * h->convs[o.conv].cout <= 1024 * 512 - 64;
     }
   }
   return SSNB_OK;

@@ -265,9 +265,15 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
 // threads enumerate the partial layout [tap][co][ci] (coalesced reads of every split), write the reference
 // layout [co][ci][tap]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin,
-                                      const float* __restrict__ mult, float out_scale, float* __restrict__ dw, int accumulate) {
+                                      const float* __restrict__ mult, float out_scale, float* __restrict__ dw, int accumulate,
+                                      const float* __restrict__ bias_partial, float* __restrict__ db) {
   const long long total = (long long)taps * Cout * Cin;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bias_partial && db && i < Cout) {          // bias gradient from the weight-gradient kernel's ones-operand accumulator
+    float sb = 0.f;
+    for (int sp = 0; sp < splits; ++sp) sb += bias_partial[(long long)sp * Cout + i];
+    db[i] = (accumulate ? db[i] : 0.f) + sb * mult[i] * out_scale;
+  }
   if (i >= total) return;
   const int ci = (int)(i % Cin);
   const int co = (int)((i / Cin) % Cout);
@@ -339,10 +345,10 @@ template int launch_wgrad<float>(const WgradArgs&, cudaStream_t);
 template int launch_wgrad<__half>(const WgradArgs&, cudaStream_t);
 
 int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
-                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s) {
+                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s, const float* bias_partial, float* db) {
   const long long total = (long long)taps * Cout * Cin;
   wgrad_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, taps, Cout, Cin, mult,
-                                                                       out_scale, dw_ref, accumulate);
+                                                                       out_scale, dw_ref, accumulate, bias_partial, db);
   SSNB_LAUNCH_CHECK("wgrad_finalize_kernel");
   return 0;
 }

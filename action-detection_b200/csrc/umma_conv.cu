@@ -39,6 +39,49 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaConvParams& p, int ti
   return t;
 }
 
+// bias / accumulate / ReLU / ReLU-gradient mask on one 16-column chunk of an accumulator row, then fp16 store
+__device__ __forceinline__ void epilogue_chunk(const UmmaConvParams& p, const uint32_t* r, int col, uint4* dst, const uint4& o0,
+                                               const uint4& o1, const uint4& y0, const uint4& y1) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + col + j);
+  }
+  if (p.accumulate) {
+    const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&o1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+      v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.mask_y) {
+    const __half2* a0 = reinterpret_cast<const __half2*>(&y0);
+    const __half2* a1 = reinterpret_cast<const __half2*>(&y1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 ya = __half22float2(a0[j]), yb = __half22float2(a1[j]);
+      if (!(ya.x > 0.f)) v[2 * j] = 0.f;
+      if (!(ya.y > 0.f)) v[2 * j + 1] = 0.f;
+      if (!(yb.x > 0.f)) v[8 + 2 * j] = 0.f;
+      if (!(yb.y > 0.f)) v[8 + 2 * j + 1] = 0.f;
+    }
+  }
+  uint4 q0, q1;
+  __half2* g0 = reinterpret_cast<__half2*>(&q0);
+  __half2* g1 = reinterpret_cast<__half2*>(&q1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { g0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); g1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]); }
+  dst[0] = q0; dst[1] = q1;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_b, const UmmaConvParams p) {
@@ -148,55 +191,30 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid && t.n0 + c0 < p.Cout) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + t.n0 + c0 + j);
-          }
-          const int col = t.n0 + c0;
-          uint4* dst = reinterpret_cast<uint4*>((col < p.n_split ? orow : orow2) + col);
-          if (p.accumulate) {
-            uint4 o0 = dst[0], o1 = dst[1];
-            const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&o1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-              v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.mask_y) {
-            const uint4* my = reinterpret_cast<const uint4*>(p.mask_y + opix * p.mask_pitch + p.mask_coff + col);
-            const uint4 y0 = __ldg(my), y1 = __ldg(my + 1);
-            const __half2* a0 = reinterpret_cast<const __half2*>(&y0);
-            const __half2* a1 = reinterpret_cast<const __half2*>(&y1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 ya = __half22float2(a0[j]), yb = __half22float2(a1[j]);
-              if (!(ya.x > 0.f)) v[2 * j] = 0.f;
-              if (!(ya.y > 0.f)) v[2 * j + 1] = 0.f;
-              if (!(yb.x > 0.f)) v[8 + 2 * j] = 0.f;
-              if (!(yb.y > 0.f)) v[8 + 2 * j + 1] = 0.f;
-            }
-          }
-          uint4 q0, q1;
-          __half2* g0 = reinterpret_cast<__half2*>(&q0);
-          __half2* g1 = reinterpret_cast<__half2*>(&q1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { g0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); g1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]); }
-          dst[0] = q0; dst[1] = q1;
+      // two 16-column chunks per iteration: the global loads of both (accumulate / mask operands) and both TMEM
+      // loads are in flight before the first use
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const bool two = c0 + 16 < p.block_n;                       // warp-uniform
+        const int cola = t.n0 + c0, colb = cola + 16;
+        const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
+        uint4* da = reinterpret_cast<uint4*>((cola < p.n_split ? orow : orow2) + cola);
+        uint4* db2 = reinterpret_cast<uint4*>((colb < p.n_split ? orow : orow2) + colb);
+        uint4 oa0 = {}, oa1 = {}, ob0 = {}, ob1 = {}, ya0 = {}, ya1 = {}, yb0 = {}, yb1 = {};
+        if (p.accumulate) {
+          if (va) { oa0 = da[0]; oa1 = da[1]; }
+          if (vb) { ob0 = db2[0]; ob1 = db2[1]; }
         }
+        if (p.mask_y) {
+          const uint4* my = reinterpret_cast<const uint4*>(p.mask_y + opix * p.mask_pitch + p.mask_coff + cola);
+          if (va) { ya0 = __ldg(my); ya1 = __ldg(my + 1); }
+          if (vb) { yb0 = __ldg(my + 2); yb1 = __ldg(my + 3); }
+        }
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr + c0, ra);
+        if (two) tmem_ld16(taddr + c0 + 16, rb);
+        tmem_ld_wait();
+        if (va) epilogue_chunk(p, ra, cola, da, oa0, oa1, ya0, ya1);
+        if (vb) epilogue_chunk(p, rb, colb, db2, ob0, ob1, yb0, yb1);
       }
       tc_fence_before();
       __syncwarp();

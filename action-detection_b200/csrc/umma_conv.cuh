@@ -86,6 +86,7 @@ struct UmmaWgradParams {
   int ntaps, tap_dy[UMMA_MAX_TAPS], tap_dx[UMMA_MAX_TAPS];
   int Cout, Cin, m_tiles, n_tiles, block_n;
   int x_stride;                   // 2: stride-2 layers, the x box steps over the input with TMA element stride 2
+  float* bias_partial;            // [split][Cout] column sums of dz (bias gradient) from an extra ones-operand MMA, or nullptr
   int taps_per_cta, tap_groups, mma_n;   // taps sharing one dz tile per CTA; N of each tap's MMA
   float* partial;
 };
@@ -99,6 +100,6 @@ int umma_wgrad_bind(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int 
                     float* partial, int max_splits, int x_stride = 1);
 int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x, int F, int cin, int cout, int ntaps,
                          const int* dy, const int* dx, float* partial, int max_splits, int x_stride = 1);
-int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s);
+int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s, float* bias_partial = nullptr);
 
 }  // namespace ssnb

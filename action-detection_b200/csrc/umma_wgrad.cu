@@ -21,7 +21,8 @@ constexpr int BOX_BYTES = 64 * 128;                 // [64 px][64 ch] fp16
 constexpr int A_BYTES = 2 * BOX_BYTES;              // 128 output channels
 constexpr int STAGE_BYTES = A_BYTES + 4 * BOX_BYTES;  // + up to 256 input channels
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int ONES_OFF = STAGES * STAGE_BYTES + 1024;                // [64 px][64 ch] tile of fp16 ones (bias-gradient operand), 1 KiB aligned
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + BOX_BYTES;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
@@ -47,7 +48,10 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   const int pt0 = split * p.ptiles_per_split;
   const int pt1 = min(pt0 + p.ptiles_per_split, ptiles);
   const int nboxes_b = p.block_n / 64;
-  const int acc_cols = p.taps_per_cta * p.mma_n;
+  // CTAs of the first input tile / tap group also reduce dz over pixels: db[co] = sum_p dz[p, co] = dz^T * 1
+  const bool do_bias = p.bias_partial != nullptr && nt == 0 && tgrp == 0;
+  const int bias_col = p.taps_per_cta * p.mma_n;
+  const int acc_cols = p.taps_per_cta * p.mma_n + (p.bias_partial ? 16 : 0);
   const uint32_t tmem_cols = acc_cols <= 32 ? 32 : (acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
@@ -60,6 +64,11 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (do_bias) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + ONES_OFF);
+    for (int i = threadIdx.x; i < BOX_BYTES / 4; i += NUM_THREADS) ones[i] = 0x3C003C00u;     // half2(1, 1)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
   }
   tc_fence_before();
   __syncthreads();
@@ -105,6 +114,13 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
             umma_f16(tmem_base + t * p.mma_n, ad, bd, idesc, (pt > pt0 || k) ? 1u : 0u);
           }
         }
+        if (do_bias) {
+          const uint32_t so = smem_u32(smem + ONES_OFF);
+#pragma unroll
+          for (int k = 0; k < 64 / UMMA_K; ++k)
+            umma_f16(tmem_base + bias_col, make_desc_mn_sw128(sa + k * UMMA_K * 128, BOX_BYTES), make_desc_mn_sw128(so + k * UMMA_K * 128, BOX_BYTES),
+                     make_idesc_f16_mn(16), (pt > pt0 || k) ? 1u : 0u);
+        }
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -131,6 +147,12 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
           }
         }
       }
+    }
+    if (do_bias) {
+      uint32_t r[16];
+      tmem_ld16(taddr + bias_col, r);
+      tmem_ld_wait();
+      if (m < p.Cout) p.bias_partial[(long long)split * p.Cout + m] = __uint_as_float(r[0]);
     }
     tc_fence_before();
   }
@@ -193,7 +215,7 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   if (splits < 1) splits = 1;
   p.ptiles_per_split = (ptiles + splits - 1) / splits;
   p.splits = (ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
-  p.partial = partial;
+  p.partial = partial; p.bias_partial = nullptr;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)dz.W, (cuuint64_t)dz.H, (cuuint64_t)F};
     cuuint64_t str[3] = {(cuuint64_t)dz.pitch * 2, (cuuint64_t)dz.W * dz.pitch * 2, (cuuint64_t)dz.H * dz.W * dz.pitch * 2};
@@ -210,7 +232,7 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   return 0;
 }
 
-int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s) {
+int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t s, float* bias_partial) {
   if (!plan.enabled) { set_thread_error("umma wgrad: plan not bound"); return 3; }
   static bool attr_set = false;
   if (!attr_set) {
@@ -218,7 +240,8 @@ int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t 
       set_thread_error("umma wgrad: cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
     attr_set = true;
   }
-  const UmmaWgradParams& p = plan.p;
+  UmmaWgradParams p = plan.p;
+  p.bias_partial = bias_partial;
   dim3 grid((unsigned)(p.m_tiles * p.n_tiles * p.tap_groups), (unsigned)p.splits);
   umma_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_dz, plan.tmap_x, p);
   SSNB_LAUNCH_CHECK("umma_wgrad_kernel");
