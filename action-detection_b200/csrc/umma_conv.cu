@@ -3,7 +3,8 @@
 //
 //   warp 0      : TMA producer   (A: 4-D activation box, B: 3-D weight box, SWIZZLE_128B)
 //   warp 1      : TMEM allocator + MMA issuer (tcgen05.mma.cta_group::1.kind::f16, M=128, N=block_n)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> bias/ReLU or accumulate -> fp16 NHWC store)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> bias/ReLU or accumulate/mask -> fp16 NHWC store); two warps per
+//                 TMEM lane quadrant take alternating 32-column groups (memory-level parallelism of the stores/loads)
 //
 // Rows of the M tile are the pixels of one TMA box (bw x bh x bf); taps shift the box origin and
 // rely on TMA's out-of-bounds zero fill for the convolution padding.
@@ -23,7 +24,8 @@ constexpr int MAX_STAGES = 8;
 constexpr int PIPE_BYTES = 4 * (BLOCK_M * BLOCK_K * 2 + 256 * BLOCK_K * 2);   // 192 KiB of operand staging
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KiB
 constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -106,7 +108,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -175,8 +177,9 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue warps 2..5; TMEM lane quadrant = warp % 4 =====
+    // ===== epilogue warps 2..9; TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
     const int quad = warp & 3;
+    const int cpar = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rf = row / (p.bw * p.bh);
     uint32_t acc = 0, acc_phase = 0;
@@ -193,7 +196,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
       // two 16-column chunks per iteration: the global loads of both (accumulate / mask operands) and both TMEM
       // loads are in flight before the first use
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
         const bool two = c0 + 16 < p.block_n;                       // warp-uniform
         const int cola = t.n0 + c0, colb = cola + 16;
         const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
@@ -218,7 +221,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // 4 arrivals (one per epilogue warp) release it
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // 8 arrivals (one per epilogue warp) release it
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
