@@ -170,6 +170,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.set_num_threads(max(1, usable_cores() // max(1, world)))     # host-side setup (synthetic data) shares the cores
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
