@@ -81,6 +81,16 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
                      const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
                      cudaStream_t s);
 
+// one launch finalises the weight (and bias) gradients of many layers: split-K partial reduction in fixed order,
+// BN-fold chain rule, 1/loss-scale, reference layout [co][ci][tap]
+constexpr int FIN_MAX = 36;
+struct FinalizeEntry {
+  const float* partial; const float* mult; float* dw; const float* bias_partial; float* db;
+  int splits, taps, Cout, Cin, block0, pad_;
+};
+struct FinalizeTable { int n, total_blocks; FinalizeEntry e[FIN_MAX]; };
+int launch_wgrad_finalize_all(const FinalizeTable& t, float out_scale, int accumulate, cudaStream_t s);
+
 // FAST-mode vectorised glue (glue_fp16.cu)
 int launch_maxpool_fwd_h8(View src, View dst, int F, int k, int stride, int pad, uint8_t* argmax, cudaStream_t s);
 int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pad, const uint8_t* argmax, int accumulate,

@@ -63,6 +63,7 @@ struct Op {
   size_t argmax_off = 0;
   int grad_accumulate = 0;  // backward: dIn += (another consumer wrote first)
   int wsplits = 1, wrows = 0;
+  size_t partial_off = 0, bias_partial_off = 0;   // this layer's split-K partials (own region: finalised in one batch)
   UmmaConvPlan umma;        // tcgen05 forward plan (FAST mode, stride-1 layers)
   UmmaConvPlan umma_dgrad;  // tcgen05 data-gradient plan
   UmmaWgradPlan umma_wgrad; // tcgen05 weight-gradient plan
@@ -108,6 +109,7 @@ struct ssnb_engine {
   char* ws = nullptr;
   bool weights_ready = false;
   std::vector<float*> dw, db;
+  std::vector<int> pending_finalize;  // conv ops whose partials wait for the batched finalize of this backward
   int grad_accumulate = 0;          // 1: dw/db += (autograd-style accumulation into existing .grad), 0: overwrite
   std::string error;
   long long launches0 = 0;
@@ -292,6 +294,15 @@ static void plan(ssnb_engine* e) {
     }
   }
   e->partial_off = off; e->partial_bytes = pmax; off = align_up(off + pmax, 1024);
+  if (e->cfg.training)
+    for (Op& o : e->ops)
+      if (o.kind == OP_CONV) {
+        const ConvSpec& c = e->convs[o.conv];
+        size_t need = (size_t)o.wsplits * c.k * c.k * c.cout * c.cin * 4;
+        if (o.conv == 0 && e->fp16) need = std::max(need, (size_t)128 * 16 * 64 * e->Cs * 4);
+        o.partial_off = off; off = align_up(off + need, 1024);
+        o.bias_partial_off = off; off = align_up(off + (size_t)std::max(o.wsplits, 128) * c.cout * 4, 256);
+      }
   e->bpartial_off = off; off = align_up(off + (size_t)1024 * 512 * 4, 1024);   // column-sum partials: <= 1024 CTAs x 512 channels
   e->ws_bytes = off;
 }
@@ -365,7 +376,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   const View x = e->view(o.in_val, false), y = e->view(o.out_val, false);
   const View dx = e->view(o.in_val, true), dy = e->view(o.out_val, true);
   const float* scale = (const float*)(e->ws + e->packed[o.conv].scale);
-  float* partial = (float*)(e->ws + e->partial_off);
+  float* partial = (float*)(e->ws + o.partial_off);
   float* bpartial = (float*)(e->ws + e->bpartial_off);
   const long long M = (long long)F * y.H * y.W;
   float* dbp = (e->db.size() && e->db[o.conv]) ? e->db[o.conv] : nullptr;
@@ -391,9 +402,10 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if ((rc = launch_upsample2_zero(dy, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;   // dz at input resolution
   if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
     const bool bias_w = full && e->fold_pools && o.dy_premasked && o.bias_in_wgrad && dbp;
-    float* bp = bias_w ? bpartial + 64 : nullptr;
+    float* bp = bias_w ? (float*)(e->ws + o.bias_partial_off) : nullptr;
     if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, bp))) return rc;
-    if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
+    if (full && e->fold_pools && o.conv != 0) { e->pending_finalize.push_back((int)(&o - e->ops.data())); rc = 0; }   // batched at the end of the backward
+    else if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
     else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s, bp, dbp);
     if (rc) return rc;
   } else if (e->dw.size() && e->dw[o.conv]) {
@@ -501,7 +513,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       if (rc) return h->fail(rc, "umma conv1 bind: " + ssnb::thread_error());
       if (use_wgrad) {
         rc = umma_wgrad_bind_taps(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), xs, h->F, Ck, c.cout, 4, dy, dx,
-                                  (float*)(h->ws + h->partial_off), 128);
+                                  (float*)(h->ws + o.partial_off), 128);
         if (rc) return h->fail(rc, "umma conv1 wgrad bind: " + ssnb::thread_error());
       }
       continue;
@@ -520,7 +532,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     if (use_wgrad) {
       // stride-2 layers: dz at its own (output) resolution, the x boxes step over the input with element stride 2
       rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), in, h->F, c.cin, c.cout, c.k, c.pad,
-                           (float*)(h->ws + h->partial_off), o.wsplits, c.stride);
+                           (float*)(h->ws + o.partial_off), o.wsplits, c.stride);
       if (rc) return h->fail(rc, "umma_wgrad_bind(" + c.id + "): " + ssnb::thread_error());
     }
   }
@@ -584,8 +596,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
           if (h->vals[v].buf == ov.buf && h->vals[v].coff == 0 && h->vals[v].C == h->bufs[ov.buf].C && first_consumer[v] >= 0) { w = (int)v; break; }
       }
       if (first_consumer[w] >= 0 && h->ops[first_consumer[w]].dgrad_masks) o.dy_premasked = true;
-      o.bias_in_wgrad = o.dy_premasked && o.conv != 0 && o.umma_wgrad.enabled && o.umma_wgrad.p.taps_per_cta * o.umma_wgrad.p.mma_n + 16 <= 512 &&
-                        o.umma_wgrad.p.splits * h->convs[o.conv].cout <= 1024 * 512 - 64;
+      o.bias_in_wgrad = o.dy_premasked && o.conv != 0 && o.umma_wgrad.enabled && o.umma_wgrad.p.taps_per_cta * o.umma_wgrad.p.mma_n + 16 <= 512;
     }
   }
   return SSNB_OK;
@@ -668,12 +679,32 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   if (!h->cfg.training) return h->fail(SSNB_ESTATE, "engine created without training=1");
   if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
   ssnb_bind_grads(h, dw, db);
+  h->pending_finalize.clear();
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
     const Op& o = h->ops[i];
     int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
     if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s, h->fold_pools && o.dgrad_masks);   // ... one fused data gradient
     if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
+  }
+  // one (or two) launches reduce the split-K partials of every tensor-core weight gradient of this backward
+  {
+    const float gs = h->fp16 ? h->cfg.grad_scale : 1.0f;
+    FinalizeTable t; t.n = 0; t.total_blocks = 0;
+    auto flush = [&]() -> int { int rc = launch_wgrad_finalize_all(t, 1.0f / gs, h->grad_accumulate, s); t.n = 0; t.total_blocks = 0; return rc; };
+    for (int oi : h->pending_finalize) {
+      const Op& o = h->ops[oi];
+      const ConvSpec& c = h->convs[o.conv];
+      FinalizeEntry& q = t.e[t.n];
+      q.partial = (const float*)(h->ws + o.partial_off); q.mult = (const float*)(h->ws + h->packed[o.conv].scale); q.dw = h->dw[o.conv];
+      const bool bias_w = o.dy_premasked && o.bias_in_wgrad && h->db.size() && h->db[o.conv];
+      q.bias_partial = bias_w ? (const float*)(h->ws + o.bias_partial_off) : nullptr; q.db = bias_w ? h->db[o.conv] : nullptr;
+      q.splits = o.umma_wgrad.p.splits; q.taps = c.k * c.k; q.Cout = c.cout; q.Cin = c.cin; q.block0 = t.total_blocks; q.pad_ = 0;
+      t.total_blocks += (int)(((long long)q.taps * q.Cout * q.Cin + 255) / 256);
+      if (++t.n == FIN_MAX) if (int rc = flush()) { h->pending_finalize.clear(); return h->fail(rc, "finalize: " + ssnb::thread_error()); }
+    }
+    h->pending_finalize.clear();
+    if (int rc = flush()) return h->fail(rc, "finalize: " + ssnb::thread_error());
   }
   return SSNB_OK;
 }

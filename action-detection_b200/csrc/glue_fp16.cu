@@ -27,10 +27,13 @@ __global__ void maxpool_fwd_h8(const __half* __restrict__ src, int H, int W, int
   const int G = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * OH * OW * G) return;
-  const int g = (int)(i % G);
-  const long long p = i / G;
-  const int ox = (int)(p % OW), oy = (int)((p / OW) % OH);
-  const long long f = p / ((long long)OW * OH);
+  // 32-bit index arithmetic (thread count < 2^31); 64-bit only for the final byte offsets
+  const unsigned iu = (unsigned)i;
+  const int g = (int)(iu % (unsigned)G);
+  const unsigned pu = iu / (unsigned)G;
+  const int ox = (int)(pu % (unsigned)OW), oy = (int)((pu / (unsigned)OW) % (unsigned)OH);
+  const long long p = pu;
+  const long long f = pu / (unsigned)(OW * OH);
   float best[8];
   int bi[8];
   bool first = true;
@@ -61,10 +64,12 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
   const int G = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * H * W * G) return;
-  const int g = (int)(i % G);
-  const long long p = i / G;
-  const int ix = (int)(p % W), iy = (int)((p / W) % H);
-  const long long f = p / ((long long)W * H);
+  const unsigned iu = (unsigned)i;
+  const int g = (int)(iu % (unsigned)G);
+  const unsigned pu = iu / (unsigned)G;
+  const int ix = (int)(pu % (unsigned)W), iy = (int)((pu / (unsigned)W) % (unsigned)H);
+  const long long p = pu;
+  const long long f = pu / (unsigned)(W * H);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   // windows covering this pixel: oy in [ceil((iy+pad-k+1)/stride), floor((iy+pad)/stride)] (<= 2 per axis for k3/s2)
   const int ty0 = iy + pad - k + 1, tx0 = ix + pad - k + 1;
@@ -132,9 +137,10 @@ __global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C,
   const int G = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * W * G) return;
-  const int g = (int)(i % G);
-  const int x = (int)((i / G) % W);
-  const long long f = i / ((long long)G * W);
+  const unsigned iu = (unsigned)i;
+  const int g = (int)(iu % (unsigned)G);
+  const int x = (int)((iu / (unsigned)G) % (unsigned)W);
+  const long long f = iu / (unsigned)(G * W);
   float prev[8], cur[8], nxt[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
@@ -275,8 +281,9 @@ __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_h8(__half* __restri
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < lanes) {
     for (long long r = r0 + rl; r < r1; r += lanes) {
-      const int ix = (int)(r % W), iy = (int)((r / W) % H);
-      const long long f = r / ((long long)W * H);
+      const unsigned ru = (unsigned)r;                       // rows < 2^31
+      const int ix = (int)(ru % (unsigned)W), iy = (int)((ru / (unsigned)W) % (unsigned)H);
+      const long long f = ru / (unsigned)(W * H);
       const int ty0 = iy + pad - k + 1, tx0 = ix + pad - k + 1;
       const int oy_lo = ty0 > 0 ? (ty0 + stride - 1) / stride : 0, oy_hi = min((iy + pad) / stride, OH - 1);
       const int ox_lo = tx0 > 0 ? (tx0 + stride - 1) / stride : 0, ox_hi = min((ix + pad) / stride, OW - 1);

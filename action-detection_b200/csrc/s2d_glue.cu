@@ -73,10 +73,12 @@ __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin
   const int H2 = H / 2, W2 = W / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * H2 * W2 * 4) return;
-  const int ds = (int)(i % 4);
-  const long long p = i / 4;
-  const int x2 = (int)(p % W2), y2 = (int)((p / W2) % H2);
-  const long long f = p / ((long long)W2 * H2);
+  const unsigned iu = (unsigned)i;                 // < 2^31 threads: 32-bit index arithmetic
+  const int ds = (int)(iu & 3u);
+  const unsigned pu = iu >> 2;
+  const int x2 = (int)(pu % (unsigned)W2), y2 = (int)((pu / (unsigned)W2) % (unsigned)H2);
+  const long long p = pu;
+  const long long f = pu / (unsigned)(W2 * H2);
   __align__(16) __half v[CS];
 #pragma unroll
   for (int c = 0; c < CS; ++c) v[c] = __float2half_rn(0.f);
@@ -103,10 +105,12 @@ __global__ void upsample2_zero_kernel(const __half* __restrict__ src, int OH, in
   const long long total = (long long)F * H * W * G;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int g = (int)(i % G);
-  const long long p = i / G;
-  const int x = (int)(p % W), y = (int)((p / W) % H);
-  const long long f = p / ((long long)W * H);
+  const unsigned iu = (unsigned)i;
+  const int g = (int)(iu % (unsigned)G);
+  const unsigned pu = iu / (unsigned)G;
+  const int x = (int)(pu % (unsigned)W), y = (int)((pu / (unsigned)W) % (unsigned)H);
+  const long long p = pu;
+  const long long f = pu / (unsigned)(W * H);
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   if (!(x & 1) && !(y & 1) && y / 2 < OH && x / 2 < OW)
     v = __ldg(reinterpret_cast<const uint4*>(src + ((f * OH + y / 2) * OW + x / 2) * spitch + scoff + g * 8));

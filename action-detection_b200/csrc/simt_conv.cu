@@ -284,6 +284,27 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
   *o = (accumulate ? *o : 0.f) + s * mult[co] * out_scale;
 }
 
+__global__ void wgrad_finalize_all_kernel(const __grid_constant__ FinalizeTable t, float out_scale, int accumulate) {
+  int ei = 0;
+  while (ei + 1 < t.n && (int)blockIdx.x >= t.e[ei + 1].block0) ++ei;       // <= 36 entries, uniform per block
+  const FinalizeEntry& q = t.e[ei];
+  const long long total = (long long)q.taps * q.Cout * q.Cin;
+  const long long i = (long long)(blockIdx.x - q.block0) * blockDim.x + threadIdx.x;
+  if (q.bias_partial && q.db && i < q.Cout) {
+    float sb = 0.f;
+    for (int sp = 0; sp < q.splits; ++sp) sb += q.bias_partial[(long long)sp * q.Cout + i];
+    q.db[i] = (accumulate ? q.db[i] : 0.f) + sb * q.mult[i] * out_scale;
+  }
+  if (i >= total) return;
+  const int ci = (int)(i % q.Cin);
+  const int co = (int)((i / q.Cin) % q.Cout);
+  const int tap = (int)(i / ((long long)q.Cin * q.Cout));
+  float s = 0.f;
+  for (int sp = 0; sp < q.splits; ++sp) s += q.partial[(long long)sp * total + i];
+  float* o = q.dw + ((long long)co * q.Cin + ci) * q.taps + tap;
+  *o = (accumulate ? *o : 0.f) + s * q.mult[co] * out_scale;
+}
+
 // column sums of dz: stage 1 partial[split][c], stage 2 db[c] = mult[c]*out_scale*sum
 template <typename T>
 __global__ void bias_grad_partial_kernel(const T* __restrict__ dz, long long rows, int C, int pitch, int coff,
@@ -350,6 +371,13 @@ int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, 
   wgrad_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, taps, Cout, Cin, mult,
                                                                        out_scale, dw_ref, accumulate, bias_partial, db);
   SSNB_LAUNCH_CHECK("wgrad_finalize_kernel");
+  return 0;
+}
+
+int launch_wgrad_finalize_all(const FinalizeTable& t, float out_scale, int accumulate, cudaStream_t s) {
+  if (t.n <= 0) return 0;
+  wgrad_finalize_all_kernel<<<(unsigned)t.total_blocks, 256, 0, s>>>(t, out_scale, accumulate);
+  SSNB_LAUNCH_CHECK("wgrad_finalize_all_kernel");
   return 0;
 }
 

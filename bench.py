@@ -175,6 +175,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SSNB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     prec = _lib.FAST_FP16 if args.precision == "fast" else _lib.EXACT_FP32
