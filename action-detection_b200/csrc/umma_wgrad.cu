@@ -207,6 +207,7 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   while (p.taps_per_cta > 1 && p.taps_per_cta * p.mma_n > 512) --p.taps_per_cta;
   if (p.taps_per_cta > ntaps) p.taps_per_cta = ntaps;
   p.tap_groups = (ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
+  p.taps_per_cta = (ntaps + p.tap_groups - 1) / p.tap_groups;        // balance the groups (9 taps: 3+3+3 rather than 4+4+1)
   const int ptiles = p.tiles_w * p.tiles_h * p.tiles_f;
   const int ctas = p.m_tiles * p.n_tiles * p.tap_groups;
   int splits = (2 * ctx.num_sms + ctas - 1) / ctas;
