@@ -461,6 +461,12 @@ def test_test_forward_and_prepare_test_fc(backbone_rgb):
     ref_feat = O.backbone_forward(backbone_rgb, x.cpu(), 3)
     assert rel_l2(base_out, ref_feat) < 1e-4
     assert rel_l2(scores, torch.nn.functional.linear(ref_feat, w_ref, b_ref)) < 1e-4
+    # the same inference call on the tensor-core path (forward-only engine, no gradient buffers)
+    from ssn_b200 import _lib
+    model.set_precision(_lib.FAST_FP16)
+    with torch.no_grad():
+        scores_f, base_f = model(x, None, None, None, None)
+    assert rel_l2(base_f, ref_feat) < 5e-2 and rel_l2(scores_f, scores) < 5e-2
 
 
 def test_fast_fused_vs_unfused_and_oracle(backbone_rgb):
