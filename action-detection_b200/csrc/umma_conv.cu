@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #include "umma_conv.cuh"
 #include "umma_dev.cuh"
@@ -82,6 +83,62 @@ __device__ __forceinline__ void epilogue_chunk(const UmmaConvParams& p, const ui
 #pragma unroll
   for (int j = 0; j < 4; ++j) { g0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); g1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]); }
   dst[0] = q0; dst[1] = q1;
+}
+
+// Epilogue role shared by both kernels: for every tile of this CTA wait for the accumulator, then TMEM -> registers ->
+// bias/ReLU (forward) or accumulate/mask (data gradient) -> fp16 NHWC stores.  Row r of the tile is pixel
+// (x, y, f) = (r % bw, (r / bw) % bh, r / (bw*bh)) in the classic layout and (r % bw, r / (bw*bf), (r / bw) % bf) in
+// the halo layout (rows ordered y-major, then frame, so that tap views have one uniform group stride).
+__device__ __forceinline__ void epilogue_loop(const UmmaConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                              int warp, int lane, int total_tiles) {
+  const int quad = warp & 3;
+  const int cpar = (warp - 2) >> 2;
+  const int row = quad * 32 + lane;
+  int rw, rh, rf;
+  if (p.halo) { rw = row % p.bw; rf = (row / p.bw) % p.bf; rh = row / (p.bw * p.bf); }
+  else { rw = row % p.bw; rh = (row / p.bw) % p.bh; rf = row / (p.bw * p.bh); }
+  uint32_t acc = 0, acc_phase = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
+    const int os = p.out_stride;
+    const bool valid = (rf < p.bf) && (rh < p.bh) && (w < p.W) && (h < p.H) && (f < p.F) && (w % os == 0) && (h % os == 0);
+    const long long opix = (long long)(f * p.OH + h / os) * p.OW + w / os;
+    __half* orow = p.out + opix * p.out_pitch + p.out_coff;
+    __half* orow2 = p.out2 + opix * p.out2_pitch + p.out2_coff - p.n_split;
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+    // two 16-column chunks per iteration: the global loads of both (accumulate / mask operands) and both TMEM
+    // loads are in flight before the first use
+    for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
+      const bool two = c0 + 16 < p.block_n;                       // warp-uniform
+      const int cola = t.n0 + c0, colb = cola + 16;
+      const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
+      uint4* da = reinterpret_cast<uint4*>((cola < p.n_split ? orow : orow2) + cola);
+      uint4* db2 = reinterpret_cast<uint4*>((colb < p.n_split ? orow : orow2) + colb);
+      uint4 oa0 = {}, oa1 = {}, ob0 = {}, ob1 = {}, ya0 = {}, ya1 = {}, yb0 = {}, yb1 = {};
+      if (p.accumulate) {
+        if (va) { oa0 = da[0]; oa1 = da[1]; }
+        if (vb) { ob0 = db2[0]; ob1 = db2[1]; }
+      }
+      if (p.mask_y) {
+        const uint4* my = reinterpret_cast<const uint4*>(p.mask_y + opix * p.mask_pitch + p.mask_coff + cola);
+        if (va) { ya0 = __ldg(my); ya1 = __ldg(my + 1); }
+        if (vb) { yb0 = __ldg(my + 2); yb1 = __ldg(my + 3); }
+      }
+      uint32_t ra[16], rb[16];
+      tmem_ld16(taddr + c0, ra);
+      if (two) tmem_ld16(taddr + c0 + 16, rb);
+      tmem_ld_wait();
+      if (va) epilogue_chunk(p, ra, cola, da, oa0, oa1, ya0, ya1);
+      if (vb) epilogue_chunk(p, rb, colb, db2, ob0, ob1, yb0, yb1);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // 8 arrivals (one per epilogue warp) release it
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -178,52 +235,131 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===== epilogue warps 2..9; TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
-    const int quad = warp & 3;
-    const int cpar = (warp - 2) >> 2;
-    const int row = quad * 32 + lane;
-    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rf = row / (p.bw * p.bh);
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
-      const int os = p.out_stride;
-      const bool valid = (rf < p.bf) && (w < p.W) && (h < p.H) && (f < p.F) && (w % os == 0) && (h % os == 0);
-      const long long opix = (long long)(f * p.OH + h / os) * p.OW + w / os;
-      __half* orow = p.out + opix * p.out_pitch + p.out_coff;
-      __half* orow2 = p.out2 + opix * p.out2_pitch + p.out2_coff - p.n_split;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-      // two 16-column chunks per iteration: the global loads of both (accumulate / mask operands) and both TMEM
-      // loads are in flight before the first use
-      for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
-        const bool two = c0 + 16 < p.block_n;                       // warp-uniform
-        const int cola = t.n0 + c0, colb = cola + 16;
-        const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
-        uint4* da = reinterpret_cast<uint4*>((cola < p.n_split ? orow : orow2) + cola);
-        uint4* db2 = reinterpret_cast<uint4*>((colb < p.n_split ? orow : orow2) + colb);
-        uint4 oa0 = {}, oa1 = {}, ob0 = {}, ob1 = {}, ya0 = {}, ya1 = {}, yb0 = {}, yb1 = {};
-        if (p.accumulate) {
-          if (va) { oa0 = da[0]; oa1 = da[1]; }
-          if (vb) { ob0 = db2[0]; ob1 = db2[1]; }
+    epilogue_loop(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- halo variant ------------------------------------------------------------------------------------------------
+// Same roles, two operand rings: the A ring holds one halo box per K chunk (tile + filter border, rows ordered
+// [y][frame][x]), the B ring one weight slab per (tap, K chunk).  A tap is a descriptor view into the halo box: start
+// shifted by (dy*bf*pitch + dx) pixel rows, 8-row groups `a_sbo` bytes apart.  Per K chunk the CTA stages
+// a_stage_bytes + ntaps*b_stage_bytes instead of ntaps*(16 KiB + b_stage_bytes).
+constexpr int HALO_A_STAGES_MAX = 4;
+constexpr int HALO_B_STAGES_MAX = 8;
+constexpr int HALO_PIPE_BYTES = 224 * 1024;
+constexpr int HALO_SMEM_BYTES = HALO_PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HALO_PIPE_BYTES);
+  uint64_t* a_full = bars;                                   // [HALO_A_STAGES_MAX]
+  uint64_t* a_empty = a_full + HALO_A_STAGES_MAX;
+  uint64_t* b_full = a_empty + HALO_A_STAGES_MAX;            // [HALO_B_STAGES_MAX]
+  uint64_t* b_empty = b_full + HALO_B_STAGES_MAX;
+  uint64_t* tfull_bar = b_empty + HALO_B_STAGES_MAX;         // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: one halo box per step (step = (tile, K chunk)), one weight slab per (step, tap) =====
+    if (lane == 0) {
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      const uint32_t a_tx = (uint32_t)(p.a_loads * p.a_load_bytes);
+      const uint32_t b_tx = (uint32_t)p.block_n * BLOCK_K * 2;
+      auto issue_a = [&](int tile, int kc) {
+        const TileCoord t = decode_tile(p, tile);
+        mbar_wait(&a_empty[as], aph ^ 1);
+        uint8_t* sa = smem + as * p.a_stage_bytes;
+        mbar_expect_tx(&a_full[as], a_tx);
+        for (int l = 0; l < p.a_loads; ++l)      // tensor-map dims are {C, W, F, H}
+          tma_load_4d(sa + l * p.a_load_bytes, &tmap_a, &a_full[as], kc * BLOCK_K, t.w0 + p.halo_x0 + p.a_load_dx[l], t.f0, t.h0 + p.halo_y0);
+        if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
+      };
+      int tile = blockIdx.x, kc = 0;
+      if (tile < total_tiles) issue_a(tile, kc);
+      while (tile < total_tiles) {
+        int ntile = tile, nkc = kc + 1;
+        if (nkc == p.kchunks) { nkc = 0; ntile += gridDim.x; }
+        // with >= 3 A stages the next halo box goes out before this step's weight slabs (deeper prefetch); with 2 it
+        // must follow them, or the producer would sit on a_empty while the B ring drains
+        if (p.a_stages >= 3 && ntile < total_tiles) issue_a(ntile, nkc);
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          mbar_expect_tx(&b_full[bs], b_tx);
+          tma_load_3d(smem_b + bs * p.b_stage_bytes, &tmap_b, &b_full[bs], kc * BLOCK_K, n0, tap);
+          if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
         }
-        if (p.mask_y) {
-          const uint4* my = reinterpret_cast<const uint4*>(p.mask_y + opix * p.mask_pitch + p.mask_coff + cola);
-          if (va) { ya0 = __ldg(my); ya1 = __ldg(my + 1); }
-          if (vb) { yb0 = __ldg(my + 2); yb1 = __ldg(my + 3); }
-        }
-        uint32_t ra[16], rb[16];
-        tmem_ld16(taddr + c0, ra);
-        if (two) tmem_ld16(taddr + c0 + 16, rb);
-        tmem_ld_wait();
-        if (va) epilogue_chunk(p, ra, cola, da, oa0, oa1, ya0, ya1);
-        if (vb) epilogue_chunk(p, rb, colb, db2, ob0, ob1, yb0, yb1);
+        if (p.a_stages < 3 && ntile < total_tiles) issue_a(ntile, nkc);
+        tile = ntile; kc = nkc;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // 8 arrivals (one per epilogue warp) release it
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.block_n);
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + as * p.a_stage_bytes);
+          const int kvalid = p.K - kc * BLOCK_K;
+          const int nk = kvalid >= BLOCK_K ? BLOCK_K / UMMA_K : (kvalid + UMMA_K - 1) / UMMA_K;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem_b + bs * p.b_stage_bytes);
+            const uint32_t av = sa + p.tap_aoff[tap];
+            const uint32_t abo = p.tap_abo[tap];
+            for (int k = 0; k < nk; ++k)
+              umma_f16(d_tmem, make_desc_k_sw128_view(av + k * UMMA_K * 2, p.a_sbo, abo), make_desc_k_sw128(sb + k * UMMA_K * 2), idesc,
+                       (kc | tap | k) ? 1u : 0u);
+            umma_commit(&b_empty[bs]);
+            if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    epilogue_loop(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles);
   }
 
   tc_fence_before();
@@ -335,6 +471,66 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   return 0;
 }
 
+// Upgrade a bound multi-tap stride-1 plan to halo mode (one A box per K chunk, taps = descriptor views).
+//   SSNB_HALO=0          keep the classic per-tap boxes
+//   SSNB_HALO_MODE=m     how horizontal shifts are realised: 0 (default) halo rows padded to a 16-pixel pitch + descriptor
+//                        base_offset; 1 same without base_offset; 2 exact pitch (bw + halo), no base_offset; 3 exact pitch +
+//                        base_offset; 4 one box per horizontal shift (every view 1024-byte aligned)
+//   SSNB_HALO_MIN_W=w    smallest image width that uses it (default 14)
+int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F) {
+  UmmaConvParams& p = plan.p;
+  p.halo = 0;
+  const char* en = getenv("SSNB_HALO");
+  if (en && en[0] == '0') return 0;
+  if (!plan.enabled || p.ntaps < 2 || p.a_stride != 1 || p.out_stride != 1 || p.kchunks_a1 != p.kchunks) return 0;
+  const char* mw = getenv("SSNB_HALO_MIN_W");
+  if (a.W < (mw ? atoi(mw) : 14)) return 0;
+  const char* md = getenv("SSNB_HALO_MODE");
+  const int mode = md ? atoi(md) : 0;
+  int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  for (int t = 0; t < p.ntaps; ++t) {
+    x0 = std::min(x0, p.tap_dx[t]); x1 = std::max(x1, p.tap_dx[t]);
+    y0 = std::min(y0, p.tap_dy[t]); y1 = std::max(y1, p.tap_dy[t]);
+  }
+  const int xh = x1 - x0, yh = y1 - y0;
+  int bh = 8;
+  while (bh > 1 && a.H % bh) bh >>= 1;
+  const int bw = 8, bf = BLOCK_M / (bw * bh);
+  int loads = 1, pw;
+  if (xh == 0) pw = bw;
+  else if (mode == 4) { loads = xh + 1; pw = bw; }
+  else if (mode >= 2) pw = bw + xh;
+  else pw = 16;
+  const int bhh = bh + yh;
+  if (loads > 4 || bw + xh > pw * (loads > 1 ? 2 : 1) || bhh > 256 || bf > 256) return 0;
+  const int a_load_bytes = pw * bf * bhh * BLOCK_K * 2;
+  const int a_stage = (loads * a_load_bytes + 1023) / 1024 * 1024;
+  const int b_stage = (p.block_n * BLOCK_K * 2 + 1023) / 1024 * 1024;
+  int a_stages = 3;
+  if ((HALO_PIPE_BYTES - 3 * a_stage) / b_stage < 4) a_stages = 2;
+  int b_stages = (HALO_PIPE_BYTES - a_stages * a_stage) / b_stage;
+  if (b_stages < 3) return 0;                               // does not fit: stay classic
+  if (b_stages > HALO_B_STAGES_MAX) b_stages = HALO_B_STAGES_MAX;
+  p.halo = 1;
+  p.bw = bw; p.bh = bh; p.bf = bf;
+  p.tiles_w = (a.W + bw - 1) / bw; p.tiles_h = (a.H + bh - 1) / bh; p.tiles_f = (F + bf - 1) / bf;
+  p.a_stages = a_stages; p.b_stages = b_stages; p.a_stage_bytes = a_stage; p.b_stage_bytes = b_stage;
+  p.a_loads = loads; p.a_load_bytes = a_load_bytes; p.halo_x0 = x0; p.halo_y0 = y0; p.a_sbo = pw * BLOCK_K * 2;
+  for (int l = 0; l < 4; ++l) p.a_load_dx[l] = loads > 1 ? l : 0;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int l = loads > 1 ? p.tap_dx[t] - x0 : 0;
+    const int dxl = loads > 1 ? 0 : p.tap_dx[t] - x0;
+    p.tap_aoff[t] = l * a_load_bytes + ((p.tap_dy[t] - y0) * bf * pw + dxl) * BLOCK_K * 2;
+    p.tap_abo[t] = (mode == 0 || mode == 3) ? ((p.tap_aoff[t] >> 7) & 7) : 0;
+  }
+  // halo box: dims {C, W, F, H} so that shared memory holds [y][frame][x][64 ch]
+  cuuint64_t dims[4] = {(cuuint64_t)p.K, (cuuint64_t)a.W, (cuuint64_t)F, (cuuint64_t)a.H};
+  cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)pw, (cuuint32_t)bf, (cuuint32_t)bhh};
+  if (int rc = encode(ctx, &plan.tmap_a, 4, reinterpret_cast<__half*>(a.base) + a.coff, dims, str, box)) { plan.enabled = false; return rc; }
+  return 0;
+}
+
 }  // namespace
 
 int umma_resolve_encode(UmmaContext& ctx) { return resolve_encode(ctx); }
@@ -351,7 +547,7 @@ int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out,
   if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, ntaps, 1, w_tap_n_k)) return rc;
   for (int t = 0; t < ntaps; ++t) { plan.p.tap_dy[t] = dy[t]; plan.p.tap_dx[t] = dx[t]; }
   plan.p.bias = bias; plan.p.relu = relu; plan.p.accumulate = 0;
-  return 0;
+  return try_halo(ctx, plan, in, F);
 }
 
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
@@ -365,7 +561,7 @@ int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, 
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = r - pad; plan.p.tap_dx[r * k + s] = s - pad; }
   plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;
-  return 0;
+  return try_halo(ctx, plan, in, F);
 }
 
 int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
@@ -375,7 +571,7 @@ int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx,
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = pad - r; plan.p.tap_dx[r * k + s] = pad - s; }
   plan.p.bias = nullptr; plan.p.relu = 0; plan.p.accumulate = accumulate;
-  return 0;
+  return try_halo(ctx, plan, dz, F);
 }
 
 int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out1, View out2, int F, int cin, int n1, int n2,
@@ -430,6 +626,16 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
   if (mask && plan.mask_y) { p.mask_y = plan.mask_y; p.mask_pitch = plan.mask_pitch; p.mask_coff = plan.mask_coff; }
   const int total = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
   const int grid = total < ctx.num_sms ? total : ctx.num_sms;
+  if (p.halo) {
+    if (!ctx.attr_set_halo) {
+      if (cudaFuncSetAttribute(umma_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES) != cudaSuccess) {
+        set_thread_error("umma conv (halo): cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
+      ctx.attr_set_halo = true;
+    }
+    umma_conv_halo_kernel<<<grid, NUM_THREADS, HALO_SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_b, p);
+    SSNB_LAUNCH_CHECK("umma_conv_halo_kernel");
+    return 0;
+  }
   umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, p);
   SSNB_LAUNCH_CHECK("umma_conv_kernel");
   return 0;

@@ -19,7 +19,7 @@ struct UmmaContext {
   bool active = false;
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
   int num_sms = 148;
-  bool attr_set = false;
+  bool attr_set = false, attr_set_halo = false;
 };
 
 struct UmmaConvParams {
@@ -39,6 +39,16 @@ struct UmmaConvParams {
   int kchunks_a1, K1;             // K chunks [0, kchunks_a1) come from tmap_a (K1 real channels), the rest from tmap_a2
   int n_split;                    // output columns >= n_split go to out2 (second destination), else to out
   __half* out2; int out2_pitch, out2_coff;
+  // halo mode (3x3 stride-1 layers, conv1): ONE A box per K chunk covers the tile plus its filter halo, stored
+  // [y][frame][x][64 ch]; every tap is a shifted UMMA descriptor view into it (no per-tap re-staging of A)
+  int halo;
+  int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
+  int a_loads, a_load_bytes;      // TMA loads per A stage (1: full halo box; >1: one box per horizontal shift)
+  int halo_x0, halo_y0;           // box origin relative to the tile origin (min dx, min dy)
+  int a_load_dx[4];               // extra W shift of each load
+  int a_sbo;                      // bytes between consecutive 8-pixel row groups of a tap view
+  int tap_aoff[UMMA_MAX_TAPS];    // byte offset of each tap's view inside the A stage
+  int tap_abo[UMMA_MAX_TAPS];     // descriptor base_offset of each tap's view
   // data gradient that is the LAST writer of its output: fuse dz = dy * (y > 0), y = activation of the same value
   const __half* mask_y; int mask_pitch, mask_coff;
 };

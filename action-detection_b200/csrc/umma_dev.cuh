@@ -70,6 +70,19 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
   return d;
 }
 
+// same, for a view into a larger (halo) tile: `sbo_bytes` between 8-row groups, start not necessarily 1024-byte
+// aligned (base_offset = descriptor bits [49,52), the row phase of the start address inside the swizzle atom)
+__device__ __forceinline__ uint64_t make_desc_k_sw128_view(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
