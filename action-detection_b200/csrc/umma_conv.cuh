@@ -19,7 +19,7 @@ struct UmmaContext {
   bool active = false;
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
   int num_sms = 148;
-  bool attr_set = false, attr_set_halo = false;
+  bool attr_set = false, attr_set_halo = false, attr_set_pair = false;
 };
 
 struct UmmaConvParams {
@@ -41,14 +41,16 @@ struct UmmaConvParams {
   __half* out2; int out2_pitch, out2_coff;
   // halo mode (3x3 stride-1 layers, conv1): ONE A box per K chunk covers the tile plus its filter halo, stored
   // [y][frame][x][64 ch]; every tap is a shifted UMMA descriptor view into it (no per-tap re-staging of A)
+  int ablate;                     // timing experiments (SSNB_ABLATE bit mask): 1 no stores, 2 no bias loads, 4 empty epilogue, 8 no MMAs
+  int epi_direct;                 // epilogue variant: 1 = per-thread row stores, 0 = shared-memory transposed, coalesced
   int halo;
+  int pair;                       // CTA-pair kernel (cta_group::2): tiles are (N tile, pair of M tiles)
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
   int a_loads, a_load_bytes;      // TMA loads per A stage (1: full halo box; >1: one box per horizontal shift)
   int halo_x0, halo_y0;           // box origin relative to the tile origin (min dx, min dy)
   int a_load_dx[4];               // extra W shift of each load
   int a_sbo;                      // bytes between consecutive 8-pixel row groups of a tap view
   int tap_aoff[UMMA_MAX_TAPS];    // byte offset of each tap's view inside the A stage
-  int tap_abo[UMMA_MAX_TAPS];     // descriptor base_offset of each tap's view
   // data gradient that is the LAST writer of its output: fuse dz = dy * (y > 0), y = activation of the same value
   const __half* mask_y; int mask_pitch, mask_coff;
 };
@@ -57,6 +59,8 @@ struct UmmaConvPlan {
   bool enabled = false;
   const __half* mask_y = nullptr; int mask_pitch = 0, mask_coff = 0;   // applied only when launched with mask=true
   CUtensorMap tmap_a, tmap_a2, tmap_b;
+  // geometry of the weight map (kept so that a variant can re-encode it with another box)
+  const __half* b_ptr = nullptr; unsigned long long b_dims[3] = {0, 0, 0}, b_strides[2] = {0, 0};
   UmmaConvParams p;
 };
 

@@ -34,8 +34,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tot_us, tot_fl = 0.0, 0.0
+    only = os.environ.get("SSNB_LAYERS")
+    only = set(only.split(",")) if only else None
     for i, (kind, iname, oname) in enumerate(e.ops()):
-        if kind != "conv":
+        if kind != "conv" or (only and oname[:-3] not in only):
             continue
         ci, co, k, s, p = spec[oname[:-3]]
         _c, hh, ww = e.value_shape(oname)
