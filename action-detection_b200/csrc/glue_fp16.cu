@@ -130,51 +130,69 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
   *reinterpret_cast<uint4*>(q) = pack8(acc);
 }
 
-// 3x3/1 average (count_include_pad, /9): one thread per (frame, column x, 8-channel group) walks down the
-// rows keeping the horizontal 3-sums of the last three rows -> 3 loads per output instead of 9
-__global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
-                            __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
+// 3x3/1 average (count_include_pad, /9): one thread per (frame, row y, strip of 4 columns, 8-channel group).  All
+// 18 loads of the 3 x 6 input patch are independent and issued before the first use (memory-level parallelism: the
+// previous row-walking version had 3 loads in flight per thread and ran at ~1.5 TB/s); horizontal 3-sums are shared
+// between the strip's outputs.  Summation order per output: (row above) + (row) + (row below), each left to right.
+constexpr int AVG_STRIP = 4;
+__global__ void __launch_bounds__(256) avgpool3_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
+                                                   __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
   const int G = C / 8;
+  const int SW = (W + AVG_STRIP - 1) / AVG_STRIP;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)F * W * G) return;
+  if (i >= (long long)F * H * SW * G) return;
   const unsigned iu = (unsigned)i;
   const int g = (int)(iu % (unsigned)G);
-  const int x = (int)((iu / (unsigned)G) % (unsigned)W);
-  const long long f = iu / (unsigned)(G * W);
-  float prev[8], cur[8], nxt[8];
+  unsigned q = iu / (unsigned)G;
+  const int x0 = (int)(q % (unsigned)SW) * AVG_STRIP; q /= (unsigned)SW;
+  const int y = (int)(q % (unsigned)H);
+  const long long f = q / (unsigned)H;
+  uint4 v[3][AVG_STRIP + 2];
+  bool ok[3][AVG_STRIP + 2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
-  auto rowsum = [&](int y, float* o) {
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    const __half* base = src + ((f * H + yy) * W) * spitch + scoff + g * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = 0.f;
-    if (y >= H) return;
-    const __half* base = src + ((f * H + y) * W) * spitch + scoff + g * 8;
-#pragma unroll
-    for (int q = -1; q <= 1; ++q) {
-      const int xx = x + q;
-      if (xx < 0 || xx >= W) continue;
-      float v[8];
-      unpack8(ldg16(base + (long long)xx * spitch), v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += v[j];
+    for (int c = 0; c < AVG_STRIP + 2; ++c) {
+      const int xx = x0 + c - 1;
+      ok[r][c] = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      if (ok[r][c]) v[r][c] = ldg16(base + (long long)xx * spitch);
     }
-  };
-  rowsum(0, cur);
-  for (int y = 0; y < H; ++y) {
-    rowsum(y + 1, nxt);
-    float s[8];
+  }
+  uint4 old[AVG_STRIP];
+  if (accumulate) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = (prev[j] + cur[j] + nxt[j]) / 9.0f;
-    __half* o = dst + ((f * H + y) * W + x) * dpitch + dcoff + g * 8;
+    for (int o = 0; o < AVG_STRIP; ++o)
+      if (x0 + o < W) old[o] = *reinterpret_cast<const uint4*>(dst + ((f * H + y) * W + x0 + o) * dpitch + dcoff + g * 8);
+  }
+#pragma unroll
+  for (int o = 0; o < AVG_STRIP; ++o) {
+    if (x0 + o >= W) continue;
+    float rs[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs[r][j] = 0.f;
+#pragma unroll
+      for (int c = o; c < o + 3; ++c) {
+        if (!ok[r][c]) continue;
+        float t[8];
+        unpack8(v[r][c], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rs[r][j] += t[j];
+      }
+    }
+    float sum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = (rs[0][j] + rs[1][j] + rs[2][j]) / 9.0f;
     if (accumulate) {
-      float old[8];
-      unpack8(*reinterpret_cast<const uint4*>(o), old);
+      float t[8];
+      unpack8(old[o], t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += old[j];
+      for (int j = 0; j < 8; ++j) sum[j] += t[j];
     }
-    *reinterpret_cast<uint4*>(o) = pack8(s);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { prev[j] = cur[j]; cur[j] = nxt[j]; }
+    *reinterpret_cast<uint4*>(dst + ((f * H + y) * W + x0 + o) * dpitch + dcoff + g * 8) = pack8(sum);
   }
 }
 
@@ -332,6 +350,90 @@ __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_h8(__half* __restri
   colsum_tail(partial, counter, C, mult, out_scale, db, &is_last, accumulate);
 }
 
+
+// k3/s2/pad0 variant of the pass above working on 2x2 input blocks: the block (2i..2i+1, 2j..2j+1) is covered by the
+// four windows (i-1..i, j-1..j) only, so one thread loads 4 windows + 4 activations for 4 outputs (the per-pixel version
+// loads 4 windows per pixel: 2.8x the L1/L2 traffic) and has 12 independent loads in flight.  Same summation order per
+// pixel (windows row-major), so dz is bit-identical.
+__global__ void __launch_bounds__(MB_THREADS) pool_mask_bias2x2_h8(__half* __restrict__ dz, int dpitch, int dcoff,
+                                                                   const __half* __restrict__ y, int ypitch, int ycoff, int H, int W,
+                                                                   const __half* __restrict__ dpool, int OH, int OW, int ppitch, int pcoff,
+                                                                   const uint8_t* __restrict__ argmax, long long blocks, int C,
+                                                                   long long blocks_per_cta, float* __restrict__ partial,
+                                                                   unsigned* __restrict__ counter, const float* __restrict__ mult,
+                                                                   float out_scale, float* __restrict__ db, int accumulate) {
+  extern __shared__ float red[];
+  __shared__ bool is_last;
+  const int G = C / 8;
+  const int lanes = MB_THREADS / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  const int BH = (H + 1) / 2, BW = (W + 1) / 2;
+  const long long b0 = (long long)blockIdx.x * blocks_per_cta;
+  const long long b1 = (b0 + blocks_per_cta < blocks) ? b0 + blocks_per_cta : blocks;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    for (long long b = b0 + rl; b < b1; b += lanes) {
+      const unsigned bu = (unsigned)b;
+      const int bj = (int)(bu % (unsigned)BW), bi = (int)((bu / (unsigned)BW) % (unsigned)BH);
+      const long long f = bu / (unsigned)(BW * BH);
+      uint2 am[4]; uint4 dv[4], yv[4]; bool wok[4], pok[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int oy = bi - 1 + (q >> 1), ox = bj - 1 + (q & 1);
+        wok[q] = oy >= 0 && oy < OH && ox >= 0 && ox < OW;
+        if (wok[q]) {
+          const long long op = (f * OH + oy) * OW + ox;
+          am[q] = __ldg(reinterpret_cast<const uint2*>(argmax + op * C + g * 8));
+          dv[q] = ldg16(dpool + op * ppitch + pcoff + g * 8);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int iy = 2 * bi + (q >> 1), ix = 2 * bj + (q & 1);
+        pok[q] = iy < H && ix < W;
+        if (pok[q]) yv[q] = ldg16(y + ((f * H + iy) * W + ix) * ypitch + ycoff + g * 8);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!pok[q]) continue;
+        const int a = q >> 1, c = q & 1;
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, yy[8];
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) {
+          const int u = wq >> 1, v = wq & 1;
+          if (!wok[wq] || !((u == 1 || a == 0) && (v == 1 || c == 0))) continue;
+          const uint32_t tag = (uint32_t)((a + 2 - 2 * u) * 3 + (c + 2 - 2 * v));
+          float t[8];
+          unpack8(dv[wq], t);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (((am[wq].x >> (8 * j)) & 0xFFu) == tag) d[j] += t[j];
+            if (((am[wq].y >> (8 * j)) & 0xFFu) == tag) d[4 + j] += t[4 + j];
+          }
+        }
+        unpack8(yv[q], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!(yy[j] > 0.f)) d[j] = 0.f;
+          d[j] = __half2float(__float2half_rn(d[j]));     // storage precision first: the bias gradient sums what the weight gradient reads
+          acc[j] += d[j];
+        }
+        const int iy = 2 * bi + a, ix = 2 * bj + c;
+        *reinterpret_cast<uint4*>(dz + ((f * H + iy) * W + ix) * dpitch + dcoff + g * 8) = pack8(d);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * C + g * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += MB_THREADS) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + c];
+    partial[(long long)blockIdx.x * C + c] = s;
+  }
+  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last, accumulate);
+}
+
 }  // namespace
 
 #define HP(v) reinterpret_cast<__half*>((v).base)
@@ -353,8 +455,8 @@ int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pa
   return 0;
 }
 int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s) {
-  const long long n = (long long)F * src.W * (src.C / 8);
-  avgpool3_h8<<<nblk(n, 128), 128, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
+  const long long n = (long long)F * src.H * ((src.W + AVG_STRIP - 1) / AVG_STRIP) * (src.C / 8);
+  avgpool3_h8<<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
   SSNB_LAUNCH_CHECK("avgpool3_h8");
   return 0;
 }
@@ -386,15 +488,29 @@ int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stri
   const long long rows = (long long)F * dz.H * dz.W;
   const int C = dz.C;
   if (C % 8 || C / 8 > 64 || stride != 2 || k != 3) { set_thread_error("pool_mask_bias: k3/s2 pools, C multiple of 8 and <= 512"); return 1; }
+  const int lanes = MB_THREADS / (C / 8);
+  unsigned* counter = reinterpret_cast<unsigned*>(partial);
+  float* part = partial + 64;
+  if (pad == 0) {                                   // 2x2-block version (every BNInception stride-2 pool)
+    const long long blocks = (long long)F * ((dz.H + 1) / 2) * ((dz.W + 1) / 2);
+    int ctas = (int)((blocks + 63) / 64);
+    if (ctas > 888) ctas = 888;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    const long long bpc = (blocks + ctas - 1) / ctas;
+    ctas = (int)((blocks + bpc - 1) / bpc);
+    pool_mask_bias2x2_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dz), dz.pitch, dz.coff, HP(y), y.pitch, y.coff, dz.H, dz.W, HP(dpool),
+                                                                        dpool.H, dpool.W, dpool.pitch, dpool.coff, argmax, blocks, C, bpc, part,
+                                                                        counter, mult, out_scale, db, accumulate);
+    SSNB_LAUNCH_CHECK("pool_mask_bias2x2_h8");
+    return 0;
+  }
   int ctas = (int)((rows + 255) / 256);
   if (ctas > 888) ctas = 888;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   const long long rpc = (rows + ctas - 1) / ctas;
   ctas = (int)((rows + rpc - 1) / rpc);
-  const int lanes = MB_THREADS / (C / 8);
-  unsigned* counter = reinterpret_cast<unsigned*>(partial);
-  float* part = partial + 64;
   pool_mask_bias_h8<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(HP(dz), dz.pitch, dz.coff, HP(y), y.pitch, y.coff, dz.H, dz.W, HP(dpool),
                                                                    dpool.H, dpool.W, dpool.pitch, dpool.coff, argmax, k, stride, pad, rows, C,
                                                                    rpc, part, counter, mult, out_scale, db, accumulate);

@@ -760,7 +760,8 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
 //                        bits, so views that start at any 128-byte row of a TMA-written tile read correctly with
 //                        descriptor base_offset 0 (a non-zero base_offset gives wrong data).
 //   SSNB_HALO_MIN_W=w    smallest image width that uses it (default 14)
-//   SSNB_PAIR=1          cta_group::2 kernel for every eligible layer (1x1 layers included)
+//   SSNB_V2=0            first-generation halo / pair kernels instead of umma_conv_v2.cu
+//   SSNB_PAIR=0|1        cta_group::2 (CTA pairs) off / on; default on with the second-generation kernel
 // `a2` is the second activation source of a fused sibling data gradient (K chunks >= kchunks_a1), or nullptr.
 int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2 = nullptr) {
   UmmaConvParams& p = plan.p;
@@ -768,9 +769,11 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   const char* en = getenv("SSNB_HALO");
   if (en && en[0] == '0') return 0;
   const char* pe = getenv("SSNB_PAIR");
-  const bool pair = pe && pe[0] == '1';
+  const char* ve = getenv("SSNB_V2");
+  const bool v2 = !(ve && ve[0] == '0') && umma_conv_v2_supported(p.ntaps);
+  const bool pair = pe ? pe[0] == '1' : v2;                 // default: pairs wherever the second-generation kernel runs
   if (!plan.enabled || p.a_stride != 1 || p.out_stride != 1) return 0;
-  if (!pair && (p.ntaps < 2 || p.kchunks_a1 != p.kchunks)) return 0;
+  if (!pair && !v2 && (p.ntaps < 2 || p.kchunks_a1 != p.kchunks)) return 0;
   if (p.kchunks_a1 != p.kchunks && (p.ntaps != 1 || !a2)) return 0;
   const char* mw = getenv("SSNB_HALO_MIN_W");
   if (a.W < (mw ? atoi(mw) : 14)) return 0;
@@ -792,24 +795,33 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   else pw = 16;
   const int bhh = bh + yh;
   if (loads > 4 || bhh > 256 || bf > 256) return 0;
+  const int pipe = v2 ? UMMA_V2_PIPE_BYTES : HALO_PIPE_BYTES;
   const int b_rows = pair ? p.block_n / 2 : p.block_n;      // weight rows each CTA stages per (tap, K chunk)
   const int a_load_bytes = pw * bf * bhh * BLOCK_K * 2;
   const int a_stage = (loads * a_load_bytes + 1023) / 1024 * 1024;
-  const int b_stage = (b_rows * BLOCK_K * 2 + 1023) / 1024 * 1024;
+  const int slab = b_rows * BLOCK_K * 2;                    // one tap of the weight stage (multiple of 1024: rows % 8 == 0)
+  int b_taps = 1;
+  if (v2 && p.ntaps > 1) {                                  // several taps per weight stage: fewer barrier hand-offs per K chunk
+    for (int g = p.ntaps; g >= 1; --g)
+      if (p.ntaps % g == 0 && g * slab <= 48 * 1024 && 2 * a_stage + 3 * g * slab <= pipe) { b_taps = g; break; }
+  }
+  const int b_stage = (b_taps * slab + 1023) / 1024 * 1024;
   int a_stages, b_stages;
   if (p.ntaps == 1) {                                       // one box + one slab per step: equal ring depths
-    a_stages = b_stages = std::min(HALO_B_STAGES_MAX, HALO_PIPE_BYTES / (a_stage + b_stage));
+    a_stages = b_stages = std::min(HALO_B_STAGES_MAX, pipe / (a_stage + b_stage));
     if (a_stages < 3) return 0;
   } else {
     a_stages = 3;
-    if ((HALO_PIPE_BYTES - 3 * a_stage) / b_stage < 4) a_stages = 2;
-    b_stages = (HALO_PIPE_BYTES - a_stages * a_stage) / b_stage;
-    if (b_stages < 3) return 0;                             // does not fit: stay classic
+    if ((pipe - 3 * a_stage) / b_stage < (v2 ? 3 : 4)) a_stages = 2;
+    b_stages = (pipe - a_stages * a_stage) / b_stage;
+    if (b_stages < (v2 ? 2 : 3)) return 0;                  // does not fit: stay classic
     if (b_stages > HALO_B_STAGES_MAX) b_stages = HALO_B_STAGES_MAX;
   }
+  p.v2 = v2 ? 1 : 0; p.b_taps = b_taps;
   p.halo = 1; p.pair = pair ? 1 : 0;
   p.bw = bw; p.bh = bh; p.bf = bf;
   p.tiles_w = (a.W + bw - 1) / bw; p.tiles_h = (a.H + bh - 1) / bh; p.tiles_f = (F + bf - 1) / bf;
+  p.tiles_q = pair ? (p.tiles_f + 1) / 2 : p.tiles_f;
   p.a_stages = a_stages; p.b_stages = b_stages; p.a_stage_bytes = a_stage; p.b_stage_bytes = b_stage;
   p.a_loads = loads; p.a_load_bytes = a_load_bytes; p.halo_x0 = x0; p.halo_y0 = y0; p.a_sbo = pw * BLOCK_K * 2;
   for (int l = 0; l < 4; ++l) p.a_load_dx[l] = loads > 1 ? l : 0;
@@ -828,10 +840,10 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   if (int rc = encode_a(&plan.tmap_a, a, p.K1)) { plan.enabled = false; return rc; }
   if (p.kchunks_a1 != p.kchunks) { if (int rc = encode_a(&plan.tmap_a2, *a2, p.K - p.K1)) { plan.enabled = false; return rc; } }
   else plan.tmap_a2 = plan.tmap_a;
-  if (pair) {                                               // each CTA of the pair stages half of the weight rows
+  if (pair || b_taps > 1) {                                 // pair: each CTA stages half of the weight rows; v2: b_taps taps per stage
     cuuint64_t bd[3] = {plan.b_dims[0], plan.b_dims[1], plan.b_dims[2]};
     cuuint64_t bs[2] = {plan.b_strides[0], plan.b_strides[1]};
-    cuuint32_t bb[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)b_rows, 1};
+    cuuint32_t bb[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)b_rows, (cuuint32_t)b_taps};
     if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(plan.b_ptr), bd, bs, bb)) { plan.enabled = false; return rc; }
   }
   return 0;
@@ -937,6 +949,7 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
   p.epi_direct = epi_transposed ? 0 : 1;
   static const int ablate = [] { const char* e = getenv("SSNB_ABLATE"); return e ? atoi(e) : 0; }();     // timing experiments only
   p.ablate = ablate;
+  if (p.v2) return umma_conv_v2_launch(ctx, plan, p, s);
   if (p.pair) {
     if (!ctx.attr_set_pair) {
       if (cudaFuncSetAttribute(umma_conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES) != cudaSuccess) {

@@ -14,6 +14,7 @@
 namespace ssnb {
 
 constexpr int UMMA_MAX_TAPS = 16;
+constexpr int UMMA_V2_PIPE_BYTES = 216 * 1024;   // operand staging of the second-generation kernel
 
 struct UmmaContext {
   bool active = false;
@@ -45,6 +46,9 @@ struct UmmaConvParams {
   int epi_direct;                 // epilogue variant: 1 = per-thread row stores, 0 = shared-memory transposed, coalesced
   int halo;
   int pair;                       // CTA-pair kernel (cta_group::2): tiles are (N tile, pair of M tiles)
+  int v2;                         // second-generation kernel (umma_conv_v2.cu): warp-uniform role loops, grouped weight stages
+  int b_taps;                     // v2: taps per weight stage
+  int tiles_q;                    // v2: frame groups (pair mode: PAIRS of frame groups) = last digit of the tile walk
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
   int a_loads, a_load_bytes;      // TMA loads per A stage (1: full halo box; >1: one box per horizontal shift)
   int halo_x0, halo_y0;           // box origin relative to the tile origin (min dx, min dy)
@@ -82,6 +86,9 @@ int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View
 int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, View dz2, View dx, int F, int cin, int k1, int k2,
                                const __half* w_n_k, int accumulate);
 int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s, bool mask = false);
+// second-generation kernel (umma_conv_v2.cu); `p` = plan.p with the per-launch fields (mask) already applied
+bool umma_conv_v2_supported(int ntaps);
+int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s);
 void umma_conv_set_mask(UmmaConvPlan& plan, View y);
 
 // host helpers shared by the tensor-core kernels

@@ -1,0 +1,388 @@
+// tcgen05 implicit-GEMM convolution, second generation (sm_100a): the role loops are written warp-uniformly.
+//
+// Measured on B200 (tools/ablate.sh): with the MMAs, the epilogue AND every TMA load removed, the first-generation
+// kernels (umma_conv.cu) still took 85-90 % of their full time -- the single-thread producer / MMA-issue loops
+// (divergent `if (lane == 0)` regions: vector registers, R2UR + vote loops around every UTMALDG / UTCHMMA, runtime
+// divisions per tile, dynamically indexed parameter arrays in local memory) bounded the kernel, not memory or the tensor
+// pipe.  Here every role loop runs on all 32 lanes with warp-uniform control flow and operands (they live in uniform
+// registers), one elected lane issues the asynchronous instructions, tiles advance by mixed-radix carry adds instead of
+// divisions, the tap loop is unrolled at compile time (NTAPS is a template parameter) and several taps share one weight
+// stage, which divides the number of barrier hand-offs per K chunk.
+//
+//   layout   halo A boxes (one per K chunk, [y][frame][x][64 ch], taps = shifted UMMA descriptor views; a 1x1 layer
+//            is the halo-free case), weight stages of G taps x rows x 64 ch
+//   PAIR     two CTAs of a cluster split two frame-adjacent M tiles and each stages half of the weight rows; the
+//            leader issues M = 256 cta_group::2 MMAs (umma_conv.cu has the protocol notes)
+//   warp 0   TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (TMEM -> bias/ReLU or accumulate/mask -> fp16 NHWC)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+#include "umma_conv.cuh"
+#include "umma_dev.cuh"
+
+namespace ssnb {
+namespace {
+
+using namespace umma;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 8;
+constexpr int BAR_BYTES = 1024;
+constexpr int SMEM_BYTES = UMMA_V2_PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES;
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Tile walk without divisions: digits (N tile, tile column, tile row, frame group) advance by the digits of the grid
+// stride with carries.  In PAIR mode the last digit counts PAIRS of frame groups and CTA `rank` owns group 2*mq + rank.
+struct TileIter {
+  int nt, mw, mh, mq, sn, sw, sh, sq;
+  __device__ __forceinline__ void init(const UmmaConvParams& p, int first, int step) {
+    nt = first % p.n_tiles; first /= p.n_tiles; mw = first % p.tiles_w; first /= p.tiles_w; mh = first % p.tiles_h; mq = first / p.tiles_h;
+    sn = step % p.n_tiles; step /= p.n_tiles; sw = step % p.tiles_w; step /= p.tiles_w; sh = step % p.tiles_h; sq = step / p.tiles_h;
+  }
+  __device__ __forceinline__ bool valid(const UmmaConvParams& p) const { return mq < p.tiles_q; }
+  __device__ __forceinline__ void next(const UmmaConvParams& p) {
+    nt += sn; int c = nt >= p.n_tiles ? 1 : 0; nt -= c ? p.n_tiles : 0;
+    mw += sw + c; c = mw >= p.tiles_w ? 1 : 0; mw -= c ? p.tiles_w : 0;
+    mh += sh + c; c = mh >= p.tiles_h ? 1 : 0; mh -= c ? p.tiles_h : 0;
+    mq += sq + c;
+  }
+};
+
+template <bool PAIR>
+__device__ __forceinline__ void commit_bar(uint64_t* bar) {
+  if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+}
+template <bool PAIR>
+__device__ __forceinline__ void mma_lohi(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma_f16_lohi_pair(d, alo, ahi, blo, bhi, idesc, acc); else umma_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc);
+}
+
+// one 16-column chunk of an accumulator row: bias / accumulate / ReLU / ReLU-gradient mask, fp16 store (32 bytes)
+__device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, int col, uint4* dst, const uint4& o0, const uint4& o1,
+                                            const uint4& y0, const uint4& y1) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (p.accumulate) {
+    const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&o1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+      v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.mask_y) {
+    const __half2* a0 = reinterpret_cast<const __half2*>(&y0);
+    const __half2* a1 = reinterpret_cast<const __half2*>(&y1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 ya = __half22float2(a0[j]), yb = __half22float2(a1[j]);
+      if (!(ya.x > 0.f)) v[2 * j] = 0.f;
+      if (!(ya.y > 0.f)) v[2 * j + 1] = 0.f;
+      if (!(yb.x > 0.f)) v[8 + 2 * j] = 0.f;
+      if (!(yb.y > 0.f)) v[8 + 2 * j + 1] = 0.f;
+    }
+  }
+  uint4 q0, q1;
+  __half2* g0 = reinterpret_cast<__half2*>(&q0);
+  __half2* g1 = reinterpret_cast<__half2*>(&q1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { g0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); g1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]); }
+  if (p.ablate & 1) { if (v[0] == 12345.678f) dst[0] = q0; return; }     // SSNB_ABLATE=1: no stores
+  dst[0] = q0; dst[1] = q1;
+}
+
+template <bool PAIR, int NTAPS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ UmmaConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UMMA_V2_PIPE_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + MAX_STAGES;
+  uint64_t* b_full = a_empty + MAX_STAGES;
+  uint64_t* b_empty = b_full + MAX_STAGES;
+  uint64_t* tfull_bar = b_empty + MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the loop
+  // state inside them can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr bool ONE_RING = NTAPS == 1;        // 1x1 layers: A box and weight slab of a step share one barrier pair
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (whole warp, one elected lane issues) =====
+    const bool el = elect_one();
+    TileIter it; it.init(p, first, step);
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    const int rows_b = PAIR ? p.block_n / 2 : p.block_n;
+    const uint32_t a_tx = (PAIR ? 2u : 1u) * (uint32_t)(p.a_loads * p.a_load_bytes);
+    const uint32_t b_tx = (PAIR ? 2u : 1u) * (uint32_t)(rows_b * p.b_taps) * BLOCK_K * 2;
+    const int groups = NTAPS / p.b_taps;
+    for (; it.valid(p); it.next(p)) {
+      const int w0 = it.mw * p.bw + p.halo_x0, h0 = it.mh * p.bh + p.halo_y0;
+      const int f0 = (PAIR ? 2 * it.mq + (int)rank : it.mq) * p.bf;
+      const int n0 = it.nt * p.block_n + (PAIR ? (int)rank * rows_b : 0);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (el) {
+          uint8_t* sa = smem + as * p.a_stage_bytes;
+          const bool src1 = kc < p.kchunks_a1;
+          const CUtensorMap* map = src1 ? &tmap_a : &tmap_a2;
+          const int c0 = (src1 ? kc : kc - p.kchunks_a1) * BLOCK_K;
+          if (PAIR) {
+            if (leader) mbar_expect_tx(&a_full[as], ONE_RING ? a_tx + b_tx : a_tx);
+            const uint32_t bar = mapa_shared(smem_u32(&a_full[as]), 0);
+            for (int l = 0; l < p.a_loads; ++l) tma_load_4d_pair(sa + l * p.a_load_bytes, map, bar, c0, w0 + p.a_load_dx[l], f0, h0);
+            if (ONE_RING) tma_load_3d_pair(smem_b + as * p.b_stage_bytes, &tmap_b, bar, kc * BLOCK_K, n0, 0);
+          } else {
+            mbar_expect_tx(&a_full[as], ONE_RING ? a_tx + b_tx : a_tx);
+            for (int l = 0; l < p.a_loads; ++l) tma_load_4d(sa + l * p.a_load_bytes, map, &a_full[as], c0, w0 + p.a_load_dx[l], f0, h0);
+            if (ONE_RING) tma_load_3d(smem_b + as * p.b_stage_bytes, &tmap_b, &a_full[as], kc * BLOCK_K, n0, 0);
+          }
+        }
+        if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
+        if (!ONE_RING) {
+          for (int g = 0; g < groups; ++g) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (el) {
+              uint8_t* sb = smem_b + bs * p.b_stage_bytes;
+              if (PAIR) {
+                if (leader) mbar_expect_tx(&b_full[bs], b_tx);
+                tma_load_3d_pair(sb, &tmap_b, mapa_shared(smem_u32(&b_full[bs]), 0), kc * BLOCK_K, n0, g * p.b_taps);
+              } else {
+                mbar_expect_tx(&b_full[bs], b_tx);
+                tma_load_3d(sb, &tmap_b, &b_full[bs], kc * BLOCK_K, n0, g * p.b_taps);
+              }
+            }
+            if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (whole warp walks the pipeline; one elected lane issues; PAIR: leader CTA only) =====
+    if (!PAIR || leader) {
+      const bool el = elect_one();
+      const uint32_t idesc = make_idesc_f16_m(PAIR ? 256 : 128, p.block_n);
+      const uint32_t a_hi = desc_hi_sw128(p.a_sbo), b_hi = desc_hi_sw128(1024);
+      const uint32_t a_stage_lo = (uint32_t)p.a_stage_bytes >> 4, b_stage_lo = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t slab_lo = (uint32_t)((PAIR ? p.block_n / 2 : p.block_n) * BLOCK_K * 2) >> 4;     // one tap inside a weight stage
+      const uint32_t a_base = desc_lo(smem_u32(smem)), b_base = desc_lo(smem_u32(smem_b));
+      const int btaps = p.b_taps;
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, acc_phase = 0;
+      TileIter it; it.init(p, first, step);
+      for (; it.valid(p); it.next(p)) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_lo0 = a_base + as * a_stage_lo;
+          const int kvalid = kc < p.kchunks_a1 ? p.K1 - kc * BLOCK_K : p.K - p.K1 - (kc - p.kchunks_a1) * BLOCK_K;
+          const int nk = kvalid >= BLOCK_K ? BLOCK_K / UMMA_K : (kvalid + UMMA_K - 1) / UMMA_K;
+          uint32_t b_lo = ONE_RING ? b_base + as * b_stage_lo : 0u;
+          int gi = 0;                                             // tap index inside the current weight stage
+#pragma unroll
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            if (!ONE_RING && gi == 0) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              b_lo = b_base + bs * b_stage_lo;
+            }
+            if (el && !(p.ablate & 8)) {
+              const uint32_t a_lo = a_lo0 + ((uint32_t)p.tap_aoff[tap] >> 4);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                if (k < nk) mma_lohi<PAIR>(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u);
+            }
+            b_lo += slab_lo;
+            if (!ONE_RING && ++gi == btaps) {
+              gi = 0;
+              if (el) commit_bar<PAIR>(&b_empty[bs]);
+              if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
+          if (el) commit_bar<PAIR>(&a_empty[as]);
+          if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
+        }
+        if (el) commit_bar<PAIR>(&tfull_bar[acc]);
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, the two warps of a quadrant alternate 32-column groups =====
+    const int quad = warp & 3;
+    const int cpar = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int rw = row % p.bw, rf = (row / p.bw) % p.bf, rh = row / (p.bw * p.bf);      // halo row order: x, frame, y
+    uint32_t acc = 0, acc_phase = 0;
+    TileIter it; it.init(p, first, step);
+    for (; it.valid(p); it.next(p)) {
+      const int w = it.mw * p.bw + rw, h = it.mh * p.bh + rh;
+      const int f = (PAIR ? 2 * it.mq + (int)rank : it.mq) * p.bf + rf;
+      const int n0 = it.nt * p.block_n;
+      const bool valid = (rh < p.bh) && (w < p.W) && (h < p.H) && (f < p.F);
+      const long long opix = (long long)(f * p.OH + h) * p.OW + w;
+      __half* orow = p.out + opix * p.out_pitch + p.out_coff;
+      __half* orow2 = p.out2 + opix * p.out2_pitch + p.out2_coff - p.n_split;
+      const __half* mrow = p.mask_y ? p.mask_y + opix * p.mask_pitch + p.mask_coff : nullptr;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+      const int ncol = (p.ablate & 4) ? 0 : p.block_n;              // SSNB_ABLATE=4 (timing experiment): empty epilogue
+      if (cpar * 32 >= ncol) {                                      // narrow tile: this warp has no columns, release at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+        }
+      }
+      for (int c0 = cpar * 32; c0 < ncol; c0 += 64) {
+        const bool two = c0 + 16 < p.block_n;                       // warp-uniform
+        const int cola = n0 + c0, colb = cola + 16;
+        const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
+        uint4* da = reinterpret_cast<uint4*>((cola < p.n_split ? orow : orow2) + cola);
+        uint4* db2 = reinterpret_cast<uint4*>((colb < p.n_split ? orow : orow2) + colb);
+        uint4 oa0 = {}, oa1 = {}, ob0 = {}, ob1 = {}, ya0 = {}, ya1 = {}, yb0 = {}, yb1 = {};
+        if (p.accumulate) {
+          if (va) { oa0 = da[0]; oa1 = da[1]; }
+          if (vb) { ob0 = db2[0]; ob1 = db2[1]; }
+        }
+        if (mrow) {
+          const uint4* my = reinterpret_cast<const uint4*>(mrow + cola);
+          if (va) { ya0 = __ldg(my); ya1 = __ldg(my + 1); }
+          if (vb) { yb0 = __ldg(my + 2); yb1 = __ldg(my + 3); }
+        }
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr + c0, ra);
+        if (two) tmem_ld16(taddr + c0 + 16, rb);
+        tmem_ld_wait();
+        if (c0 + 64 >= p.block_n) {                                 // last TMEM read of this tile: hand the accumulator back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+        if (va) store_chunk(p, ra, cola, da, oa0, oa1, ya0, ya1);
+        if (vb) store_chunk(p, rb, colb, db2, ob0, ob1, yb0, yb1);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <bool PAIR, int NTAPS>
+int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = umma_conv_v2_kernel<PAIR, NTAPS>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      set_thread_error("umma conv v2: cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
+    attr_set = true;
+  }
+  const int total = p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_q;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = s;
+  if (PAIR) {
+    const int pairs = std::min(total, num_sms / 2);
+    cfg.gridDim = dim3(2 * pairs);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(std::min(total, num_sms));
+  }
+  if (cudaLaunchKernelEx(&cfg, kern, plan.tmap_a, plan.tmap_a2, plan.tmap_b, p) != cudaSuccess) {
+    set_thread_error(std::string("umma_conv_v2_kernel launch: ") + cudaGetErrorString(cudaGetLastError())); return 2; }
+  return 0;
+}
+
+}  // namespace
+
+bool umma_conv_v2_supported(int ntaps) { return ntaps == 1 || ntaps == 4 || ntaps == 9; }
+
+int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s) {
+  int rc;
+  if (p.pair) {
+    if (p.ntaps == 1) rc = launch_one<true, 1>(plan, p, ctx.num_sms, s);
+    else if (p.ntaps == 4) rc = launch_one<true, 4>(plan, p, ctx.num_sms, s);
+    else rc = launch_one<true, 9>(plan, p, ctx.num_sms, s);
+  } else {
+    if (p.ntaps == 1) rc = launch_one<false, 1>(plan, p, ctx.num_sms, s);
+    else if (p.ntaps == 4) rc = launch_one<false, 4>(plan, p, ctx.num_sms, s);
+    else rc = launch_one<false, 9>(plan, p, ctx.num_sms, s);
+  }
+  if (rc) return rc;
+  SSNB_LAUNCH_CHECK("umma_conv_v2_kernel");
+  return 0;
+}
+
+}  // namespace ssnb

@@ -110,6 +110,17 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t alo, uin
       "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of a converged warp (warp-uniform role loops: everybody walks the pipeline, this lane issues)
+__device__ __forceinline__ bool elect_one_lane() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- CTA pair (cta_group::2) forms ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -35,7 +35,9 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // warp index through a shuffle (provably warp-uniform): the role loops below run on all 32 lanes with uniform control
+  // flow, one elected lane issues the TMA / MMA instructions (see umma_conv_v2.cu for the measurements behind this)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
   int id = blockIdx.x;
   const int tgrp = id % p.tap_groups; id /= p.tap_groups;
   const int nt = id % p.n_tiles; id /= p.n_tiles;
@@ -76,15 +78,15 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(2 + nboxes_b * ntap) * BOX_BYTES;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        int q = pt;
-        const int w0 = (q % p.tiles_w) * p.bw; q /= p.tiles_w;
-        const int h0 = (q % p.tiles_h) * p.bh; q /= p.tiles_h;
-        const int f0 = q * p.bf;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    const bool el = elect_one_lane();
+    uint32_t stage = 0, phase = 0;
+    const uint32_t tx_bytes = (uint32_t)(2 + nboxes_b * ntap) * BOX_BYTES;
+    // pixel-tile coordinates advance by carries (no divisions in the loop)
+    int tw = pt0 % p.tiles_w, th = (pt0 / p.tiles_w) % p.tiles_h, tf = pt0 / (p.tiles_w * p.tiles_h);
+    for (int pt = pt0; pt < pt1; ++pt) {
+      const int w0 = tw * p.bw, h0 = th * p.bh, f0 = tf * p.bf;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (el) {
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
         mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -94,38 +96,44 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
           for (int b = 0; b < nboxes_b; ++b)
             tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64,
                         w0 * p.x_stride + p.tap_dx[tap0 + t], h0 * p.x_stride + p.tap_dy[tap0 + t], f0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tf; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16_mn(p.mma_n);
-      uint32_t stage = 0, phase = 0;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+    const bool el = elect_one_lane();
+    const uint32_t idesc = make_idesc_f16_mn(p.mma_n), idesc_bias = make_idesc_f16_mn(16);
+    // descriptors as (lo, hi) words: hi constant (SBO 1024, version, SWIZZLE_128B), lo = address >> 4 | LBO field
+    const uint32_t hi = desc_hi_sw128(1024);
+    const uint32_t lbo = (uint32_t)((BOX_BYTES >> 4) & 0x3FFF) << 16;
+    const uint32_t base_lo = ((smem_u32(smem) >> 4) & 0x3FFF) | lbo;
+    const uint32_t ones_lo = ((smem_u32(smem + ONES_OFF) >> 4) & 0x3FFF) | lbo;
+    const uint32_t kstep_lo = (UMMA_K * 128) >> 4;                    // 16 pixel rows
+    uint32_t stage = 0, phase = 0;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa_lo = base_lo + stage * (STAGE_BYTES >> 4);
+      const uint32_t sb_lo = sa_lo + (A_BYTES >> 4);
+      if (el) {
+        const uint32_t first = pt > pt0 ? 1u : 0u;
         for (int t = 0; t < ntap; ++t) {
+          const uint32_t xb_lo = sb_lo + t * nboxes_b * (BOX_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < 64 / UMMA_K; ++k) {      // 16 pixel rows (2 groups of 8) per instruction
-            const uint64_t ad = make_desc_mn_sw128(sa + k * UMMA_K * 128, BOX_BYTES);
-            const uint64_t bd = make_desc_mn_sw128(sb + t * nboxes_b * BOX_BYTES + k * UMMA_K * 128, BOX_BYTES);
-            umma_f16(tmem_base + t * p.mma_n, ad, bd, idesc, (pt > pt0 || k) ? 1u : 0u);
-          }
+          for (int k = 0; k < 64 / UMMA_K; ++k)      // 16 pixel rows (2 groups of 8) per instruction
+            umma_f16_lohi(tmem_base + t * p.mma_n, sa_lo + k * kstep_lo, hi, xb_lo + k * kstep_lo, hi, idesc, first | (uint32_t)k);
         }
         if (do_bias) {
-          const uint32_t so = smem_u32(smem + ONES_OFF);
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; ++k)
-            umma_f16(tmem_base + bias_col, make_desc_mn_sw128(sa + k * UMMA_K * 128, BOX_BYTES), make_desc_mn_sw128(so + k * UMMA_K * 128, BOX_BYTES),
-                     make_idesc_f16_mn(16), (pt > pt0 || k) ? 1u : 0u);
+            umma_f16_lohi(tmem_base + bias_col, sa_lo + k * kstep_lo, hi, ones_lo + k * kstep_lo, hi, idesc_bias, first | (uint32_t)k);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    if (el) umma_commit(tfull_bar);
+    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int m = m0 + quad * 32 + lane;            // output channel of this thread's accumulator row
