@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_profiler_api.h>
+
 #include "../../include/ssnb.h"
 #include "common.cuh"
 #include "umma_conv.cuh"
@@ -129,6 +131,14 @@ struct ssnb_engine {
 namespace ssnb {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// profiling aid: SSNB_PROFILE_FWD_OPS / SSNB_PROFILE_BWD_OPS = comma-separated op ids; the engine brackets those ops of a whole
+// forward / backward pass with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`)
+static bool profiled_op(const char* env, const std::string& id) {
+  const char* e = getenv(env);
+  if (!e || !*e) return false;
+  const std::string list = std::string(",") + e + ",";
+  return list.find("," + id + ",") != std::string::npos;
+}
 static int pool_out(int h, int k, int s, int p) {   // ceil_mode (layer_factory.py:46-50)
   int o = (h + 2 * p - k + s - 1) / s + 1;
   if ((o - 1) * s >= h + p) --o;
@@ -659,8 +669,11 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
   if (rc) { h->s2d_ready = false; return h->fail(rc, "input layout: " + ssnb::thread_error()); }
   for (const Op& o : h->ops) {
     if (o.fuse_role == 2) continue;                       // computed by its block's fused launch
+    const bool prof = profiled_op("SSNB_PROFILE_FWD_OPS", o.id);
+    if (prof) cudaProfilerStart();
     if (o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].fwd, s);
     else rc = run_fwd(h, o, input_nchw, feat, s);
+    if (prof) cudaProfilerStop();
     if (rc) { h->s2d_ready = false; return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error()); }
   }
   h->s2d_ready = false;
@@ -683,8 +696,11 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
     const Op& o = h->ops[i];
+    const bool prof = profiled_op("SSNB_PROFILE_BWD_OPS", o.id);
+    if (prof) cudaProfilerStart();
     int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
     if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s, h->fold_pools && o.dgrad_masks);   // ... one fused data gradient
+    if (prof) cudaProfilerStop();
     if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
   }
   // one (or two) launches reduce the split-K partials of every tensor-core weight gradient of this backward

@@ -21,6 +21,9 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 __device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// max pooling on packed halves: compares and selects run as half2 mask operations (no fp32 round trip; the first
+// version spent ~400 instructions per thread on conversions and was issue-bound at 2.6 TB/s).  Semantics unchanged:
+// first maximum wins, NaN propagates (ATen's rule).
 __global__ void maxpool_fwd_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
                                __half* __restrict__ dst, int OH, int OW, int dpitch, int dcoff, int F, int k, int stride,
                                int pad, uint8_t* __restrict__ argmax) {
@@ -34,27 +37,37 @@ __global__ void maxpool_fwd_h8(const __half* __restrict__ src, int H, int W, int
   const int ox = (int)(pu % (unsigned)OW), oy = (int)((pu / (unsigned)OW) % (unsigned)OH);
   const long long p = pu;
   const long long f = pu / (unsigned)(OW * OH);
-  float best[8];
-  int bi[8];
+  uint32_t best[4] = {0u, 0u, 0u, 0u};     // 4 x half2
+  uint32_t bi[4] = {0u, 0u, 0u, 0u};       // 4 x (two 16-bit tap indices, same lanes as the half2 values)
   bool first = true;
+  const __half* base = src + (f * H * W) * spitch + scoff + g * 8;
   for (int r = 0; r < k; ++r) {
     const int iy = oy * stride + r - pad;
     if (iy < 0 || iy >= H) continue;
     for (int s = 0; s < k; ++s) {
       const int ix = ox * stride + s - pad;
       if (ix < 0 || ix >= W) continue;
-      float v[8];
-      unpack8(ldg16(src + ((f * H + iy) * W + ix) * spitch + scoff + g * 8), v);
+      const uint4 q = ldg16(base + ((long long)iy * W + ix) * spitch);
+      const uint32_t v[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t tag = (uint32_t)(r * k + s) * 0x00010001u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (first || v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; bi[j] = r * k + s; }
+      for (int j = 0; j < 4; ++j) {
+        const __half2 hv = *reinterpret_cast<const __half2*>(&v[j]);
+        const __half2 hb = *reinterpret_cast<const __half2*>(&best[j]);
+        // NaN-propagating maximum; the tap index moves where the maximum changed (v > best, or a NaN arrived), or when
+        // nothing was taken yet: 3 instructions per half2
+        const __half2 hn = __hmax2_nan(hb, hv);
+        const uint32_t m = first ? 0xFFFFFFFFu : __hneu2_mask(hn, hb);
+        best[j] = first ? v[j] : *reinterpret_cast<const uint32_t*>(&hn);
+        bi[j] = (tag & m) | (bi[j] & ~m);
+      }
       first = false;
     }
   }
-  *reinterpret_cast<uint4*>(dst + p * dpitch + dcoff + g * 8) = pack8(best);
+  *reinterpret_cast<uint4*>(dst + p * dpitch + dcoff + g * 8) = make_uint4(best[0], best[1], best[2], best[3]);
   uint2 a;
-  a.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-  a.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+  a.x = (bi[0] & 0xFFu) | ((bi[0] >> 8) & 0xFF00u) | ((bi[1] & 0xFFu) << 16) | ((bi[1] >> 16) << 24);
+  a.y = (bi[2] & 0xFFu) | ((bi[2] >> 8) & 0xFF00u) | ((bi[3] & 0xFFu) << 16) | ((bi[3] >> 16) << 24);
   *reinterpret_cast<uint2*>(argmax + p * C + g * 8) = a;
 }
 
@@ -130,69 +143,51 @@ __global__ void maxpool_bwd_h8(__half* __restrict__ dsrc, int H, int W, int C, i
   *reinterpret_cast<uint4*>(q) = pack8(acc);
 }
 
-// 3x3/1 average (count_include_pad, /9): one thread per (frame, row y, strip of 4 columns, 8-channel group).  All
-// 18 loads of the 3 x 6 input patch are independent and issued before the first use (memory-level parallelism: the
-// previous row-walking version had 3 loads in flight per thread and ran at ~1.5 TB/s); horizontal 3-sums are shared
-// between the strip's outputs.  Summation order per output: (row above) + (row) + (row below), each left to right.
-constexpr int AVG_STRIP = 4;
-__global__ void __launch_bounds__(256) avgpool3_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
-                                                   __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
+// 3x3/1 average (count_include_pad, /9): one thread per (frame, column x, 8-channel group) walks down the
+// rows keeping the horizontal 3-sums of the last three rows -> 3 loads per output instead of 9
+__global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
+                            __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
   const int G = C / 8;
-  const int SW = (W + AVG_STRIP - 1) / AVG_STRIP;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)F * H * SW * G) return;
+  if (i >= (long long)F * W * G) return;
   const unsigned iu = (unsigned)i;
   const int g = (int)(iu % (unsigned)G);
-  unsigned q = iu / (unsigned)G;
-  const int x0 = (int)(q % (unsigned)SW) * AVG_STRIP; q /= (unsigned)SW;
-  const int y = (int)(q % (unsigned)H);
-  const long long f = q / (unsigned)H;
-  uint4 v[3][AVG_STRIP + 2];
-  bool ok[3][AVG_STRIP + 2];
+  const int x = (int)((iu / (unsigned)G) % (unsigned)W);
+  const long long f = iu / (unsigned)(G * W);
+  float prev[8], cur[8], nxt[8];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int yy = y + r - 1;
-    const __half* base = src + ((f * H + yy) * W) * spitch + scoff + g * 8;
+  for (int j = 0; j < 8; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
+  auto rowsum = [&](int y, float* o) {
 #pragma unroll
-    for (int c = 0; c < AVG_STRIP + 2; ++c) {
-      const int xx = x0 + c - 1;
-      ok[r][c] = yy >= 0 && yy < H && xx >= 0 && xx < W;
-      if (ok[r][c]) v[r][c] = ldg16(base + (long long)xx * spitch);
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    if (y >= H) return;
+    const __half* base = src + ((f * H + y) * W) * spitch + scoff + g * 8;
+#pragma unroll
+    for (int q = -1; q <= 1; ++q) {
+      const int xx = x + q;
+      if (xx < 0 || xx >= W) continue;
+      float v[8];
+      unpack8(ldg16(base + (long long)xx * spitch), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += v[j];
     }
-  }
-  uint4 old[AVG_STRIP];
-  if (accumulate) {
+  };
+  rowsum(0, cur);
+  for (int y = 0; y < H; ++y) {
+    rowsum(y + 1, nxt);
+    float s[8];
 #pragma unroll
-    for (int o = 0; o < AVG_STRIP; ++o)
-      if (x0 + o < W) old[o] = *reinterpret_cast<const uint4*>(dst + ((f * H + y) * W + x0 + o) * dpitch + dcoff + g * 8);
-  }
-#pragma unroll
-  for (int o = 0; o < AVG_STRIP; ++o) {
-    if (x0 + o >= W) continue;
-    float rs[3][8];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) rs[r][j] = 0.f;
-#pragma unroll
-      for (int c = o; c < o + 3; ++c) {
-        if (!ok[r][c]) continue;
-        float t[8];
-        unpack8(v[r][c], t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rs[r][j] += t[j];
-      }
-    }
-    float sum[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sum[j] = (rs[0][j] + rs[1][j] + rs[2][j]) / 9.0f;
+    for (int j = 0; j < 8; ++j) s[j] = (prev[j] + cur[j] + nxt[j]) * (1.0f / 9.0f);      // (a true division costs ~8 instructions; the kernel is issue-bound)
+    __half* o = dst + ((f * H + y) * W + x) * dpitch + dcoff + g * 8;
     if (accumulate) {
-      float t[8];
-      unpack8(old[o], t);
+      float old[8];
+      unpack8(*reinterpret_cast<const uint4*>(o), old);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum[j] += t[j];
+      for (int j = 0; j < 8; ++j) s[j] += old[j];
     }
-    *reinterpret_cast<uint4*>(dst + ((f * H + y) * W + x0 + o) * dpitch + dcoff + g * 8) = pack8(sum);
+    *reinterpret_cast<uint4*>(o) = pack8(s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { prev[j] = cur[j]; cur[j] = nxt[j]; }
   }
 }
 
@@ -353,8 +348,7 @@ __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_h8(__half* __restri
 
 // k3/s2/pad0 variant of the pass above working on 2x2 input blocks: the block (2i..2i+1, 2j..2j+1) is covered by the
 // four windows (i-1..i, j-1..j) only, so one thread loads 4 windows + 4 activations for 4 outputs (the per-pixel version
-// loads 4 windows per pixel: 2.8x the L1/L2 traffic) and has 12 independent loads in flight.  Same summation order per
-// pixel (windows row-major), so dz is bit-identical.
+// loads 4 windows per pixel: 2.8x the L1/L2 traffic) and has 12 independent loads in flight.
 __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias2x2_h8(__half* __restrict__ dz, int dpitch, int dcoff,
                                                                    const __half* __restrict__ y, int ypitch, int ycoff, int H, int W,
                                                                    const __half* __restrict__ dpool, int OH, int OW, int ppitch, int pcoff,
@@ -393,33 +387,45 @@ __global__ void __launch_bounds__(MB_THREADS) pool_mask_bias2x2_h8(__half* __res
         pok[q] = iy < H && ix < W;
         if (pok[q]) yv[q] = ldg16(y + ((f * H + iy) * W + ix) * ypitch + ycoff + g * 8);
       }
+      // packed-half arithmetic (the fp32 version of this loop was issue-bound: 65 % issue utilisation at 1.9 TB/s):
+      // byte-compare the arg-max tags, widen the byte masks to half lanes, AND-select the pooled gradient, add as half2
+      uint32_t bsum[4] = {0u, 0u, 0u, 0u};                       // half2 sums of the block's dz (bias gradient)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (!pok[q]) continue;
         const int a = q >> 1, c = q & 1;
-        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, yy[8];
+        uint32_t d2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int wq = 0; wq < 4; ++wq) {
           const int u = wq >> 1, v = wq & 1;
-          if (!wok[wq] || !((u == 1 || a == 0) && (v == 1 || c == 0))) continue;
-          const uint32_t tag = (uint32_t)((a + 2 - 2 * u) * 3 + (c + 2 - 2 * v));
-          float t[8];
-          unpack8(dv[wq], t);
+          if (!((u == 1 || a == 0) && (v == 1 || c == 0))) continue;      // compile-time: this window never covers the pixel
+          if (!wok[wq]) continue;
+          const uint32_t tag4 = (uint32_t)((a + 2 - 2 * u) * 3 + (c + 2 - 2 * v)) * 0x01010101u;
+          const uint32_t mx = __vcmpeq4(am[wq].x, tag4), my = __vcmpeq4(am[wq].y, tag4);
+          const uint32_t k[4] = {__byte_perm(mx, 0u, 0x1100), __byte_perm(mx, 0u, 0x3322), __byte_perm(my, 0u, 0x1100), __byte_perm(my, 0u, 0x3322)};
+          const uint32_t t[4] = {dv[wq].x, dv[wq].y, dv[wq].z, dv[wq].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (((am[wq].x >> (8 * j)) & 0xFFu) == tag) d[j] += t[j];
-            if (((am[wq].y >> (8 * j)) & 0xFFu) == tag) d[4 + j] += t[4 + j];
+            const uint32_t sel = t[j] & k[j];
+            const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&d2[j]), *reinterpret_cast<const __half2*>(&sel));
+            d2[j] = *reinterpret_cast<const uint32_t*>(&r);
           }
         }
-        unpack8(yv[q], yy);
+        const uint32_t yy[4] = {yv[q].x, yv[q].y, yv[q].z, yv[q].w};
+        const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (!(yy[j] > 0.f)) d[j] = 0.f;
-          d[j] = __half2float(__float2half_rn(d[j]));     // storage precision first: the bias gradient sums what the weight gradient reads
-          acc[j] += d[j];
+        for (int j = 0; j < 4; ++j) {
+          d2[j] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&yy[j]), zero);       // ReLU gradient: keep where y > 0
+          const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&bsum[j]), *reinterpret_cast<const __half2*>(&d2[j]));
+          bsum[j] = *reinterpret_cast<const uint32_t*>(&r);
         }
         const int iy = 2 * bi + a, ix = 2 * bj + c;
-        *reinterpret_cast<uint4*>(dz + ((f * H + iy) * W + ix) * dpitch + dcoff + g * 8) = pack8(d);
+        *reinterpret_cast<uint4*>(dz + ((f * H + iy) * W + ix) * dpitch + dcoff + g * 8) = make_uint4(d2[0], d2[1], d2[2], d2[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&bsum[j]));
+        acc[2 * j] += t.x; acc[2 * j + 1] += t.y;
       }
     }
 #pragma unroll
@@ -455,8 +461,8 @@ int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pa
   return 0;
 }
 int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s) {
-  const long long n = (long long)F * src.H * ((src.W + AVG_STRIP - 1) / AVG_STRIP) * (src.C / 8);
-  avgpool3_h8<<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
+  const long long n = (long long)F * src.W * (src.C / 8);
+  avgpool3_h8<<<nblk(n, 128), 128, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
   SSNB_LAUNCH_CHECK("avgpool3_h8");
   return 0;
 }

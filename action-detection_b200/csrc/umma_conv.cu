@@ -1,5 +1,6 @@
-// tcgen05 implicit-GEMM convolution (sm_100a): TMA-staged operand tiles, single-thread UMMA issue,
-// fp32 accumulators in TMEM, warp-specialised persistent CTAs.
+// tcgen05 implicit-GEMM convolution (sm_100a): host-side planning for both kernel generations, and the first-generation
+// kernel (per-tap A boxes), which still runs the four stride-2 forward layers (TMA element-stride boxes) and everything
+// under SSNB_V2=0.  All stride-1 layers run on umma_conv_v2.cu (halo boxes, CTA pairs, warp-uniform role loops).
 //
 //   warp 0      : TMA producer   (A: 4-D activation box, B: 3-D weight box, SWIZZLE_128B)
 //   warp 1      : TMEM allocator + MMA issuer (tcgen05.mma.cta_group::1.kind::f16, M=128, N=block_n)
@@ -24,22 +25,17 @@ using namespace umma;
 constexpr int MAX_STAGES = 8;
 constexpr int PIPE_BYTES = 4 * (BLOCK_M * BLOCK_K * 2 + 256 * BLOCK_K * 2);   // 192 KiB of operand staging
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KiB
-constexpr int B_BYTES_MAX = 256 * BLOCK_K * 2;     // 32 KiB
 constexpr int NUM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_STAGE_BYTES = 32 * 128;          // per epilogue warp: [32 rows][64 fp16]
-constexpr int BAR_BYTES = 1024;                    // barriers + tap table
-constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int BAR_BYTES = 1024;                    // barriers
+constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES;
 
 struct TileCoord { int w0, h0, f0, n0; };
-// pair mode: `tile` counts (N tile, PAIR of M tiles); CTA `rank` of the pair owns M tile 2*mp + rank (the missing partner
-// of an odd tile count decodes to f0 >= F: its boxes are all zero fill, its rows never stored)
-__device__ __forceinline__ TileCoord decode_tile(const UmmaConvParams& p, int tile, int rank = 0) {
+__device__ __forceinline__ TileCoord decode_tile(const UmmaConvParams& p, int tile) {
   TileCoord t;
   const int nt = tile % p.n_tiles;
   int m = tile / p.n_tiles;
-  if (p.pair) m = 2 * m + rank;
   t.n0 = nt * p.block_n;
   t.w0 = (m % p.tiles_w) * p.bw; m /= p.tiles_w;
   t.h0 = (m % p.tiles_h) * p.bh; m /= p.tiles_h;
@@ -96,7 +92,7 @@ __device__ __forceinline__ void epilogue_chunk(const UmmaConvParams& p, const ui
 // (x, y, f) = (r % bw, (r / bw) % bh, r / (bw*bh)) in the classic layout and (r % bw, r / (bw*bf), (r / bw) % bf) in
 // the halo layout (rows ordered y-major, then frame, so that tap views have one uniform group stride).
 __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                              int warp, int lane, int total_tiles, int tile0, int tstep, int rank = 0) {
+                                              int warp, int lane, int total_tiles, int tile0, int tstep) {
   const int quad = warp & 3;
   const int cpar = (warp - 2) >> 2;
   const int row = quad * 32 + lane;
@@ -105,7 +101,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
   else { rw = row % p.bw; rh = (row / p.bw) % p.bh; rf = row / (p.bw * p.bh); }
   uint32_t acc = 0, acc_phase = 0;
   for (int tile = tile0; tile < total_tiles; tile += tstep) {
-    const TileCoord t = decode_tile(p, tile, rank);
+    const TileCoord t = decode_tile(p, tile);
     const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
     const int os = p.out_stride;
     const bool valid = (rf < p.bf) && (rh < p.bh) && (w < p.W) && (h < p.H) && (f < p.F) && (w % os == 0) && (h % os == 0);
@@ -143,117 +139,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      if (p.pair) mbar_arrive_cluster(&tempty_bar[acc], 0);
-      else mbar_arrive(&tempty_bar[acc]);     // 8 arrivals (one per epilogue warp) release it
-    }
-    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-  }
-}
-
-// Epilogue role shared by both kernels: for every tile of this CTA wait for the accumulator, then
-//   phase 1  TMEM -> registers (thread = accumulator row = pixel) -> bias + ReLU in fp32 -> fp16 -> this warp's 4 KiB
-//            staging tile in shared memory ([32 rows][128 B], 16-byte chunks XOR-swizzled by row: conflict-free)
-//   phase 2  re-read with lanes along the channel dimension (8 lanes x 16 B = one 128-byte pixel row, 4 rows per
-//            instruction) -> optional accumulate with the old gradient / ReLU-gradient mask -> coalesced 16-byte stores.
-// A warp-wide store thus touches 4 rows x 128 B instead of 32 rows x 16 B (8x fewer memory wavefronts).
-// Row r of the tile is pixel (x, y, f) = (r % bw, (r / bw) % bh, r / (bw*bh)) in the classic layout and
-// (r % bw, r / (bw*bf), (r / bw) % bf) in the halo layout (rows ordered y-major, then frame).
-// The two warps of a TMEM lane quadrant split the tile's columns in halves.
-__device__ __forceinline__ void epilogue_loop(const UmmaConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                              int warp, int lane, int total_tiles, uint8_t* stage_all, int tile0, int tstep, int rank = 0) {
-  const int quad = warp & 3;
-  const int cpar = (warp - 2) >> 2;
-  uint8_t* stg = stage_all + (warp - 2) * EPI_STAGE_BYTES;
-  const uint32_t stg_u32 = smem_u32(stg);
-  const int row = quad * 32 + lane;
-  int rw, rh, rf;
-  if (p.halo) { rw = row % p.bw; rf = (row / p.bw) % p.bf; rh = row / (p.bw * p.bf); }
-  else { rw = row % p.bw; rh = (row / p.bw) % p.bh; rf = row / (p.bw * p.bh); }
-  const int half_n = ((p.block_n + 1) / 2 + 15) / 16 * 16;        // columns [cpar*half_n, min(block_n, (cpar+1)*half_n))
-  const int cbeg = cpar * half_n, cend = min(p.block_n, cbeg + half_n);
-  const int l8 = lane & 7, lr = lane >> 3;                         // phase 2: 16-byte chunk / row-in-group of this lane
-  uint32_t acc = 0, acc_phase = 0;
-  for (int tile = tile0; tile < total_tiles; tile += tstep) {
-    const TileCoord t = decode_tile(p, tile, rank);
-    const int w = t.w0 + rw, h = t.h0 + rh, f = t.f0 + rf;
-    const int os = p.out_stride;
-    const bool valid = (rf < p.bf) && (rh < p.bh) && (w < p.W) && (h < p.H) && (f < p.F) && (w % os == 0) && (h % os == 0);
-    const int opix = valid ? (f * p.OH + h / os) * p.OW + w / os : -1;       // F*OH*OW < 2^31
-    mbar_wait(&tfull_bar[acc], acc_phase);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-    for (int c0 = cbeg; c0 < cend; c0 += 64) {
-      const int ncols = min(64, cend - c0);                      // multiple of 16, warp-uniform
-      // ---- phase 1 ----
-      uint32_t r[64];
-#pragma unroll
-      for (int j = 0; j < 64; j += 16)
-        if (j < ncols) tmem_ld16(taddr + c0 + j, r + j);
-      tmem_ld_wait();
-      if (c0 + 64 >= cend) {                                      // last TMEM read of this tile: hand the accumulator back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {                                          // 8 arrivals per CTA (one per epilogue warp) release it
-          if (p.pair) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the pair's accumulators are owned by the leader's MMA thread
-          else mbar_arrive(&tempty_bar[acc]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 64; j += 8) {
-        if (j < ncols) {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[j + q]);
-          if (p.bias) {
-            // columns past Cout (N-tile overhang) read the zero padding of the bias buffer's 256-byte granule or are never stored
-            const int col = min(t.n0 + c0 + j, p.Cout - 8);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-          }
-          uint4 o;
-          __half2* g = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + (((j >> 3) ^ (lane & 7)) << 4)) = o;
-        }
-      }
-      __syncwarp();
-      // ---- phase 2 ----
-      const int col = t.n0 + c0 + l8 * 8;
-      const bool colok = l8 * 8 < ncols && col < p.Cout;
-      __half* obase; int opitch;
-      if (col < p.n_split) { obase = p.out + p.out_coff + col; opitch = p.out_pitch; }
-      else { obase = p.out2 + p.out2_coff - p.n_split + col; opitch = p.out2_pitch; }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + lr;
-        const int pix = __shfl_sync(0xffffffffu, opix, rr);
-        if (pix >= 0 && colok) {
-          uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((l8 ^ (rr & 7)) << 4));
-          uint4* dst = reinterpret_cast<uint4*>(obase + (long long)pix * opitch);
-          __half2* hv = reinterpret_cast<__half2*>(&v);
-          if (p.accumulate) {
-            const uint4 o = *dst;
-            const __half2* ho = reinterpret_cast<const __half2*>(&o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hv[q] = __hadd2(hv[q], ho[q]);
-          }
-          if (p.mask_y) {
-            const uint4 y = __ldg(reinterpret_cast<const uint4*>(p.mask_y + (long long)pix * p.mask_pitch + p.mask_coff + col));
-            const __half2* hy = reinterpret_cast<const __half2*>(&y);
-            const __half2 zero = __float2half2_rn(0.f);
-            uint32_t* bv = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) bv[q] &= __hgt2_mask(hy[q], zero);            // keep where y > 0 (NaN -> 0)
-          }
-          *dst = v;
-        }
-      }
-      __syncwarp();
+      mbar_arrive(&tempty_bar[acc]);     // 8 arrivals (one per epilogue warp) release it
     }
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
@@ -356,8 +242,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===== epilogue warps 2..9; TMEM lane quadrant = warp % 4, column-group parity = (warp - 2) / 4 =====
-    if (p.epi_direct) epilogue_loop_direct(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, blockIdx.x, gridDim.x);
-    else epilogue_loop(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, smem + PIPE_BYTES + BAR_BYTES, blockIdx.x, gridDim.x);
+    epilogue_loop_direct(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, blockIdx.x, gridDim.x);
   }
 
   tc_fence_before();
@@ -365,285 +250,6 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-// ---- halo variant ------------------------------------------------------------------------------------------------
-// Same roles, two operand rings: the A ring holds one halo box per K chunk (tile + filter border, rows ordered
-// [y][frame][x]), the B ring one weight slab per (tap, K chunk).  A tap is a descriptor view into the halo box: start
-// shifted by (dy*bf*pitch + dx) pixel rows, 8-row groups `a_sbo` bytes apart.  Per K chunk the CTA stages
-// a_stage_bytes + ntaps*b_stage_bytes instead of ntaps*(16 KiB + b_stage_bytes).
-constexpr int HALO_A_STAGES_MAX = 8;
-constexpr int HALO_B_STAGES_MAX = 8;
-constexpr int HALO_PIPE_BYTES = 192 * 1024;
-constexpr int HALO_SMEM_BYTES = HALO_PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const UmmaConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HALO_PIPE_BYTES);
-  uint64_t* a_full = bars;                                   // [HALO_A_STAGES_MAX]
-  uint64_t* a_empty = a_full + HALO_A_STAGES_MAX;
-  uint64_t* b_full = a_empty + HALO_A_STAGES_MAX;            // [HALO_B_STAGES_MAX]
-  uint64_t* b_empty = b_full + HALO_B_STAGES_MAX;
-  uint64_t* tfull_bar = b_empty + HALO_B_STAGES_MAX;         // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;                      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint32_t* tap_lo = tmem_slot + 4;                          // [UMMA_MAX_TAPS] descriptor address increments of the tap views
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
-
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + UMMA_MAX_TAPS) tap_lo[threadIdx.x - 64] = (uint32_t)p.tap_aoff[threadIdx.x - 64] >> 4;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer: one halo box per step (step = (tile, K chunk)), one weight slab per (step, tap) =====
-    if (lane == 0) {
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      const uint32_t a_tx = (uint32_t)(p.a_loads * p.a_load_bytes);
-      const uint32_t b_tx = (uint32_t)p.block_n * BLOCK_K * 2;
-      auto issue_a = [&](int tile, int kc) {
-        const TileCoord t = decode_tile(p, tile);
-        mbar_wait(&a_empty[as], aph ^ 1);
-        uint8_t* sa = smem + as * p.a_stage_bytes;
-        mbar_expect_tx(&a_full[as], a_tx);
-        for (int l = 0; l < p.a_loads; ++l)      // tensor-map dims are {C, W, F, H}
-          tma_load_4d(sa + l * p.a_load_bytes, &tmap_a, &a_full[as], kc * BLOCK_K, t.w0 + p.halo_x0 + p.a_load_dx[l], t.f0, t.h0 + p.halo_y0);
-        if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
-      };
-      int tile = blockIdx.x, kc = 0;
-      if (tile < total_tiles) issue_a(tile, kc);
-      while (tile < total_tiles) {
-        int ntile = tile, nkc = kc + 1;
-        if (nkc == p.kchunks) { nkc = 0; ntile += gridDim.x; }
-        // with >= 3 A stages the next halo box goes out before this step's weight slabs (deeper prefetch); with 2 it
-        // must follow them, or the producer would sit on a_empty while the B ring drains
-        if (p.a_stages >= 3 && ntile < total_tiles) issue_a(ntile, nkc);
-        const int n0 = (tile % p.n_tiles) * p.block_n;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          mbar_wait(&b_empty[bs], bph ^ 1);
-          mbar_expect_tx(&b_full[bs], b_tx);
-          tma_load_3d(smem_b + bs * p.b_stage_bytes, &tmap_b, &b_full[bs], kc * BLOCK_K, n0, tap);
-          if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
-        }
-        if (p.a_stages < 3 && ntile < total_tiles) issue_a(ntile, nkc);
-        tile = ntile; kc = nkc;
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.block_n);
-      // descriptors as (lo, hi) words: hi is constant (SBO, version, SWIZZLE_128B), lo = address >> 4 (+ LBO field), so a
-      // tap / K-step / stage change is one 32-bit add
-      const uint32_t a_hi = desc_hi_sw128(p.a_sbo), b_hi = desc_hi_sw128(1024);
-      const uint32_t a_stage_lo = (uint32_t)p.a_stage_bytes >> 4, b_stage_lo = (uint32_t)p.b_stage_bytes >> 4;
-      const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_lo0 = desc_lo(smem_u32(smem)) + (uint32_t)as * a_stage_lo;
-          const int kvalid = p.K - kc * BLOCK_K;
-          const int nk = kvalid >= BLOCK_K ? BLOCK_K / UMMA_K : (kvalid + UMMA_K - 1) / UMMA_K;
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t b_lo = b_lo0 + (uint32_t)bs * b_stage_lo;
-            const uint32_t a_lo = a_lo0 + tap_lo[tap];
-            if (p.ablate & 8) {
-            } else if (nk == BLOCK_K / UMMA_K) {
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_f16_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u);
-            } else {
-              for (int k = 0; k < nk; ++k)
-                umma_f16_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u);
-            }
-            umma_commit(&b_empty[bs]);
-            if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
-          }
-          umma_commit(&a_empty[as]);
-          if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
-        }
-        umma_commit(&tfull_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    if (p.epi_direct) epilogue_loop_direct(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, blockIdx.x, gridDim.x);
-    else epilogue_loop(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, smem + HALO_PIPE_BYTES + BAR_BYTES, blockIdx.x, gridDim.x);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-// ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------------------
-// Two CTAs of a cluster (one TPC) work on two adjacent M tiles with ONE M=256 MMA stream issued by the leader: each CTA
-// stages its own A box (halo layout; a 1x1 layer is the halo-free special case) and HALF of the weight slab; the MMA
-// reads both halves, each CTA's TMEM receives its own 128 accumulator rows.  Per CTA and (tap, K chunk) the B traffic
-// halves and the instruction count per FLOP halves.
-//   full barriers live in the leader (count 1: its producer's expect_tx of BOTH CTAs' bytes; the partner's TMA
-//   completes on the leader's barrier);  empty / accumulator-full barriers are per CTA, signalled by multicast commits;
-//   the leader's accumulator-empty barriers count the epilogue warps of both CTAs (16 arrivals).
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-umma_conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                      const __grid_constant__ CUtensorMap tmap_b, const UmmaConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HALO_PIPE_BYTES);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + HALO_A_STAGES_MAX;
-  uint64_t* b_full = a_empty + HALO_A_STAGES_MAX;
-  uint64_t* b_empty = b_full + HALO_B_STAGES_MAX;
-  uint64_t* tfull_bar = b_empty + HALO_B_STAGES_MAX;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint32_t* tap_lo = tmem_slot + 4;
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_f;
-  const int total_tiles = ((m_tiles + 1) / 2) * p.n_tiles;        // pair tiles
-
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + UMMA_MAX_TAPS) tap_lo[threadIdx.x - 64] = (uint32_t)p.tap_aoff[threadIdx.x - 64] >> 4;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs): own A box, own half of the weight slab; completion on the LEADER's barriers =====
-    if (lane == 0) {
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      const uint32_t a_tx = 2u * (uint32_t)(p.a_loads * p.a_load_bytes);
-      const int half_n = p.block_n / 2;
-      const uint32_t b_tx = 2u * (uint32_t)half_n * BLOCK_K * 2;
-      auto issue_a = [&](int tile, int kc) {
-        const TileCoord t = decode_tile(p, tile, (int)rank);
-        mbar_wait(&a_empty[as], aph ^ 1);
-        uint8_t* sa = smem + as * p.a_stage_bytes;
-        if (leader) mbar_expect_tx(&a_full[as], a_tx);
-        const uint32_t bar = mapa_shared(smem_u32(&a_full[as]), 0);
-        const bool first = kc < p.kchunks_a1;
-        const CUtensorMap* map = first ? &tmap_a : &tmap_a2;
-        const int c0 = (first ? kc : kc - p.kchunks_a1) * BLOCK_K;
-        for (int l = 0; l < p.a_loads; ++l)
-          tma_load_4d_pair(sa + l * p.a_load_bytes, map, bar, c0, t.w0 + p.halo_x0 + p.a_load_dx[l], t.f0, t.h0 + p.halo_y0);
-        if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
-      };
-      int tile = pair_id, kc = 0;
-      if (tile < total_tiles) issue_a(tile, kc);
-      while (tile < total_tiles) {
-        int ntile = tile, nkc = kc + 1;
-        if (nkc == p.kchunks) { nkc = 0; ntile += npairs; }
-        if (p.a_stages >= 3 && ntile < total_tiles) issue_a(ntile, nkc);
-        const int n0 = (tile % p.n_tiles) * p.block_n + (int)rank * half_n;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          mbar_wait(&b_empty[bs], bph ^ 1);
-          if (leader) mbar_expect_tx(&b_full[bs], b_tx);
-          tma_load_3d_pair(smem_b + bs * p.b_stage_bytes, &tmap_b, mapa_shared(smem_u32(&b_full[bs]), 0), kc * BLOCK_K, n0, tap);
-          if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
-        }
-        if (p.a_stages < 3 && ntile < total_tiles) issue_a(ntile, nkc);
-        tile = ntile; kc = nkc;
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: leader CTA only, M = 256 across the pair =====
-    if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_f16_m(256, p.block_n);
-      const uint32_t a_hi = desc_hi_sw128(p.a_sbo), b_hi = desc_hi_sw128(1024);
-      const uint32_t a_stage_lo = (uint32_t)p.a_stage_bytes >> 4, b_stage_lo = (uint32_t)p.b_stage_bytes >> 4;
-      const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, acc_phase = 0;
-      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_lo0 = desc_lo(smem_u32(smem)) + (uint32_t)as * a_stage_lo;
-          const int kvalid = kc < p.kchunks_a1 ? p.K1 - kc * BLOCK_K : p.K - p.K1 - (kc - p.kchunks_a1) * BLOCK_K;
-          const int nk = kvalid >= BLOCK_K ? BLOCK_K / UMMA_K : (kvalid + UMMA_K - 1) / UMMA_K;
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t b_lo = b_lo0 + (uint32_t)bs * b_stage_lo;
-            const uint32_t a_lo = a_lo0 + tap_lo[tap];
-            if (p.ablate & 8) {
-            } else if (nk == BLOCK_K / UMMA_K) {
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                umma_f16_lohi_pair(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u);
-            } else {
-              for (int k = 0; k < nk; ++k)
-                umma_f16_lohi_pair(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u);
-            }
-            umma_commit_pair(&b_empty[bs]);               // frees the slab slot in BOTH CTAs
-            if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
-          }
-          umma_commit_pair(&a_empty[as]);
-          if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
-        }
-        umma_commit_pair(&tfull_bar[acc]);                // both CTAs' epilogues
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    if (p.epi_direct) epilogue_loop_direct(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, pair_id, npairs, (int)rank);
-    else epilogue_loop(p, tmem_base, tfull_bar, tempty_bar, warp, lane, total_tiles, smem + HALO_PIPE_BYTES + BAR_BYTES, pair_id, npairs, (int)rank);
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -751,32 +357,30 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   return 0;
 }
 
-// Upgrade a bound stride-1 plan to the halo layout (one A box per K chunk, taps = descriptor views) and, where enabled,
-// to the CTA-pair kernel.
-//   SSNB_HALO=0          keep the classic per-tap boxes (also disables the pair kernel)
+// Route a bound stride-1 plan to the second-generation kernel (umma_conv_v2.cu): halo layout (one A box per K chunk
+// covers the tile plus the filter border, taps = shifted UMMA descriptor views; a 1x1 layer is the halo-free case),
+// several taps per weight stage, CTA pairs.
+//   SSNB_V2=0            keep every layer on the first-generation kernel of this file
+//   SSNB_PAIR=0          single-CTA MMAs (cta_group::1) instead of CTA pairs
 //   SSNB_HALO_MODE=m     how horizontal shifts are realised: 2 (default) halo rows at their exact pitch (bw + halo pixels);
 //                        1 rows padded to a 16-pixel pitch; 4 one box per horizontal shift (every view 1024-byte aligned).
-//                        Measured on B200: the UMMA unit applies the 128-byte swizzle to absolute shared-memory address
-//                        bits, so views that start at any 128-byte row of a TMA-written tile read correctly with
-//                        descriptor base_offset 0 (a non-zero base_offset gives wrong data).
-//   SSNB_HALO_MIN_W=w    smallest image width that uses it (default 14)
-//   SSNB_V2=0            first-generation halo / pair kernels instead of umma_conv_v2.cu
-//   SSNB_PAIR=0|1        cta_group::2 (CTA pairs) off / on; default on with the second-generation kernel
+//                        Measured on B200 (tools/halo_probe.sh): the UMMA unit applies the 128-byte swizzle to absolute
+//                        shared-memory address bits, so views that start at any 128-byte row of a TMA-written tile read
+//                        correctly with descriptor base_offset 0 (a non-zero base_offset gives wrong data).
+//   SSNB_HALO_MIN_W=w    smallest image width that uses it (default 7: every stride-1 layer)
 // `a2` is the second activation source of a fused sibling data gradient (K chunks >= kchunks_a1), or nullptr.
+constexpr int V2_STAGES_MAX = 8;
 int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2 = nullptr) {
   UmmaConvParams& p = plan.p;
-  p.halo = 0; p.pair = 0;
-  const char* en = getenv("SSNB_HALO");
-  if (en && en[0] == '0') return 0;
-  const char* pe = getenv("SSNB_PAIR");
+  p.halo = 0; p.pair = 0; p.v2 = 0;
   const char* ve = getenv("SSNB_V2");
-  const bool v2 = !(ve && ve[0] == '0') && umma_conv_v2_supported(p.ntaps);
-  const bool pair = pe ? pe[0] == '1' : v2;                 // default: pairs wherever the second-generation kernel runs
+  if ((ve && ve[0] == '0') || !umma_conv_v2_supported(p.ntaps)) return 0;
+  const char* pe = getenv("SSNB_PAIR");
+  const bool pair = !(pe && pe[0] == '0');
   if (!plan.enabled || p.a_stride != 1 || p.out_stride != 1) return 0;
-  if (!pair && !v2 && (p.ntaps < 2 || p.kchunks_a1 != p.kchunks)) return 0;
   if (p.kchunks_a1 != p.kchunks && (p.ntaps != 1 || !a2)) return 0;
   const char* mw = getenv("SSNB_HALO_MIN_W");
-  if (a.W < (mw ? atoi(mw) : 14)) return 0;
+  if (a.W < (mw ? atoi(mw) : 7)) return 0;
   const char* md = getenv("SSNB_HALO_MODE");
   const int mode = md ? atoi(md) : 2;
   int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
@@ -795,29 +399,29 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   else pw = 16;
   const int bhh = bh + yh;
   if (loads > 4 || bhh > 256 || bf > 256) return 0;
-  const int pipe = v2 ? UMMA_V2_PIPE_BYTES : HALO_PIPE_BYTES;
+  const int pipe = UMMA_V2_PIPE_BYTES;
   const int b_rows = pair ? p.block_n / 2 : p.block_n;      // weight rows each CTA stages per (tap, K chunk)
   const int a_load_bytes = pw * bf * bhh * BLOCK_K * 2;
   const int a_stage = (loads * a_load_bytes + 1023) / 1024 * 1024;
   const int slab = b_rows * BLOCK_K * 2;                    // one tap of the weight stage (multiple of 1024: rows % 8 == 0)
   int b_taps = 1;
-  if (v2 && p.ntaps > 1) {                                  // several taps per weight stage: fewer barrier hand-offs per K chunk
+  if (p.ntaps > 1) {                                        // several taps per weight stage: fewer barrier hand-offs per K chunk
     for (int g = p.ntaps; g >= 1; --g)
       if (p.ntaps % g == 0 && g * slab <= 48 * 1024 && 2 * a_stage + 3 * g * slab <= pipe) { b_taps = g; break; }
   }
   const int b_stage = (b_taps * slab + 1023) / 1024 * 1024;
   int a_stages, b_stages;
   if (p.ntaps == 1) {                                       // one box + one slab per step: equal ring depths
-    a_stages = b_stages = std::min(HALO_B_STAGES_MAX, pipe / (a_stage + b_stage));
+    a_stages = b_stages = std::min(V2_STAGES_MAX, pipe / (a_stage + b_stage));
     if (a_stages < 3) return 0;
   } else {
     a_stages = 3;
-    if ((pipe - 3 * a_stage) / b_stage < (v2 ? 3 : 4)) a_stages = 2;
+    if ((pipe - 3 * a_stage) / b_stage < 3) a_stages = 2;
     b_stages = (pipe - a_stages * a_stage) / b_stage;
-    if (b_stages < (v2 ? 2 : 3)) return 0;                  // does not fit: stay classic
-    if (b_stages > HALO_B_STAGES_MAX) b_stages = HALO_B_STAGES_MAX;
+    if (b_stages < 2) return 0;                             // does not fit: stay on the first-generation kernel
+    if (b_stages > V2_STAGES_MAX) b_stages = V2_STAGES_MAX;
   }
-  p.v2 = v2 ? 1 : 0; p.b_taps = b_taps;
+  p.v2 = 1; p.b_taps = b_taps;
   p.halo = 1; p.pair = pair ? 1 : 0;
   p.bw = bw; p.bh = bh; p.bf = bf;
   p.tiles_w = (a.W + bw - 1) / bw; p.tiles_h = (a.H + bh - 1) / bh; p.tiles_f = (F + bf - 1) / bf;
@@ -945,35 +549,11 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
   }
   UmmaConvParams p = plan.p;
   if (mask && plan.mask_y) { p.mask_y = plan.mask_y; p.mask_pitch = plan.mask_pitch; p.mask_coff = plan.mask_coff; }
-  static const bool epi_transposed = [] { const char* e = getenv("SSNB_EPI"); return e && e[0] == '1'; }();
-  p.epi_direct = epi_transposed ? 0 : 1;
   static const int ablate = [] { const char* e = getenv("SSNB_ABLATE"); return e ? atoi(e) : 0; }();     // timing experiments only
   p.ablate = ablate;
   if (p.v2) return umma_conv_v2_launch(ctx, plan, p, s);
-  if (p.pair) {
-    if (!ctx.attr_set_pair) {
-      if (cudaFuncSetAttribute(umma_conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES) != cudaSuccess) {
-        set_thread_error("umma conv (pair): cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
-      ctx.attr_set_pair = true;
-    }
-    const int ptiles = ((p.tiles_w * p.tiles_h * p.tiles_f + 1) / 2) * p.n_tiles;
-    const int pairs = std::min(ptiles, ctx.num_sms / 2);
-    umma_conv_pair_kernel<<<2 * pairs, NUM_THREADS, HALO_SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, p);
-    SSNB_LAUNCH_CHECK("umma_conv_pair_kernel");
-    return 0;
-  }
   const int total = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
   const int grid = total < ctx.num_sms ? total : ctx.num_sms;
-  if (p.halo) {
-    if (!ctx.attr_set_halo) {
-      if (cudaFuncSetAttribute(umma_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BYTES) != cudaSuccess) {
-        set_thread_error("umma conv (halo): cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
-      ctx.attr_set_halo = true;
-    }
-    umma_conv_halo_kernel<<<grid, NUM_THREADS, HALO_SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_b, p);
-    SSNB_LAUNCH_CHECK("umma_conv_halo_kernel");
-    return 0;
-  }
   umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, p);
   SSNB_LAUNCH_CHECK("umma_conv_kernel");
   return 0;

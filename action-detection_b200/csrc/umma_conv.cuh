@@ -20,7 +20,7 @@ struct UmmaContext {
   bool active = false;
   void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
   int num_sms = 148;
-  bool attr_set = false, attr_set_halo = false, attr_set_pair = false;
+  bool attr_set = false;
 };
 
 struct UmmaConvParams {
@@ -43,7 +43,6 @@ struct UmmaConvParams {
   // halo mode (3x3 stride-1 layers, conv1): ONE A box per K chunk covers the tile plus its filter halo, stored
   // [y][frame][x][64 ch]; every tap is a shifted UMMA descriptor view into it (no per-tap re-staging of A)
   int ablate;                     // timing experiments (SSNB_ABLATE bit mask): 1 no stores, 2 no bias loads, 4 empty epilogue, 8 no MMAs
-  int epi_direct;                 // epilogue variant: 1 = per-thread row stores, 0 = shared-memory transposed, coalesced
   int halo;
   int pair;                       // CTA-pair kernel (cta_group::2): tiles are (N tile, pair of M tiles)
   int v2;                         // second-generation kernel (umma_conv_v2.cu): warp-uniform role loops, grouped weight stages
@@ -109,6 +108,9 @@ struct UmmaWgradParams {
   int x_stride;                   // 2: stride-2 layers, the x box steps over the input with TMA element stride 2
   float* bias_partial;            // [split][Cout] column sums of dz (bias gradient) from an extra ones-operand MMA, or nullptr
   int taps_per_cta, tap_groups, mma_n;   // taps sharing one dz tile per CTA; N of each tap's MMA
+  int stages, stage_bytes;        // pipeline depth / stride
+  int halo;                       // x staged as one halo box per 64 channels; taps are descriptor views (tap_xoff)
+  int x_box_bytes, x_box_tx, x_sbo, halo_x0, halo_y0, tap_xoff[UMMA_MAX_TAPS];   // box stride in smem / bytes one box delivers
   float* partial;
 };
 struct UmmaWgradPlan {

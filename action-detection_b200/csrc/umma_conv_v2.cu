@@ -31,7 +31,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int BAR_BYTES = 1024;
-constexpr int SMEM_BYTES = UMMA_V2_PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES;
+constexpr int BIAS_MAX = 1024;                     // floats of folded-BN bias staged in shared memory (n_tiles * block_n)
+constexpr int SMEM_BYTES = UMMA_V2_PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_MAX * 4;
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -70,17 +71,14 @@ __device__ __forceinline__ void mma_lohi(uint32_t d, uint32_t alo, uint32_t ahi,
 }
 
 // one 16-column chunk of an accumulator row: bias / accumulate / ReLU / ReLU-gradient mask, fp16 store (32 bytes)
-__device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, int col, uint4* dst, const uint4& o0, const uint4& o1,
-                                            const uint4& y0, const uint4& y1) {
+__device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, const float4* bias, uint4* dst, const uint4& o0,
+                                            const uint4& o1, const uint4& y0, const uint4& y1) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
   if (p.bias) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
+    for (int j = 0; j < 4; ++j) { v[4 * j] += bias[j].x; v[4 * j + 1] += bias[j].y; v[4 * j + 2] += bias[j].z; v[4 * j + 3] += bias[j].w; }
   }
   if (p.accumulate) {
     const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
@@ -141,6 +139,11 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr bool ONE_RING = NTAPS == 1;        // 1x1 layers: A box and weight slab of a step share one barrier pair
 
+  // folded-BN bias of every output column of this launch, zero past Cout: the epilogue reads it with broadcast LDS
+  // (a global __ldg there sat on the critical path right after the TMEM load: half of the epilogue's stall samples)
+  float* bias_s = reinterpret_cast<float*>(smem + UMMA_V2_PIPE_BYTES + BAR_BYTES);
+  if (p.bias)
+    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += NUM_THREADS) bias_s[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
@@ -266,13 +269,16 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, the two warps of a quadrant alternate 32-column groups =====
+    // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int cpar = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int rw = row % p.bw, rf = (row / p.bw) % p.bf, rh = row / (p.bw * p.bf);      // halo row order: x, frame, y
     uint32_t acc = 0, acc_phase = 0;
     TileIter it; it.init(p, first, step);
+    // every thread stores its own accumulator row, 32 bytes per 16 columns; the two warps of a quadrant alternate
+    // 32-column groups.  (A shared-memory transposed, fully coalesced variant was measured slower -- 13.6 vs 12.3 ms per
+    // training step -- and removed; see profiles/README.md.)
     for (; it.valid(p); it.next(p)) {
       const int w = it.mw * p.bw + rw, h = it.mh * p.bh + rh;
       const int f = (PAIR ? 2 * it.mq + (int)rank : it.mq) * p.bf + rf;
@@ -282,10 +288,32 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __half* orow = p.out + opix * p.out_pitch + p.out_coff;
       __half* orow2 = p.out2 + opix * p.out2_pitch + p.out2_coff - p.n_split;
       const __half* mrow = p.mask_y ? p.mask_y + opix * p.mask_pitch + p.mask_coff : nullptr;
+      const int ncol = (p.ablate & 4) ? 0 : p.block_n;              // SSNB_ABLATE=4 (timing experiment): empty epilogue
+      // Global operands of the epilogue (old gradient to accumulate into, activation for the ReLU-gradient mask) are
+      // software-pipelined: the loads of column group i+1 go out before group i is processed, and those of a tile's
+      // first group before the wait for its accumulator, so their DRAM/L2 latency overlaps the MMAs and the TMEM reads.
+      struct Pre { uint4 oa0, oa1, ob0, ob1, ya0, ya1, yb0, yb1; };
+      auto prefetch = [&](int c0, Pre& q) {
+        const bool two = c0 + 16 < p.block_n;
+        const int cola = n0 + c0, colb = cola + 16;
+        const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
+        if (p.accumulate) {
+          const uint4* da = reinterpret_cast<const uint4*>((cola < p.n_split ? orow : orow2) + cola);
+          const uint4* db2 = reinterpret_cast<const uint4*>((colb < p.n_split ? orow : orow2) + colb);
+          if (va) { q.oa0 = da[0]; q.oa1 = da[1]; }
+          if (vb) { q.ob0 = db2[0]; q.ob1 = db2[1]; }
+        }
+        if (mrow) {
+          const uint4* my = reinterpret_cast<const uint4*>(mrow + cola);
+          if (va) { q.ya0 = __ldg(my); q.ya1 = __ldg(my + 1); }
+          if (vb) { q.yb0 = __ldg(my + 2); q.yb1 = __ldg(my + 3); }
+        }
+      };
+      Pre cur = {};
+      if (cpar * 32 < ncol) prefetch(cpar * 32, cur);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-      const int ncol = (p.ablate & 4) ? 0 : p.block_n;              // SSNB_ABLATE=4 (timing experiment): empty epilogue
       if (cpar * 32 >= ncol) {                                      // narrow tile: this warp has no columns, release at once
         tc_fence_before();
         __syncwarp();
@@ -299,15 +327,15 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
         uint4* da = reinterpret_cast<uint4*>((cola < p.n_split ? orow : orow2) + cola);
         uint4* db2 = reinterpret_cast<uint4*>((colb < p.n_split ? orow : orow2) + colb);
-        uint4 oa0 = {}, oa1 = {}, ob0 = {}, ob1 = {}, ya0 = {}, ya1 = {}, yb0 = {}, yb1 = {};
-        if (p.accumulate) {
-          if (va) { oa0 = da[0]; oa1 = da[1]; }
-          if (vb) { ob0 = db2[0]; ob1 = db2[1]; }
-        }
-        if (mrow) {
-          const uint4* my = reinterpret_cast<const uint4*>(mrow + cola);
-          if (va) { ya0 = __ldg(my); ya1 = __ldg(my + 1); }
-          if (vb) { yb0 = __ldg(my + 2); yb1 = __ldg(my + 3); }
+        Pre nxt = {};
+        if (c0 + 64 < ncol) prefetch(c0 + 64, nxt);
+        float4 ba[4], bb[4];
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
+            bb[j] = *reinterpret_cast<const float4*>(bias_s + (two ? colb : cola) + 4 * j);
+          }
         }
         uint32_t ra[16], rb[16];
         tmem_ld16(taddr + c0, ra);
@@ -320,8 +348,9 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
           }
         }
-        if (va) store_chunk(p, ra, cola, da, oa0, oa1, ya0, ya1);
-        if (vb) store_chunk(p, rb, colb, db2, ob0, ob1, yb0, yb1);
+        if (va) store_chunk(p, ra, ba, da, cur.oa0, cur.oa1, cur.ya0, cur.ya1);
+        if (vb) store_chunk(p, rb, bb, db2, cur.ob0, cur.ob1, cur.yb0, cur.yb1);
+        cur = nxt;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

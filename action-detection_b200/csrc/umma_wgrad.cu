@@ -8,6 +8,8 @@
 //   warps 2..5: epilogue -> split-K partials (reduced in fixed order by wgrad_finalize_kernel).
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 
 #include "umma_conv.cuh"
 #include "umma_dev.cuh"
@@ -16,24 +18,25 @@ namespace ssnb {
 namespace {
 
 using namespace umma;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int BOX_BYTES = 64 * 128;                 // [64 px][64 ch] fp16
 constexpr int A_BYTES = 2 * BOX_BYTES;              // 128 output channels
-constexpr int STAGE_BYTES = A_BYTES + 4 * BOX_BYTES;  // + up to 256 input channels
+constexpr int PIPE_BYTES = 4 * (A_BYTES + 4 * BOX_BYTES);   // 192 KiB of operand staging
 constexpr int NUM_THREADS = 192;
-constexpr int ONES_OFF = STAGES * STAGE_BYTES + 1024;                // [64 px][64 ch] tile of fp16 ones (bias-gradient operand), 1 KiB aligned
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + BOX_BYTES;
+constexpr int ONES_OFF = PIPE_BYTES + 1024;                // [64 px][64 ch] tile of fp16 ones (bias-gradient operand), 1 KiB aligned
+constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + BOX_BYTES;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
                   const UmmaWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
 
   // warp index through a shuffle (provably warp-uniform): the role loops below run on all 32 lanes with uniform control
   // flow, one elected lane issues the TMA / MMA instructions (see umma_conv_v2.cu for the measurements behind this)
@@ -59,7 +62,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dz)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(tfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -80,7 +83,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   if (warp == 0) {
     const bool el = elect_one_lane();
     uint32_t stage = 0, phase = 0;
-    const uint32_t tx_bytes = (uint32_t)(2 + nboxes_b * ntap) * BOX_BYTES;
+    const uint32_t tx_bytes = p.halo ? (uint32_t)(2 * BOX_BYTES + nboxes_b * p.x_box_tx) : (uint32_t)(2 + nboxes_b * ntap) * BOX_BYTES;
     // pixel-tile coordinates advance by carries (no divisions in the loop)
     int tw = pt0 % p.tiles_w, th = (pt0 / p.tiles_w) % p.tiles_h, tf = pt0 / (p.tiles_w * p.tiles_h);
     for (int pt = pt0; pt < pt1; ++pt) {
@@ -90,12 +93,21 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
         mbar_expect_tx(&full_bar[stage], tx_bytes);
-        tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, h0, f0);
-        tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, h0, f0);
-        for (int t = 0; t < ntap; ++t)
+        if (p.halo) {
+          // halo layout: tensor-map dims {C, W, F, H}; ONE x box per 64 input channels covers the tile plus the filter
+          // border, every tap of this CTA is a shifted descriptor view into it
+          tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, f0, h0);
+          tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, f0, h0);
           for (int b = 0; b < nboxes_b; ++b)
-            tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64,
-                        w0 * p.x_stride + p.tap_dx[tap0 + t], h0 * p.x_stride + p.tap_dy[tap0 + t], f0);
+            tma_load_4d(sb + b * p.x_box_bytes, &tmap_x, &full_bar[stage], n0 + b * 64, w0 + p.halo_x0, f0, h0 + p.halo_y0);
+        } else {
+          tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, h0, f0);
+          tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, h0, f0);
+          for (int t = 0; t < ntap; ++t)
+            for (int b = 0; b < nboxes_b; ++b)
+              tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64,
+                          w0 * p.x_stride + p.tap_dx[tap0 + t], h0 * p.x_stride + p.tap_dy[tap0 + t], f0);
+        }
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
       if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tf; } }
@@ -109,19 +121,24 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     const uint32_t base_lo = ((smem_u32(smem) >> 4) & 0x3FFF) | lbo;
     const uint32_t ones_lo = ((smem_u32(smem + ONES_OFF) >> 4) & 0x3FFF) | lbo;
     const uint32_t kstep_lo = (UMMA_K * 128) >> 4;                    // 16 pixel rows
+    // x operand: classic = one [64 px][64 ch] box per (tap, 64 channels); halo = views into the halo box: 8-pixel row
+    // groups x_sbo bytes apart, 64-channel atoms x_box_bytes apart
+    const uint32_t hi_x = p.halo ? desc_hi_sw128(p.x_sbo) : hi;
+    const uint32_t lbo_x = p.halo ? ((uint32_t)((p.x_box_bytes >> 4) & 0x3FFF) << 16) : lbo;
+    const uint32_t kstep_x = p.halo ? (uint32_t)(2 * p.x_sbo) >> 4 : kstep_lo;
     uint32_t stage = 0, phase = 0;
     for (int pt = pt0; pt < pt1; ++pt) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t sa_lo = base_lo + stage * (STAGE_BYTES >> 4);
-      const uint32_t sb_lo = sa_lo + (A_BYTES >> 4);
+      const uint32_t sa_lo = base_lo + stage * ((uint32_t)STAGE_BYTES >> 4);
+      const uint32_t sb_lo = ((sa_lo + (A_BYTES >> 4)) & 0xFFFFu) | lbo_x;
       if (el) {
         const uint32_t first = pt > pt0 ? 1u : 0u;
         for (int t = 0; t < ntap; ++t) {
-          const uint32_t xb_lo = sb_lo + t * nboxes_b * (BOX_BYTES >> 4);
+          const uint32_t xb_lo = sb_lo + (p.halo ? (uint32_t)p.tap_xoff[tap0 + t] >> 4 : (uint32_t)(t * nboxes_b) * (BOX_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; ++k)      // 16 pixel rows (2 groups of 8) per instruction
-            umma_f16_lohi(tmem_base + t * p.mma_n, sa_lo + k * kstep_lo, hi, xb_lo + k * kstep_lo, hi, idesc, first | (uint32_t)k);
+            umma_f16_lohi(tmem_base + t * p.mma_n, sa_lo + k * kstep_lo, hi, xb_lo + k * kstep_x, hi_x, idesc, first | (uint32_t)k);
         }
         if (do_bias) {
 #pragma unroll
@@ -210,21 +227,68 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   // the accumulators (taps * mma_n fp32 columns) must fit the 512 TMEM columns
   p.mma_n = p.block_n;
   if (p.n_tiles == 1 && cin < p.block_n) p.mma_n = (cin + 15) / 16 * 16;     // narrow inputs (conv1 space-to-depth: 16)
-  p.taps_per_cta = 4 / (p.block_n / 64);
-  if (p.taps_per_cta < 1) p.taps_per_cta = 1;
-  while (p.taps_per_cta > 1 && p.taps_per_cta * p.mma_n > 512) --p.taps_per_cta;
-  if (p.taps_per_cta > ntaps) p.taps_per_cta = ntaps;
+  // halo variant (stride-1 multi-tap layers, SSNB_WGRAD_HALO=0 disables): ONE x box per 64 input channels covers the
+  // 64-pixel tile plus the filter border ([y][frame][x] pixel order, as in umma_conv_v2.cu) and every tap is a shifted
+  // descriptor view into it, so the taps a CTA can take are limited by TMEM columns only and x is staged once, not per tap
+  int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  for (int t = 0; t < ntaps; ++t) { x0 = std::min(x0, tdx[t]); x1 = std::max(x1, tdx[t]); y0 = std::min(y0, tdy[t]); y1 = std::max(y1, tdy[t]); }
+  const char* he = getenv("SSNB_WGRAD_HALO");
+  bool halo = !(he && he[0] == '0') && x_stride == 1 && ntaps > 1 && dz.W >= 7;
+  int hbw = 8, hbh = 8, hbf = 1, pw = 8, x_box = 0, h_taps = 1, h_stages = 0;
+  if (halo) {
+    while (hbh > 1 && dz.H % hbh) hbh >>= 1;
+    hbf = 64 / (hbw * hbh);
+    pw = hbw + (x1 - x0);
+    x_box = (pw * hbf * (hbh + (y1 - y0)) * 128 + 1023) / 1024 * 1024;
+    h_taps = std::min(ntaps, (512 - 16) / p.mma_n);
+    h_stages = std::min(MAX_STAGES, PIPE_BYTES / (A_BYTES + (p.block_n / 64) * x_box));
+    if (h_taps < 2 || h_stages < 3) halo = false;
+  }
+  p.halo = halo ? 1 : 0;
+  if (halo) {
+    p.bw = hbw; p.bh = hbh; p.bf = hbf;
+    p.tiles_w = (dz.W + hbw - 1) / hbw; p.tiles_h = dz.H / hbh; p.tiles_f = (F + hbf - 1) / hbf;
+    p.taps_per_cta = h_taps;
+    p.x_box_bytes = x_box; p.x_box_tx = pw * hbf * (hbh + (y1 - y0)) * 128; p.x_sbo = pw * 128; p.halo_x0 = x0; p.halo_y0 = y0;
+    p.stage_bytes = A_BYTES + (p.block_n / 64) * x_box; p.stages = h_stages;
+    for (int t = 0; t < ntaps; ++t) p.tap_xoff[t] = ((tdy[t] - y0) * hbf * pw + (tdx[t] - x0)) * 128;
+  } else {
+    p.stage_bytes = A_BYTES + 4 * BOX_BYTES; p.stages = 4;
+    // several taps per CTA share one dz tile: stage = 2 dz boxes + taps * (block_n/64) x boxes <= 6 boxes, and
+    // the accumulators (taps * mma_n fp32 columns) must fit the 512 TMEM columns
+    p.taps_per_cta = 4 / (p.block_n / 64);
+    if (p.taps_per_cta < 1) p.taps_per_cta = 1;
+    while (p.taps_per_cta > 1 && p.taps_per_cta * p.mma_n > 512) --p.taps_per_cta;
+    if (p.taps_per_cta > ntaps) p.taps_per_cta = ntaps;
+  }
   p.tap_groups = (ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
   p.taps_per_cta = (ntaps + p.tap_groups - 1) / p.tap_groups;        // balance the groups (9 taps: 3+3+3 rather than 4+4+1)
   const int ptiles = p.tiles_w * p.tiles_h * p.tiles_f;
   const int ctas = p.m_tiles * p.n_tiles * p.tap_groups;
-  int splits = (2 * ctx.num_sms + ctas - 1) / ctas;
+  // one CTA per SM is resident (192 KiB pipeline), so a second wave only runs after the first: ONE wave of CTAs with
+  // twice the pixels each does the same work with half the split-K partial traffic (every CTA writes its whole
+  // 128 x taps*N fp32 accumulator: 100-250 KB) and no wave tail (conv2_3x3 used to run 300 CTAs = three waves)
+  const char* we = getenv("SSNB_WGRAD_WAVES");
+  int splits = ((we ? atoi(we) : 1) * ctx.num_sms) / ctas;
+  if (splits < 1) splits = 1;
   if (splits > max_splits) splits = max_splits;
   if (splits > ptiles) splits = ptiles;
   if (splits < 1) splits = 1;
   p.ptiles_per_split = (ptiles + splits - 1) / splits;
   p.splits = (ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
   p.partial = partial; p.bias_partial = nullptr;
+  if (halo) {
+    cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)dz.W, (cuuint64_t)F, (cuuint64_t)dz.H};
+    cuuint64_t str[3] = {(cuuint64_t)dz.pitch * 2, (cuuint64_t)dz.H * dz.W * dz.pitch * 2, (cuuint64_t)dz.W * dz.pitch * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bf, (cuuint32_t)p.bh};
+    if (int rc = umma_encode_f16(ctx, &plan.tmap_dz, 4, reinterpret_cast<__half*>(dz.base) + dz.coff, dims, str, box)) return rc;
+    cuuint64_t xd[4] = {(cuuint64_t)cin, (cuuint64_t)x.W, (cuuint64_t)F, (cuuint64_t)x.H};
+    cuuint64_t xs[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.H * x.W * x.pitch * 2, (cuuint64_t)x.W * x.pitch * 2};
+    cuuint32_t xb[4] = {64, (cuuint32_t)pw, (cuuint32_t)p.bf, (cuuint32_t)(p.bh + (y1 - y0))};
+    if (int rc = umma_encode_f16(ctx, &plan.tmap_x, 4, reinterpret_cast<__half*>(x.base) + x.coff, xd, xs, xb)) return rc;
+    plan.enabled = true;
+    return 0;
+  }
   {
     cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)dz.W, (cuuint64_t)dz.H, (cuuint64_t)F};
     cuuint64_t str[3] = {(cuuint64_t)dz.pitch * 2, (cuuint64_t)dz.W * dz.pitch * 2, (cuuint64_t)dz.H * dz.W * dz.pitch * 2};

@@ -21,9 +21,14 @@ for k, v in bb.items():
 model = model.to(dev).train()
 model.set_precision(_lib.FAST_FP16, 4096.0)
 batch = tuple(t.to(dev) for t in synth.synth_batch(4, 20, 3, seed=0))
+params = [p for p in model.parameters() if p.requires_grad]
+flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+off = 0
+for p in params:
+    p.grad = flat_grad[off:off + p.numel()].view_as(p)
+    off += p.numel()
 for i in range(steps):
-    for p in model.parameters():
-        p.grad = None
+    flat_grad.zero_()
     losses = model.fused_step(*batch)
 torch.cuda.synchronize()
 print("losses", losses.tolist())
