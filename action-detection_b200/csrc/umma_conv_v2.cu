@@ -70,9 +70,32 @@ __device__ __forceinline__ void mma_lohi(uint32_t d, uint32_t alo, uint32_t ahi,
   if (PAIR) umma_f16_lohi_pair(d, alo, ahi, blo, bhi, idesc, acc); else umma_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction per thread per 16 fp16 columns instead of two
+// 128-bit ones -- the scattered row accesses of the epilogue are bound by LSU wavefronts, not bytes
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ U8 ldg256(const void* p) {
+  U8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ U8 ldg256_nc(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const U8& a) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]),
+               "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7])
+               : "memory");
+}
+
 // one 16-column chunk of an accumulator row: bias / accumulate / ReLU / ReLU-gradient mask, fp16 store (32 bytes)
-__device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, const float4* bias, uint4* dst, const uint4& o0,
-                                            const uint4& o1, const uint4& y0, const uint4& y1) {
+__device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, const float4* bias, __half* dst, const U8& old,
+                                            const U8& y) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -81,37 +104,29 @@ __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint3
     for (int j = 0; j < 4; ++j) { v[4 * j] += bias[j].x; v[4 * j + 1] += bias[j].y; v[4 * j + 2] += bias[j].z; v[4 * j + 3] += bias[j].w; }
   }
   if (p.accumulate) {
-    const __half2* h0 = reinterpret_cast<const __half2*>(&o0);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&o1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-      v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+    for (int j = 0; j < 8; ++j) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&old.v[j]));
+      v[2 * j] += a.x; v[2 * j + 1] += a.y;
     }
   }
   if (p.relu) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (p.mask_y) {
-    const __half2* a0 = reinterpret_cast<const __half2*>(&y0);
-    const __half2* a1 = reinterpret_cast<const __half2*>(&y1);
+  U8 q;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 ya = __half22float2(a0[j]), yb = __half22float2(a1[j]);
-      if (!(ya.x > 0.f)) v[2 * j] = 0.f;
-      if (!(ya.y > 0.f)) v[2 * j + 1] = 0.f;
-      if (!(yb.x > 0.f)) v[8 + 2 * j] = 0.f;
-      if (!(yb.y > 0.f)) v[8 + 2 * j + 1] = 0.f;
-    }
+  for (int j = 0; j < 8; ++j) {
+    const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    q.v[j] = *reinterpret_cast<const uint32_t*>(&h);
   }
-  uint4 q0, q1;
-  __half2* g0 = reinterpret_cast<__half2*>(&q0);
-  __half2* g1 = reinterpret_cast<__half2*>(&q1);
+  if (p.mask_y) {
+    const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { g0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); g1[j] = __floats2half2_rn(v[8 + 2 * j], v[8 + 2 * j + 1]); }
-  if (p.ablate & 1) { if (v[0] == 12345.678f) dst[0] = q0; return; }     // SSNB_ABLATE=1: no stores
-  dst[0] = q0; dst[1] = q1;
+    for (int j = 0; j < 8; ++j) q.v[j] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&y.v[j]), zero);     // keep where y > 0 (NaN -> 0)
+  }
+  if (p.ablate & 1) { if (v[0] == 12345.678f) stg256(dst, q); return; }     // SSNB_ABLATE=1: no stores
+  stg256(dst, q);
 }
 
 template <bool PAIR, int NTAPS>
@@ -292,21 +307,18 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // Global operands of the epilogue (old gradient to accumulate into, activation for the ReLU-gradient mask) are
       // software-pipelined: the loads of column group i+1 go out before group i is processed, and those of a tile's
       // first group before the wait for its accumulator, so their DRAM/L2 latency overlaps the MMAs and the TMEM reads.
-      struct Pre { uint4 oa0, oa1, ob0, ob1, ya0, ya1, yb0, yb1; };
+      struct Pre { U8 oa, ob, ya, yb; };
       auto prefetch = [&](int c0, Pre& q) {
         const bool two = c0 + 16 < p.block_n;
         const int cola = n0 + c0, colb = cola + 16;
         const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
         if (p.accumulate) {
-          const uint4* da = reinterpret_cast<const uint4*>((cola < p.n_split ? orow : orow2) + cola);
-          const uint4* db2 = reinterpret_cast<const uint4*>((colb < p.n_split ? orow : orow2) + colb);
-          if (va) { q.oa0 = da[0]; q.oa1 = da[1]; }
-          if (vb) { q.ob0 = db2[0]; q.ob1 = db2[1]; }
+          if (va) q.oa = ldg256((cola < p.n_split ? orow : orow2) + cola);
+          if (vb) q.ob = ldg256((colb < p.n_split ? orow : orow2) + colb);
         }
         if (mrow) {
-          const uint4* my = reinterpret_cast<const uint4*>(mrow + cola);
-          if (va) { q.ya0 = __ldg(my); q.ya1 = __ldg(my + 1); }
-          if (vb) { q.yb0 = __ldg(my + 2); q.yb1 = __ldg(my + 3); }
+          if (va) q.ya = ldg256_nc(mrow + cola);
+          if (vb) q.yb = ldg256_nc(mrow + colb);
         }
       };
       Pre cur = {};
@@ -325,8 +337,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const bool two = c0 + 16 < p.block_n;                       // warp-uniform
         const int cola = n0 + c0, colb = cola + 16;
         const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
-        uint4* da = reinterpret_cast<uint4*>((cola < p.n_split ? orow : orow2) + cola);
-        uint4* db2 = reinterpret_cast<uint4*>((colb < p.n_split ? orow : orow2) + colb);
+        __half* da = (cola < p.n_split ? orow : orow2) + cola;
+        __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
         Pre nxt = {};
         if (c0 + 64 < ncol) prefetch(c0 + 64, nxt);
         float4 ba[4], bb[4];
@@ -348,8 +360,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
           }
         }
-        if (va) store_chunk(p, ra, ba, da, cur.oa0, cur.oa1, cur.ya0, cur.ya1);
-        if (vb) store_chunk(p, rb, bb, db2, cur.ob0, cur.ob1, cur.yb0, cur.yb1);
+        if (va) store_chunk(p, ra, ba, da, cur.oa, cur.ya);
+        if (vb) store_chunk(p, rb, bb, db2, cur.ob, cur.yb);
         cur = nxt;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

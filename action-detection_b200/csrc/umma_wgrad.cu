@@ -227,13 +227,15 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   // the accumulators (taps * mma_n fp32 columns) must fit the 512 TMEM columns
   p.mma_n = p.block_n;
   if (p.n_tiles == 1 && cin < p.block_n) p.mma_n = (cin + 15) / 16 * 16;     // narrow inputs (conv1 space-to-depth: 16)
-  // halo variant (stride-1 multi-tap layers, SSNB_WGRAD_HALO=0 disables): ONE x box per 64 input channels covers the
+  // halo variant (stride-1 multi-tap layers; opt-in with SSNB_WGRAD_HALO=1 -- correct, but measured SLOWER than per-tap
+  // boxes on B200: 3.7 vs 2.9 ms over the 69 layers; the kernel is bound by shared-memory reads of the dz tile, which
+  // every N=64..128 MMA repeats, not by staging traffic): ONE x box per 64 input channels covers the
   // 64-pixel tile plus the filter border ([y][frame][x] pixel order, as in umma_conv_v2.cu) and every tap is a shifted
   // descriptor view into it, so the taps a CTA can take are limited by TMEM columns only and x is staged once, not per tap
   int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
   for (int t = 0; t < ntaps; ++t) { x0 = std::min(x0, tdx[t]); x1 = std::max(x1, tdx[t]); y0 = std::min(y0, tdy[t]); y1 = std::max(y1, tdy[t]); }
   const char* he = getenv("SSNB_WGRAD_HALO");
-  bool halo = !(he && he[0] == '0') && x_stride == 1 && ntaps > 1 && dz.W >= 7;
+  bool halo = (he && he[0] == '1') && x_stride == 1 && ntaps > 1 && dz.W >= 7;
   int hbw = 8, hbh = 8, hbf = 1, pw = 8, x_box = 0, h_taps = 1, h_stages = 0;
   if (halo) {
     while (hbh > 1 && dz.H % hbh) hbh >>= 1;

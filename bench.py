@@ -357,15 +357,15 @@ def main():
                 big = (oname[:-3], flop, best)
         peak = peaks.get("bf16_tflops", 1590.0)
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("umma_conv_kernel:%s_fwd" % big[0], {}).get("dram_bytes")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("umma_conv_v2_kernel:%s_fwd" % big[0], {}).get("dram_bytes")
         except Exception:
             traffic = None
         achieved = big[1] / (big[2] / 1e3) / 1e12
         fam = tot_flop / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor",
-                "kernel": ("umma_conv_kernel" if prec == _lib.FAST_FP16 else "conv_kernel<float> (SIMT)") + ", largest launch: %s forward" % big[0],
+                "kernel": ("umma_conv_v2_kernel" if prec == _lib.FAST_FP16 else "conv_kernel<float> (SIMT)") + ", largest launch: %s forward" % big[0],
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_unit": "bytes per launch (ncu --set full dram read+write, profiles/r01_ncu_full_tensor_kernels.txt)",
+                "traffic_unit": "bytes per launch (ncu --set full dram read+write, profiles/r01_ncu_full_v2.txt)",
                 "peak_source": peak_src + " bf16 burst (kernel timed alone, L2 flushed before each launch)",
                 "flop_per_launch": big[1], "ms_per_launch": big[2],
                 "family_average": {"launches_timed": n_l, "achieved": fam, "frac": fam / peak,
