@@ -381,7 +381,7 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   if (p.kchunks_a1 != p.kchunks && (p.ntaps != 1 || !a2)) return 0;
   // the v2 epilogue moves 16 fp16 columns per 256-bit access: rows and channel slices must be 32-byte aligned; its
   // shared-memory bias table holds 1024 columns
-  if (p.out_pitch % 16 || p.out_coff % 16 || p.out2_pitch % 16 || p.out2_coff % 16 || p.n_split % 16 || p.n_tiles * p.block_n > 1024) return 0;
+  if (p.out_pitch % 16 || p.out_coff % 16 || p.out2_pitch % 16 || p.out2_coff % 16 || p.n_split % 16 || (p.bias && p.n_tiles * p.block_n > 1024)) return 0;
   if (plan.mask_y && (plan.mask_pitch % 16 || plan.mask_coff % 16)) return 0;
   const char* mw = getenv("SSNB_HALO_MIN_W");
   if (a.W < (mw ? atoi(mw) : 7)) return 0;

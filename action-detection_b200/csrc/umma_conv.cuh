@@ -110,6 +110,7 @@ struct UmmaWgradParams {
   int taps_per_cta, tap_groups, mma_n;   // taps sharing one dz tile per CTA; N of each tap's MMA
   int stages, stage_bytes;        // pipeline depth / stride
   int halo;                       // x staged as one halo box per 64 channels; taps are descriptor views (tap_xoff)
+  int run_len, run_stride;        // halo: the CTA's taps are one run of equally spaced views taken by a single MMA (N = run_len*64)
   int x_box_bytes, x_box_tx, x_sbo, halo_x0, halo_y0, tap_xoff[UMMA_MAX_TAPS];   // box stride in smem / bytes one box delivers
   float* partial;
 };

@@ -114,7 +114,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     }
   } else if (warp == 1) {
     const bool el = elect_one_lane();
-    const uint32_t idesc = make_idesc_f16_mn(p.mma_n), idesc_bias = make_idesc_f16_mn(16);
+    const uint32_t idesc = make_idesc_f16_mn(p.mma_n), idesc_bias = make_idesc_f16_mn(16), idesc_run = make_idesc_f16_mn(ntap * p.mma_n);
     // descriptors as (lo, hi) words: hi constant (SBO 1024, version, SWIZZLE_128B), lo = address >> 4 | LBO field
     const uint32_t hi = desc_hi_sw128(1024);
     const uint32_t lbo = (uint32_t)((BOX_BYTES >> 4) & 0x3FFF) << 16;
@@ -134,11 +134,21 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const uint32_t sb_lo = ((sa_lo + (A_BYTES >> 4)) & 0xFFFFu) | lbo_x;
       if (el) {
         const uint32_t first = pt > pt0 ? 1u : 0u;
+        if (p.run_len > 1) {
+          // the taps of this CTA form ONE run whose views are `run_stride` bytes apart: a single MMA takes them as
+          // consecutive 64-channel N atoms (LBO = run_stride), so the dz tile is read once per K step instead of once
+          // per tap (the kernel is bound by those shared-memory reads)
+          const uint32_t xb_lo = (sb_lo & 0xFFFFu) + ((uint32_t)p.tap_xoff[tap0] >> 4) + (((uint32_t)p.run_stride >> 4) << 16);
+#pragma unroll
+          for (int k = 0; k < 64 / UMMA_K; ++k)
+            umma_f16_lohi(tmem_base, sa_lo + k * kstep_lo, hi, xb_lo + k * kstep_x, hi_x, idesc_run, first | (uint32_t)k);
+        } else {
         for (int t = 0; t < ntap; ++t) {
           const uint32_t xb_lo = sb_lo + (p.halo ? (uint32_t)p.tap_xoff[tap0 + t] >> 4 : (uint32_t)(t * nboxes_b) * (BOX_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; ++k)      // 16 pixel rows (2 groups of 8) per instruction
             umma_f16_lohi(tmem_base + t * p.mma_n, sa_lo + k * kstep_lo, hi, xb_lo + k * kstep_x, hi_x, idesc, first | (uint32_t)k);
+        }
         }
         if (do_bias) {
 #pragma unroll
@@ -227,26 +237,48 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   // the accumulators (taps * mma_n fp32 columns) must fit the 512 TMEM columns
   p.mma_n = p.block_n;
   if (p.n_tiles == 1 && cin < p.block_n) p.mma_n = (cin + 15) / 16 * 16;     // narrow inputs (conv1 space-to-depth: 16)
-  // halo variant (stride-1 multi-tap layers; opt-in with SSNB_WGRAD_HALO=1 -- correct, but measured SLOWER than per-tap
-  // boxes on B200: 3.7 vs 2.9 ms over the 69 layers; the kernel is bound by shared-memory reads of the dz tile, which
-  // every N=64..128 MMA repeats, not by staging traffic): ONE x box per 64 input channels covers the
-  // 64-pixel tile plus the filter border ([y][frame][x] pixel order, as in umma_conv_v2.cu) and every tap is a shifted
-  // descriptor view into it, so the taps a CTA can take are limited by TMEM columns only and x is staged once, not per tap
+  // halo variant (stride-1 multi-tap layers): ONE x box per 64 input channels covers the 64-pixel tile plus the filter
+  // border ([y][frame][x] pixel order, as in umma_conv_v2.cu) and every tap is a shifted descriptor view into it.
+  // Default: only where a whole ROW of taps can then be taken by a single MMA -- 64-channel layers, whose tap views are
+  // equally spaced, so they are consecutive 64-channel N atoms with LBO = the tap spacing (128 B for a 3x3 row, 1 KiB
+  // for conv1's four vertical taps).  That reads the 4 KiB dz tile once per K step instead of once per tap, which is
+  // what bounds this kernel (shared-memory bandwidth): conv2_3x3 283 -> 163 us, conv1 254 -> 148 us.  Without the
+  // fusion the halo layout is SLOWER than per-tap boxes (more taps per CTA, same dz re-reads: 3.7 vs 2.9 ms over the
+  // 69 layers), so wider layers keep the classic layout.  SSNB_WGRAD_HALO=0 off, 1 halo everywhere without fusion,
+  // 2 halo everywhere + fusion where possible.
   int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
   for (int t = 0; t < ntaps; ++t) { x0 = std::min(x0, tdx[t]); x1 = std::max(x1, tdx[t]); y0 = std::min(y0, tdy[t]); y1 = std::max(y1, tdy[t]); }
   const char* he = getenv("SSNB_WGRAD_HALO");
-  bool halo = (he && he[0] == '1') && x_stride == 1 && ntaps > 1 && dz.W >= 7;
+  const int hmode = he ? atoi(he) : 3;                  // 3 = default: halo only with run fusion
+  bool halo = hmode != 0 && x_stride == 1 && ntaps > 1 && dz.W >= 7;
+  int run_len = 1, run_stride = 0;
+  if (halo && hmode >= 2 && p.block_n == 64 && p.mma_n == 64) {
+    const int pw0 = 8 + (x1 - x0);
+    int hb = 8; while (hb > 1 && dz.H % hb) hb >>= 1;
+    const int hf = 64 / (8 * hb);
+    auto off = [&](int t) { return ((tdy[t] - y0) * hf * pw0 + (tdx[t] - x0)) * 128; };
+    for (int r = 4; r >= 2; --r) {                      // longest run length (N = r*64 <= 256) that tiles the tap list evenly
+      if (ntaps % r) continue;
+      bool ok = true;
+      const int st = off(1) - off(0);
+      for (int g = 0; g < ntaps / r && ok; ++g)
+        for (int i = 1; i < r && ok; ++i) ok = off(g * r + i) - off(g * r + i - 1) == st;
+      if (ok && st > 0 && st % 16 == 0) { run_len = r; run_stride = st; break; }
+    }
+  }
+  if (hmode == 3 && run_len == 1) halo = false;
   int hbw = 8, hbh = 8, hbf = 1, pw = 8, x_box = 0, h_taps = 1, h_stages = 0;
   if (halo) {
     while (hbh > 1 && dz.H % hbh) hbh >>= 1;
     hbf = 64 / (hbw * hbh);
     pw = hbw + (x1 - x0);
     x_box = (pw * hbf * (hbh + (y1 - y0)) * 128 + 1023) / 1024 * 1024;
-    h_taps = std::min(ntaps, (512 - 16) / p.mma_n);
+    h_taps = run_len > 1 ? run_len : std::min(ntaps, (512 - 16) / p.mma_n);
     h_stages = std::min(MAX_STAGES, PIPE_BYTES / (A_BYTES + (p.block_n / 64) * x_box));
     if (h_taps < 2 || h_stages < 3) halo = false;
   }
   p.halo = halo ? 1 : 0;
+  p.run_len = halo ? run_len : 1; p.run_stride = run_stride;
   if (halo) {
     p.bw = hbw; p.bh = hbh; p.bf = hbf;
     p.tiles_w = (dz.W + hbw - 1) / hbw; p.tiles_h = dz.H / hbh; p.tiles_f = (F + hbf - 1) / hbf;
