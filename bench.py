@@ -36,23 +36,53 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every ~5 ms; nvidia-smi as a fallback)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]          # nvmlClocksEventReason*: HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
 
     def __init__(self, index):
-        self.rows, self.stop_flag, self.index = [], False, index
+        self.rows, self.stop_flag, self.index = [], False, index      # rows: (sm_mhz, max_mhz, [reason flags])
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.rows.append((float(sm), float(mx), [bool(r & b) for b in self.BITS]))
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [t.strip() for t in out.split(",")]
+        if len(c) >= 6:
+            self.rows.append((float(c[0]), float(c[1]), [t.lower().startswith("active") for t in c[2:6]]))
 
     def _run(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.005 if self.nvml else 0.1)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -64,12 +94,11 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def usable_cores():
@@ -175,7 +204,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SSNB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: whatever NCCL_DEBUG level the environment asks for goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ssnb_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     prec = _lib.FAST_FP16 if args.precision == "fast" else _lib.EXACT_FP32
