@@ -129,6 +129,8 @@ __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint3
   stg256(dst, q);
 }
 
+// register budget: 10 warps on 4 sub-partitions = 3 warps on one of them, 16384 / (3 * 32) = 170 -> ptxas caps at 168
+// (a __maxnreg__(200) build compiles but cannot launch); two prefetch buffers fit, three spill
 template <bool PAIR, int NTAPS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
@@ -321,8 +323,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (vb) q.yb = ldg256_nc(mrow + colb);
         }
       };
-      Pre cur = {};
-      if (cpar * 32 < ncol) prefetch(cpar * 32, cur);
+      Pre pp[2] = {};                                                // ping-pong (indices are compile-time after unrolling): no register copies
+      if (cpar * 32 < ncol) prefetch(cpar * 32, pp[0]);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -333,36 +335,41 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      for (int c0 = cpar * 32; c0 < ncol; c0 += 64) {
-        const bool two = c0 + 16 < p.block_n;                       // warp-uniform
-        const int cola = n0 + c0, colb = cola + 16;
-        const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
-        __half* da = (cola < p.n_split ? orow : orow2) + cola;
-        __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
-        Pre nxt = {};
-        if (c0 + 64 < ncol) prefetch(c0 + 64, nxt);
-        float4 ba[4], bb[4];
-        if (p.bias) {
+      for (int cbase = cpar * 32; cbase < ncol; cbase += 128) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
-            bb[j] = *reinterpret_cast<const float4*>(bias_s + (two ? colb : cola) + 4 * j);
+        for (int u = 0; u < 2; ++u) {
+          const int c0 = cbase + 64 * u;
+          if (c0 < ncol) {
+            // one 32-column group: prefetch the next group's operands, then TMEM -> registers -> epilogue math
+            const bool two = c0 + 16 < p.block_n;                   // warp-uniform
+            const int cola = n0 + c0, colb = cola + 16;
+            const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
+            __half* da = (cola < p.n_split ? orow : orow2) + cola;
+            __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
+            if (c0 + 64 < ncol) prefetch(c0 + 64, pp[u ^ 1]);
+            float4 ba[4], bb[4];
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
+                bb[j] = *reinterpret_cast<const float4*>(bias_s + (two ? colb : cola) + 4 * j);
+              }
+            }
+            uint32_t ra[16], rb[16];
+            tmem_ld16(taddr + c0, ra);
+            if (two) tmem_ld16(taddr + c0 + 16, rb);
+            tmem_ld_wait();
+            if (c0 + 64 >= p.block_n) {                             // last TMEM read of this tile: hand the accumulator back early
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
+            if (va) store_chunk(p, ra, ba, da, pp[u].oa, pp[u].ya);
+            if (vb) store_chunk(p, rb, bb, db2, pp[u].ob, pp[u].yb);
           }
         }
-        uint32_t ra[16], rb[16];
-        tmem_ld16(taddr + c0, ra);
-        if (two) tmem_ld16(taddr + c0 + 16, rb);
-        tmem_ld_wait();
-        if (c0 + 64 >= p.block_n) {                                 // last TMEM read of this tile: hand the accumulator back early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
-          }
-        }
-        if (va) store_chunk(p, ra, ba, da, cur.oa, cur.ya);
-        if (vb) store_chunk(p, rb, bb, db2, cur.ob, cur.yb);
-        cur = nxt;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -379,12 +386,14 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 template <bool PAIR, int NTAPS>
 int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, cudaStream_t s) {
-  static bool attr_set = false;
+  static bool attr_set[64] = {};          // function attributes are per device
   auto kern = umma_conv_v2_kernel<PAIR, NTAPS>;
-  if (!attr_set) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       set_thread_error("umma conv v2: cannot raise dynamic shared memory limit"); cudaGetLastError(); return 2; }
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int total = p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_q;
   cudaLaunchConfig_t cfg = {};
