@@ -191,19 +191,22 @@ class SSN(torch.nn.Module):
         return [self.starting_segment, self.starting_segment + self.course_segment, self.num_segments]
 
     def train_forward(self, input, aug_scaling, target, reg_target, prop_type):
-        base_out = self.base_model(self._frames(input))
-        activity_ft, completeness_ft = self.stpp(base_out, aug_scaling, self._seg_split())
-        raw_act_fc = self.activity_fc(activity_ft)
-        raw_comp_fc = self.completeness_fc(completeness_ft)
+        # The row selections depend on prop_type only.  nonzero() synchronises host and device (its result size is
+        # data dependent), so it runs BEFORE the backbone is enqueued: the host then stays ahead of the GPU for the
+        # whole step instead of stalling behind the backbone forward and leaving the GPU idle while it catches up.
         type_data = prop_type.view(-1).data
         # .view(-1) instead of the reference's .squeeze(): identical for >1 selected row and keeps
         # the row dimension when exactly one row matches.
         act_indexer = ((type_data == 0) | (type_data == 2)).nonzero().view(-1)
         comp_indexer = ((type_data == 0) | (type_data == 1)).nonzero().view(-1)
+        reg_indexer = (type_data == 0).nonzero().view(-1) if self.with_regression else None
+        base_out = self.base_model(self._frames(input))
+        activity_ft, completeness_ft = self.stpp(base_out, aug_scaling, self._seg_split())
+        raw_act_fc = self.activity_fc(activity_ft)
+        raw_comp_fc = self.completeness_fc(completeness_ft)
         target = target.view(-1)
         if self.with_regression:
             reg_target = reg_target.view(-1, 2)
-            reg_indexer = (type_data == 0).nonzero().view(-1)
             raw_regress_fc = self.regressor_fc(completeness_ft).view(-1, self.completeness_fc.out_features, 2)
             return raw_act_fc[act_indexer, :], target[act_indexer], \
                 raw_comp_fc[comp_indexer, :], target[comp_indexer], \
