@@ -1,6 +1,8 @@
 // FAST-mode (fp16 NHWC) memory-bound glue, vectorised: every thread moves 8 channels (16 bytes) so a
 // warp covers 256 contiguous channels / 512 bytes per pixel row.  Same semantics as the generic
 // kernels in simt_glue.cu (Caffe ceil-mode pooling, layer_factory.py:41-53; first-max-wins argmax).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ssnb {
@@ -188,6 +190,69 @@ __global__ void avgpool3_h8(const __half* __restrict__ src, int H, int W, int C,
     *reinterpret_cast<uint4*>(o) = pack8(s);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { prev[j] = cur[j]; cur[j] = nxt[j]; }
+  }
+}
+
+// EXPERIMENTAL (SSNB_AVGPOOL=pair; not yet validated on a GPU -- the round-1 budget was spent): two adjacent columns
+// per thread share the loads, the fp16->fp32 conversions and the middle partial sum b + c, ~65 instead of ~100
+// instructions per output (the kernel is issue-bound).  Sums associate as a + (b + c) instead of (a + b) + c.
+__global__ void avgpool3_pair_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
+                                 __half* __restrict__ dst, int dpitch, int dcoff, int F, int accumulate) {
+  const int G = C / 8, W2 = (W + 1) / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)F * W2 * G) return;
+  const unsigned iu = (unsigned)i;
+  const int g = (int)(iu % (unsigned)G);
+  const int x = 2 * (int)((iu / (unsigned)G) % (unsigned)W2);
+  const long long f = iu / (unsigned)(G * W2);
+  const bool has1 = x + 1 < W;                       // second column of the pair exists
+  float p0[8], c0[8], n0[8], p1[8], c1[8], n1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { p0[j] = c0[j] = p1[j] = c1[j] = 0.f; }
+  auto rowsum = [&](int y, float* o0, float* o1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o0[j] = 0.f; o1[j] = 0.f; }
+    if (y >= H) return;
+    const __half* base = src + ((f * H + y) * W) * spitch + scoff + g * 8;
+    float a[8], b[8], c[8], d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = 0.f; c[j] = 0.f; d[j] = 0.f; }
+    if (x - 1 >= 0) unpack8(ldg16(base + (long long)(x - 1) * spitch), a);
+    unpack8(ldg16(base + (long long)x * spitch), b);
+    if (x + 1 < W) unpack8(ldg16(base + (long long)(x + 1) * spitch), c);
+    if (x + 2 < W) unpack8(ldg16(base + (long long)(x + 2) * spitch), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = b[j] + c[j];
+      o0[j] = a[j] + m;
+      o1[j] = m + d[j];
+    }
+  };
+  rowsum(0, c0, c1);
+  for (int y = 0; y < H; ++y) {
+    rowsum(y + 1, n0, n1);
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s0[j] = (p0[j] + c0[j] + n0[j]) * (1.0f / 9.0f);
+      s1[j] = (p1[j] + c1[j] + n1[j]) * (1.0f / 9.0f);
+    }
+    __half* o = dst + ((f * H + y) * W + x) * dpitch + dcoff + g * 8;
+    if (accumulate) {
+      float old[8];
+      unpack8(*reinterpret_cast<const uint4*>(o), old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s0[j] += old[j];
+      if (has1) {
+        unpack8(*reinterpret_cast<const uint4*>(o + dpitch), old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] += old[j];
+      }
+    }
+    *reinterpret_cast<uint4*>(o) = pack8(s0);
+    if (has1) *reinterpret_cast<uint4*>(o + dpitch) = pack8(s1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { p0[j] = c0[j]; c0[j] = n0[j]; p1[j] = c1[j]; c1[j] = n1[j]; }
   }
 }
 
@@ -461,6 +526,13 @@ int launch_maxpool_bwd_h8(View dsrc, View ddst, int F, int k, int stride, int pa
   return 0;
 }
 int launch_avgpool3_h8(View src, View dst, int F, int accumulate, cudaStream_t s) {
+  static const bool pair = [] { const char* e = getenv("SSNB_AVGPOOL"); return e && e[0] == 'p'; }();     // experimental variant
+  if (pair) {
+    const long long n2 = (long long)F * ((src.W + 1) / 2) * (src.C / 8);
+    avgpool3_pair_h8<<<nblk(n2, 128), 128, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
+    SSNB_LAUNCH_CHECK("avgpool3_pair_h8");
+    return 0;
+  }
   const long long n = (long long)F * src.W * (src.C / 8);
   avgpool3_h8<<<nblk(n, 128), 128, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.pitch, dst.coff, F, accumulate);
   SSNB_LAUNCH_CHECK("avgpool3_h8");

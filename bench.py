@@ -401,6 +401,57 @@ def main():
                 "family_average": {"launches_timed": n_l, "achieved": fam, "frac": fam / peak,
                                    "note": "all %d stride-1 forward launches of the kernel, sum(flop)/sum(time)" % n_l}}
 
+    # ---- STPP bandwidth (the second half of BASELINE.json's metric): the fused global-pool + STPP kernel at the bench
+    #      shape (28.9 MB of fp16 activations: launch-latency bound) and the standalone STPP kernel at a
+    #      size where HBM bandwidth is the bound.  Reported beside the headline; a failure here never costs the bench line.
+    stpp_info = None
+    if rank == 0:
+        try:
+            import ctypes as C
+            hbm = float(peaks.get("hbm_gbs", 6650.0))
+            eng = model.base_model.engine_for(VIDEOS_PER_GPU * PROPS * SEG, True, dev)
+            n_prop = VIDEOS_PER_GPU * PROPS
+            lo, hi, nm, col = model.stpp.part_table([2, 7, 9])
+            feat = torch.empty(n_prop * SEG, 1024, device=dev)
+            course = torch.empty(n_prop, 1024, device=dev)
+            pooled = torch.empty(n_prop, len(lo) * 1024, device=dev)
+            sc = torch.rand(n_prop, 2, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e9
+            for _ in range(5):
+                l2_flush.zero_()
+                a.record()
+                rc = _lib.lib.ssnb_gpool_stpp_fwd(eng.h, None, C.c_void_p(sc.data_ptr()), SEG, len(lo), _lib.int_array(lo), _lib.int_array(hi),
+                                                  _lib.int_array(nm), _lib.int_array(col), 2, 7, C.c_void_p(feat.data_ptr()),
+                                                  C.c_void_p(course.data_ptr()), C.c_void_p(pooled.data_ptr()), stream)
+                b.record(); b.synchronize()
+                if rc != 0:
+                    raise RuntimeError("ssnb_gpool_stpp_fwd rc=%d" % rc)
+                best = min(best, a.elapsed_time(b))
+            fused_bytes = n_prop * SEG * 49 * 1024 * 2 + feat.numel() * 4 + course.numel() * 4 + pooled.numel() * 4
+            big_n = 16384                                   # 16384 proposals x 9 segments x 1024 fp32 = 0.6 GB in, 0.4 GB out
+            ft = torch.randn(big_n * SEG, 1024, device=dev)
+            scb = torch.rand(big_n, 2, device=dev)
+            big_best = 1e9
+            for _ in range(4):
+                l2_flush.zero_()
+                a.record()
+                ca, cc = model.stpp(ft, scb, [2, 7, 9])
+                b.record(); b.synchronize()
+                big_best = min(big_best, a.elapsed_time(b))
+            big_bytes = ft.numel() * 4 + scb.numel() * 4 + ca.numel() * 4 + cc.numel() * 4
+            stpp_info = {"fused_gpool_stpp": {"proposals": n_prop, "bytes": int(fused_bytes), "us": best * 1e3,
+                                              "GB/s": fused_bytes / (best / 1e3) / 1e9, "frac_of_hbm_peak": fused_bytes / (best / 1e3) / 1e9 / hbm,
+                                              "note": "bench shape; launch-latency bound at this size"},
+                         "stpp_fwd_large": {"proposals": big_n, "bytes": int(big_bytes), "us": big_best * 1e3,
+                                            "GB/s": big_bytes / (big_best / 1e3) / 1e9, "frac_of_hbm_peak": big_bytes / (big_best / 1e3) / 1e9 / hbm,
+                                            "note": "StructuredTemporalPyramidPooling.forward, fp32, algorithmic bytes (61,448 B/proposal)"},
+                         "hbm_peak_GB/s": hbm}
+            del ft, scb, ca, cc
+        except Exception as ex:                             # never lose the headline over the side measurement
+            stpp_info = {"error": repr(ex)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(1, 1)
@@ -420,7 +471,7 @@ def main():
                 "losses": [float(v) for v in losses.tolist()],
                 "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                         "steps": e2e_steps, "path": "SSN.forward + CrossEntropy/CompletenessLoss/ClassWiseRegressionLoss + backward + SGD from pinned host tensors, H2D double-buffered on a copy stream, loss.item() every step"},
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "stpp": stpp_info, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         # all ranks leave together; skip NCCL/graph teardown (it can block when a captured graph holds the
