@@ -429,7 +429,7 @@ def main():
                 if rc != 0:
                     raise RuntimeError("ssnb_gpool_stpp_fwd rc=%d" % rc)
                 best = min(best, a.elapsed_time(b))
-            fused_bytes = n_prop * SEG * 49 * 1024 * 2 + feat.numel() * 4 + course.numel() * 4 + pooled.numel() * 4
+            fused_bytes = n_prop * SEG * 49 * 1024 * (2 if prec == _lib.FAST_FP16 else 4) + feat.numel() * 4 + course.numel() * 4 + pooled.numel() * 4
             big_n = 16384                                   # 16384 proposals x 9 segments x 1024 fp32 = 0.6 GB in, 0.4 GB out
             ft = torch.randn(big_n * SEG, 1024, device=dev)
             scb = torch.rand(big_n, 2, device=dev)
