@@ -94,12 +94,13 @@ __device__ __forceinline__ void stg256(void* p, const U8& a) {
 }
 
 // one 16-column chunk of an accumulator row: bias / accumulate / ReLU / ReLU-gradient mask, fp16 store (32 bytes)
+template <bool HAS_BIAS>
 __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, const float4* bias, __half* dst, const U8& old,
                                             const U8& y) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias) {
+  if (HAS_BIAS && p.bias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { v[4 * j] += bias[j].x; v[4 * j + 1] += bias[j].y; v[4 * j + 2] += bias[j].z; v[4 * j + 3] += bias[j].w; }
   }
@@ -110,7 +111,7 @@ __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint3
       v[2 * j] += a.x; v[2 * j + 1] += a.y;
     }
   }
-  if (p.relu) {
+  if (HAS_BIAS && p.relu) {                  // (bias and ReLU are the forward epilogue)
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
   }
@@ -131,7 +132,7 @@ __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint3
 
 // register budget: 10 warps on 4 sub-partitions = 3 warps on one of them, 16384 / (3 * 32) = 170 -> ptxas caps at 168
 // (a __maxnreg__(200) build compiles but cannot launch); two prefetch buffers fit, three spill
-template <bool PAIR, int NTAPS>
+template <bool PAIR, int NTAPS, bool DG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ UmmaConvParams p) {
@@ -323,8 +324,12 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (vb) q.yb = ldg256_nc(mrow + colb);
         }
       };
-      Pre pp[2] = {};                                                // ping-pong (indices are compile-time after unrolling): no register copies
+      // DG (data-gradient specialisation, no bias table / ReLU code): three rotating buffers = two groups in flight;
+      // otherwise two (the bias registers of the forward path leave no room for a third under the 168-register cap)
+      constexpr int NB = DG ? 3 : 2;
+      Pre pp[NB] = {};                                               // indices are compile-time after unrolling: no register copies
       if (cpar * 32 < ncol) prefetch(cpar * 32, pp[0]);
+      if (NB == 3 && cpar * 32 + 64 < ncol) prefetch(cpar * 32 + 64, pp[1]);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -335,20 +340,20 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
         }
       }
-      for (int cbase = cpar * 32; cbase < ncol; cbase += 128) {
+      for (int cbase = cpar * 32; cbase < ncol; cbase += 64 * NB) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < NB; ++u) {
           const int c0 = cbase + 64 * u;
           if (c0 < ncol) {
-            // one 32-column group: prefetch the next group's operands, then TMEM -> registers -> epilogue math
+            // one 32-column group: prefetch the operands of a later group, then TMEM -> registers -> epilogue math
             const bool two = c0 + 16 < p.block_n;                   // warp-uniform
             const int cola = n0 + c0, colb = cola + 16;
             const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
             __half* da = (cola < p.n_split ? orow : orow2) + cola;
             __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
-            if (c0 + 64 < ncol) prefetch(c0 + 64, pp[u ^ 1]);
+            if (c0 + 64 * (NB - 1) < ncol) prefetch(c0 + 64 * (NB - 1), pp[(u + NB - 1) % NB]);
             float4 ba[4], bb[4];
-            if (p.bias) {
+            if (!DG && p.bias) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
@@ -366,8 +371,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
               }
             }
-            if (va) store_chunk(p, ra, ba, da, pp[u].oa, pp[u].ya);
-            if (vb) store_chunk(p, rb, bb, db2, pp[u].ob, pp[u].yb);
+            if (va) store_chunk<!DG>(p, ra, ba, da, pp[u].oa, pp[u].ya);
+            if (vb) store_chunk<!DG>(p, rb, bb, db2, pp[u].ob, pp[u].yb);
           }
         }
       }
@@ -384,10 +389,10 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <bool PAIR, int NTAPS>
+template <bool PAIR, int NTAPS, bool DG>
 int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, cudaStream_t s) {
   static bool attr_set[64] = {};          // function attributes are per device
-  auto kern = umma_conv_v2_kernel<PAIR, NTAPS>;
+  auto kern = umma_conv_v2_kernel<PAIR, NTAPS, DG>;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -415,21 +420,25 @@ int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, c
   return 0;
 }
 
+template <bool PAIR, bool DG>
+int launch_taps(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, cudaStream_t s) {
+  if (p.ntaps == 1) return launch_one<PAIR, 1, DG>(plan, p, num_sms, s);
+  if (p.ntaps == 4) return launch_one<PAIR, 4, DG>(plan, p, num_sms, s);
+  return launch_one<PAIR, 9, DG>(plan, p, num_sms, s);
+}
+
 }  // namespace
 
 bool umma_conv_v2_supported(int ntaps) { return ntaps == 1 || ntaps == 4 || ntaps == 9; }
 
 int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s) {
+  // SSNB_EPI_DEEP=1 (experimental, not yet validated on a GPU): data gradients whose epilogue reads global operands run
+  // the DG specialisation (no bias / ReLU code, three prefetch buffers)
+  static const bool deep = [] { const char* e = getenv("SSNB_EPI_DEEP"); return e && e[0] == '1'; }();
+  const bool dg = deep && !p.bias && !p.relu && (p.accumulate || p.mask_y);
   int rc;
-  if (p.pair) {
-    if (p.ntaps == 1) rc = launch_one<true, 1>(plan, p, ctx.num_sms, s);
-    else if (p.ntaps == 4) rc = launch_one<true, 4>(plan, p, ctx.num_sms, s);
-    else rc = launch_one<true, 9>(plan, p, ctx.num_sms, s);
-  } else {
-    if (p.ntaps == 1) rc = launch_one<false, 1>(plan, p, ctx.num_sms, s);
-    else if (p.ntaps == 4) rc = launch_one<false, 4>(plan, p, ctx.num_sms, s);
-    else rc = launch_one<false, 9>(plan, p, ctx.num_sms, s);
-  }
+  if (p.pair) rc = dg ? launch_taps<true, true>(plan, p, ctx.num_sms, s) : launch_taps<true, false>(plan, p, ctx.num_sms, s);
+  else rc = dg ? launch_taps<false, true>(plan, p, ctx.num_sms, s) : launch_taps<false, false>(plan, p, ctx.num_sms, s);
   if (rc) return rc;
   SSNB_LAUNCH_CHECK("umma_conv_v2_kernel");
   return 0;
