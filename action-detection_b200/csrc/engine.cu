@@ -594,7 +594,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       else if (c.kind == OP_CONV && (c.fuse_role == 1 ? h->fused[c.fuse_block].enabled : (c.fuse_role == 0 && c.umma_dgrad.enabled))) {
         c.dgrad_masks = true;
         const View yv = h->view((int)v, false);
-        if (c.fuse_role == 1) umma_conv_set_mask(h->fused[c.fuse_block].dgrad, yv); else umma_conv_set_mask(c.umma_dgrad, yv);
+        if (c.fuse_role == 1) umma_conv_set_mask(h->umma_ctx, h->fused[c.fuse_block].dgrad, yv); else umma_conv_set_mask(h->umma_ctx, c.umma_dgrad, yv);
       }
     }
     for (Op& o : h->ops) {

@@ -403,7 +403,14 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   else pw = 16;
   const int bhh = bh + yh;
   if (loads > 4 || bhh > 256 || bf > 256) return 0;
-  const int pipe = UMMA_V2_PIPE_BYTES;
+  // experimental TMA-fed epilogue (SSNB_EPI_TMA=1) for data gradients: a ring of 3 x (old-gradient + activation chunk) at the
+  // top of the staging area; the operand rings get what is left
+  const char* te = getenv("SSNB_EPI_TMA");
+  const bool want_ring = te && te[0] == '1' && !p.bias && !p.relu;
+  constexpr int EPI_STAGE = 2 * 128 * 128, EPI_STAGES = 3;
+  int pipe = UMMA_V2_PIPE_BYTES - (want_ring ? EPI_STAGES * EPI_STAGE : 0);
+  bool ring = want_ring;
+retry_without_ring:
   const int b_rows = pair ? p.block_n / 2 : p.block_n;      // weight rows each CTA stages per (tap, K chunk)
   const int a_load_bytes = pw * bf * bhh * BLOCK_K * 2;
   const int a_stage = (loads * a_load_bytes + 1023) / 1024 * 1024;
@@ -417,12 +424,12 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   int a_stages, b_stages;
   if (p.ntaps == 1) {                                       // one box + one slab per step: equal ring depths
     a_stages = b_stages = std::min(V2_STAGES_MAX, pipe / (a_stage + b_stage));
-    if (a_stages < 3) return 0;
+    if (a_stages < 3) { if (ring) { ring = false; pipe = UMMA_V2_PIPE_BYTES; goto retry_without_ring; } return 0; }
   } else {
     a_stages = 3;
     if ((pipe - 3 * a_stage) / b_stage < 3) a_stages = 2;
     b_stages = (pipe - a_stages * a_stage) / b_stage;
-    if (b_stages < 2) return 0;                             // does not fit: stay on the first-generation kernel
+    if (b_stages < 2) { if (ring) { ring = false; pipe = UMMA_V2_PIPE_BYTES; goto retry_without_ring; } return 0; }   // does not fit: stay on the first-generation kernel
     if (b_stages > V2_STAGES_MAX) b_stages = V2_STAGES_MAX;
   }
   p.v2 = 1; p.b_taps = b_taps;
@@ -448,6 +455,19 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   if (int rc = encode_a(&plan.tmap_a, a, p.K1)) { plan.enabled = false; return rc; }
   if (p.kchunks_a1 != p.kchunks) { if (int rc = encode_a(&plan.tmap_a2, *a2, p.K - p.K1)) { plan.enabled = false; return rc; } }
   else plan.tmap_a2 = plan.tmap_a;
+  p.epi_stages = 0; p.epi_stage_bytes = 0; plan.epi_maps_ready = false; plan.epi_mask_ready = false;
+  if (ring) {                                               // experimental TMA-fed epilogue: [128 rows][64 ch] boxes of the output view
+    p.epi_stages = EPI_STAGES; p.epi_stage_bytes = EPI_STAGE;
+    plan.epi_box[0] = bw; plan.epi_box[1] = bf; plan.epi_box[2] = bh; plan.epi_F = F;
+    cuuint64_t od[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.OW, (cuuint64_t)F, (cuuint64_t)p.OH};
+    cuuint64_t os[3] = {(cuuint64_t)p.out_pitch * 2, (cuuint64_t)p.OH * p.OW * p.out_pitch * 2, (cuuint64_t)p.OW * p.out_pitch * 2};
+    cuuint32_t ob[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bf, (cuuint32_t)bh};
+    if (int rc = encode(ctx, &plan.tmap_old, 4, p.out + p.out_coff, od, os, ob)) { plan.enabled = false; return rc; }
+    plan.tmap_y = plan.tmap_old;
+    plan.epi_maps_ready = true;
+  } else {
+    plan.tmap_old = plan.tmap_a; plan.tmap_y = plan.tmap_a;  // valid descriptors, never dereferenced
+  }
   if (pair || b_taps > 1) {                                 // pair: each CTA stages half of the weight rows; v2: b_taps taps per stage
     cuuint64_t bd[3] = {plan.b_dims[0], plan.b_dims[1], plan.b_dims[2]};
     cuuint64_t bs[2] = {plan.b_strides[0], plan.b_strides[1]};
@@ -540,8 +560,15 @@ int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, V
   return try_halo(ctx, plan, a, F, k1 ? &dz2 : nullptr);
 }
 
-void umma_conv_set_mask(UmmaConvPlan& plan, View y) {
+void umma_conv_set_mask(UmmaContext& ctx, UmmaConvPlan& plan, View y) {
   plan.mask_y = reinterpret_cast<const __half*>(y.base); plan.mask_pitch = y.pitch; plan.mask_coff = y.coff;
+  plan.epi_mask_ready = false;
+  if (plan.epi_maps_ready) {                                 // experimental TMA-fed epilogue: the activation tiles come through TMA too
+    cuuint64_t d[4] = {(cuuint64_t)plan.p.Cout, (cuuint64_t)y.W, (cuuint64_t)plan.epi_F, (cuuint64_t)y.H};
+    cuuint64_t st[3] = {(cuuint64_t)y.pitch * 2, (cuuint64_t)y.H * y.W * y.pitch * 2, (cuuint64_t)y.W * y.pitch * 2};
+    cuuint32_t b[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)plan.epi_box[0], (cuuint32_t)plan.epi_box[1], (cuuint32_t)plan.epi_box[2]};
+    plan.epi_mask_ready = encode(ctx, &plan.tmap_y, 4, reinterpret_cast<__half*>(y.base) + y.coff, d, st, b) == 0;
+  }
 }
 
 int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s, bool mask) {

@@ -48,6 +48,7 @@ struct UmmaConvParams {
   int v2;                         // second-generation kernel (umma_conv_v2.cu): warp-uniform role loops, grouped weight stages
   int b_taps;                     // v2: taps per weight stage
   int tiles_q;                    // v2: frame groups (pair mode: PAIRS of frame groups) = last digit of the tile walk
+  int epi_stages, epi_stage_bytes;// v2, experimental TMA-fed epilogue: ring depth (0 = off) and stride (old + activation chunk)
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
   int a_loads, a_load_bytes;      // TMA loads per A stage (1: full halo box; >1: one box per horizontal shift)
   int halo_x0, halo_y0;           // box origin relative to the tile origin (min dx, min dy)
@@ -62,6 +63,9 @@ struct UmmaConvPlan {
   bool enabled = false;
   const __half* mask_y = nullptr; int mask_pitch = 0, mask_coff = 0;   // applied only when launched with mask=true
   CUtensorMap tmap_a, tmap_a2, tmap_b;
+  CUtensorMap tmap_old, tmap_y;   // experimental TMA-fed epilogue: output (old gradient) and mask-activation tiles, [128 rows][64 ch] boxes
+  bool epi_maps_ready = false, epi_mask_ready = false;
+  int epi_box[3] = {0, 0, 0}, epi_F = 0;     // box {W, F, H} extents and frame count for encoding tmap_y when the mask is attached
   // geometry of the weight map (kept so that a variant can re-encode it with another box)
   const __half* b_ptr = nullptr; unsigned long long b_dims[3] = {0, 0, 0}, b_strides[2] = {0, 0};
   UmmaConvParams p;
@@ -88,7 +92,7 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
 // second-generation kernel (umma_conv_v2.cu); `p` = plan.p with the per-launch fields (mask) already applied
 bool umma_conv_v2_supported(int ntaps);
 int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s);
-void umma_conv_set_mask(UmmaConvPlan& plan, View y);
+void umma_conv_set_mask(UmmaContext& ctx, UmmaConvPlan& plan, View y);
 
 // host helpers shared by the tensor-core kernels
 int umma_resolve_encode(UmmaContext& ctx);

@@ -31,6 +31,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int BAR_BYTES = 1024;
+constexpr int EPI_RING_MAX = 4;                   // stages of the TMA-fed epilogue ring
+constexpr int EPI_TENSOR_BYTES = 128 * 128;        // one [128 rows][64 fp16] chunk of the old gradient or of the activation
 constexpr int BIAS_MAX = 1024;                     // floats of folded-BN bias staged in shared memory (n_tiles * block_n)
 constexpr int SMEM_BYTES = UMMA_V2_PIPE_BYTES + 1024 /*align slack*/ + BAR_BYTES + BIAS_MAX * 4;
 
@@ -132,10 +134,17 @@ __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint3
 
 // register budget: 10 warps on 4 sub-partitions = 3 warps on one of them, 16384 / (3 * 32) = 170 -> ptxas caps at 168
 // (a __maxnreg__(200) build compiles but cannot launch); two prefetch buffers fit, three spill
-template <bool PAIR, int NTAPS, bool DG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EPI selects the epilogue: 0 default; 1 data-gradient specialisation (SSNB_EPI_DEEP=1: no bias / ReLU code, three
+// register prefetch buffers); 2 TMA-fed (SSNB_EPI_TMA=1: an eleventh warp streams the old-gradient / activation tiles
+// of every 64-column chunk into a shared-memory ring with TMA, the epilogue warps read them with conflict-free LDS
+// instead of scattered global loads).  Variants 1 and 2 are experimental: written in round 1 after the GPU budget was
+// spent, not yet run.  The default instantiations' SASS is unchanged by their presence (same instruction counts).
+template <bool PAIR, int NTAPS, int EPI>
+__global__ void __launch_bounds__(EPI == 2 ? NUM_THREADS + 32 : NUM_THREADS, 1)
 umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ UmmaConvParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_old,
+                    const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ UmmaConvParams p) {
+  constexpr bool DG = EPI == 1, TMAE = EPI == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
@@ -146,7 +155,9 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* b_empty = b_full + MAX_STAGES;
   uint64_t* tfull_bar = b_empty + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* e_full = tempty_bar + 2;               // [EPI_RING_MAX] TMA-fed epilogue ring (EPI == 2)
+  uint64_t* e_empty = e_full + EPI_RING_MAX;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_empty + EPI_RING_MAX);
 
   // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the loop
   // state inside them can live in uniform registers
@@ -161,13 +172,18 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // (a global __ldg there sat on the critical path right after the TMEM load: half of the epilogue's stall samples)
   float* bias_s = reinterpret_cast<float*>(smem + UMMA_V2_PIPE_BYTES + BAR_BYTES);
   if (p.bias)
-    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += NUM_THREADS) bias_s[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += (TMAE ? NUM_THREADS + 32 : NUM_THREADS)) bias_s[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * EPI_WARPS); }
+    if (TMAE) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_old)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_y)) : "memory");
+      for (int i = 0; i < EPI_RING_MAX; ++i) { mbar_init(&e_full[i], 1); mbar_init(&e_empty[i], EPI_WARPS); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -286,13 +302,15 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (!TMAE || warp < 2 + EPI_WARPS) {
     // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int cpar = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int rw = row % p.bw, rf = (row / p.bw) % p.bf, rh = row / (p.bw * p.bf);      // halo row order: x, frame, y
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t es = 0, eph = 0;                                       // TMA-fed epilogue ring position (EPI == 2)
+    const uint8_t* epi_ring = smem + UMMA_V2_PIPE_BYTES - p.epi_stages * p.epi_stage_bytes;
     TileIter it; it.init(p, first, step);
     // every thread stores its own accumulator row, 32 bytes per 16 columns; the two warps of a quadrant alternate
     // 32-column groups.  (A shared-memory transposed, fully coalesced variant was measured slower -- 13.6 vs 12.3 ms per
@@ -324,42 +342,41 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (vb) q.yb = ldg256_nc(mrow + colb);
         }
       };
-      // DG (data-gradient specialisation, no bias table / ReLU code): three rotating buffers = two groups in flight;
-      // otherwise two (the bias registers of the forward path leave no room for a third under the 168-register cap)
-      constexpr int NB = DG ? 3 : 2;
-      Pre pp[NB] = {};                                               // indices are compile-time after unrolling: no register copies
-      if (cpar * 32 < ncol) prefetch(cpar * 32, pp[0]);
-      if (NB == 3 && cpar * 32 + 64 < ncol) prefetch(cpar * 32 + 64, pp[1]);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
-      if (cpar * 32 >= ncol) {                                      // narrow tile: this warp has no columns, release at once
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+      if (TMAE) {
+        // ---- TMA-fed: the operands of 64-column chunk i of this tile are in ring stage `es` (old gradient at +0, activation
+        //      at +16 KiB, rows in TMEM lane order, 128-byte rows with the TMA 128-byte swizzle) ----
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+        if (cpar * 32 >= ncol) {                                    // narrow tile: this warp has no columns, release at once
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+          }
         }
-      }
-      for (int cbase = cpar * 32; cbase < ncol; cbase += 64 * NB) {
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-          const int c0 = cbase + 64 * u;
+        const int nchunks = (p.block_n + 63) / 64;
+        for (int i = 0; i < nchunks; ++i) {
+          const int c0 = i * 64 + cpar * 32;
+          mbar_wait(&e_full[es], eph);
+          const uint8_t* st = epi_ring + es * p.epi_stage_bytes + row * 128;
+          const int sw = row & 7, j0 = cpar * 4;                    // 16-byte chunk index of this warp's first column inside the 64
+          U8 oa = {}, ob = {}, ya = {}, yb = {};
+          auto lds32 = [&](const uint8_t* base, int j, U8& q) {     // 16 columns = two swizzled 16-byte chunks
+            const uint4 lo = *reinterpret_cast<const uint4*>(base + ((j ^ sw) << 4));
+            const uint4 hi = *reinterpret_cast<const uint4*>(base + (((j + 1) ^ sw) << 4));
+            q.v[0] = lo.x; q.v[1] = lo.y; q.v[2] = lo.z; q.v[3] = lo.w; q.v[4] = hi.x; q.v[5] = hi.y; q.v[6] = hi.z; q.v[7] = hi.w;
+          };
+          if (p.accumulate) { lds32(st, j0, oa); lds32(st, j0 + 2, ob); }
+          if (mrow) { lds32(st + EPI_TENSOR_BYTES, j0, ya); lds32(st + EPI_TENSOR_BYTES, j0 + 2, yb); }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&e_empty[es]);                 // release semantics order the shared loads above before it
+          if (++es == (uint32_t)p.epi_stages) { es = 0; eph ^= 1; }
           if (c0 < ncol) {
-            // one 32-column group: prefetch the operands of a later group, then TMEM -> registers -> epilogue math
             const bool two = c0 + 16 < p.block_n;                   // warp-uniform
             const int cola = n0 + c0, colb = cola + 16;
             const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
-            __half* da = (cola < p.n_split ? orow : orow2) + cola;
-            __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
-            if (c0 + 64 * (NB - 1) < ncol) prefetch(c0 + 64 * (NB - 1), pp[(u + NB - 1) % NB]);
-            float4 ba[4], bb[4];
-            if (!DG && p.bias) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
-                bb[j] = *reinterpret_cast<const float4*>(bias_s + (two ? colb : cola) + 4 * j);
-              }
-            }
+            float4 ba[4] = {}, bb[4] = {};
             uint32_t ra[16], rb[16];
             tmem_ld16(taddr + c0, ra);
             if (two) tmem_ld16(taddr + c0 + 16, rb);
@@ -371,12 +388,92 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
               }
             }
-            if (va) store_chunk<!DG>(p, ra, ba, da, pp[u].oa, pp[u].ya);
-            if (vb) store_chunk<!DG>(p, rb, bb, db2, pp[u].ob, pp[u].yb);
+            if (va) store_chunk<false>(p, ra, ba, orow + cola, oa, ya);
+            if (vb) store_chunk<false>(p, rb, bb, orow + colb, ob, yb);
+          }
+        }
+      } else {
+        // DG (data-gradient specialisation, no bias table / ReLU code): three rotating buffers = two groups in flight;
+        // otherwise two (the bias registers of the forward path leave no room for a third under the 168-register cap)
+        constexpr int NB = DG ? 3 : 2;
+        Pre pp[NB] = {};                                               // indices are compile-time after unrolling: no register copies
+        if (cpar * 32 < ncol) prefetch(cpar * 32, pp[0]);
+        if (NB == 3 && cpar * 32 + 64 < ncol) prefetch(cpar * 32 + 64, pp[1]);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+        if (cpar * 32 >= ncol) {                                      // narrow tile: this warp has no columns, release at once
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+        for (int cbase = cpar * 32; cbase < ncol; cbase += 64 * NB) {
+  #pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            const int c0 = cbase + 64 * u;
+            if (c0 < ncol) {
+              // one 32-column group: prefetch the operands of a later group, then TMEM -> registers -> epilogue math
+              const bool two = c0 + 16 < p.block_n;                   // warp-uniform
+              const int cola = n0 + c0, colb = cola + 16;
+              const bool va = valid && cola < p.Cout, vb = two && valid && colb < p.Cout;
+              __half* da = (cola < p.n_split ? orow : orow2) + cola;
+              __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
+              if (c0 + 64 * (NB - 1) < ncol) prefetch(c0 + 64 * (NB - 1), pp[(u + NB - 1) % NB]);
+              float4 ba[4], bb[4];
+              if (!DG && p.bias) {
+  #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
+                  bb[j] = *reinterpret_cast<const float4*>(bias_s + (two ? colb : cola) + 4 * j);
+                }
+              }
+              uint32_t ra[16], rb[16];
+              tmem_ld16(taddr + c0, ra);
+              if (two) tmem_ld16(taddr + c0 + 16, rb);
+              tmem_ld_wait();
+              if (c0 + 64 >= p.block_n) {                             // last TMEM read of this tile: hand the accumulator back early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+                }
+              }
+              if (va) store_chunk<!DG>(p, ra, ba, da, pp[u].oa, pp[u].ya);
+              if (vb) store_chunk<!DG>(p, rb, bb, db2, pp[u].ob, pp[u].yb);
+            }
           }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue loader (EPI == 2, warp 10): old-gradient / activation chunks of every tile, ring of p.epi_stages =====
+    const bool el = elect_one();
+    uint8_t* epi_ring = smem + UMMA_V2_PIPE_BYTES - p.epi_stages * p.epi_stage_bytes;
+    const uint32_t tx = (p.accumulate ? (uint32_t)EPI_TENSOR_BYTES : 0u) + (p.mask_y ? (uint32_t)EPI_TENSOR_BYTES : 0u);
+    const int nchunks = (p.block_n + 63) / 64;
+    uint32_t es = 0, eph = 0;
+    TileIter it; it.init(p, first, step);
+    for (; it.valid(p); it.next(p)) {
+      const int w0 = it.mw * p.bw, h0 = it.mh * p.bh;
+      const int f0 = (PAIR ? 2 * it.mq + (int)rank : it.mq) * p.bf;
+      const int n0 = it.nt * p.block_n;
+      for (int i = 0; i < nchunks; ++i) {
+        mbar_wait(&e_empty[es], eph ^ 1);
+        if (el) {
+          uint8_t* st = epi_ring + es * p.epi_stage_bytes;
+          if (tx) {
+            mbar_expect_tx(&e_full[es], tx);
+            if (p.accumulate) tma_load_4d(st, &tmap_old, &e_full[es], n0 + i * 64, w0, f0, h0);
+            if (p.mask_y) tma_load_4d(st + EPI_TENSOR_BYTES, &tmap_y, &e_full[es], n0 + i * 64, w0, f0, h0);
+          } else {
+            mbar_arrive(&e_full[es]);
+          }
+        }
+        if (++es == (uint32_t)p.epi_stages) { es = 0; eph ^= 1; }
+      }
     }
   }
 
@@ -389,10 +486,10 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <bool PAIR, int NTAPS, bool DG>
+template <bool PAIR, int NTAPS, int EPI>
 int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, cudaStream_t s) {
   static bool attr_set[64] = {};          // function attributes are per device
-  auto kern = umma_conv_v2_kernel<PAIR, NTAPS, DG>;
+  auto kern = umma_conv_v2_kernel<PAIR, NTAPS, EPI>;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -403,7 +500,7 @@ int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, c
   const int total = p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_q;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(EPI == 2 ? NUM_THREADS + 32 : NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = s;
   if (PAIR) {
@@ -415,16 +512,16 @@ int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, c
   } else {
     cfg.gridDim = dim3(std::min(total, num_sms));
   }
-  if (cudaLaunchKernelEx(&cfg, kern, plan.tmap_a, plan.tmap_a2, plan.tmap_b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, kern, plan.tmap_a, plan.tmap_a2, plan.tmap_b, plan.tmap_old, plan.tmap_y, p) != cudaSuccess) {
     set_thread_error(std::string("umma_conv_v2_kernel launch: ") + cudaGetErrorString(cudaGetLastError())); return 2; }
   return 0;
 }
 
-template <bool PAIR, bool DG>
+template <bool PAIR, int EPI>
 int launch_taps(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, cudaStream_t s) {
-  if (p.ntaps == 1) return launch_one<PAIR, 1, DG>(plan, p, num_sms, s);
-  if (p.ntaps == 4) return launch_one<PAIR, 4, DG>(plan, p, num_sms, s);
-  return launch_one<PAIR, 9, DG>(plan, p, num_sms, s);
+  if (p.ntaps == 1) return launch_one<PAIR, 1, EPI>(plan, p, num_sms, s);
+  if (p.ntaps == 4) return launch_one<PAIR, 4, EPI>(plan, p, num_sms, s);
+  return launch_one<PAIR, 9, EPI>(plan, p, num_sms, s);
 }
 
 }  // namespace
@@ -432,13 +529,14 @@ int launch_taps(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, 
 bool umma_conv_v2_supported(int ntaps) { return ntaps == 1 || ntaps == 4 || ntaps == 9; }
 
 int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s) {
-  // SSNB_EPI_DEEP=1 (experimental, not yet validated on a GPU): data gradients whose epilogue reads global operands run
-  // the DG specialisation (no bias / ReLU code, three prefetch buffers)
+  // experimental epilogues for data gradients whose epilogue reads global operands (old gradient / activation):
+  // SSNB_EPI_TMA=1 (plan bound with the ring: p.epi_stages > 0) or SSNB_EPI_DEEP=1
   static const bool deep = [] { const char* e = getenv("SSNB_EPI_DEEP"); return e && e[0] == '1'; }();
-  const bool dg = deep && !p.bias && !p.relu && (p.accumulate || p.mask_y);
+  const bool reads = !p.bias && !p.relu && (p.accumulate || p.mask_y);
+  const int epi = (reads && p.epi_stages > 0 && plan.epi_maps_ready && (!p.mask_y || plan.epi_mask_ready)) ? 2 : ((reads && deep) ? 1 : 0);
   int rc;
-  if (p.pair) rc = dg ? launch_taps<true, true>(plan, p, ctx.num_sms, s) : launch_taps<true, false>(plan, p, ctx.num_sms, s);
-  else rc = dg ? launch_taps<false, true>(plan, p, ctx.num_sms, s) : launch_taps<false, false>(plan, p, ctx.num_sms, s);
+  if (p.pair) rc = epi == 2 ? launch_taps<true, 2>(plan, p, ctx.num_sms, s) : (epi == 1 ? launch_taps<true, 1>(plan, p, ctx.num_sms, s) : launch_taps<true, 0>(plan, p, ctx.num_sms, s));
+  else rc = epi == 2 ? launch_taps<false, 2>(plan, p, ctx.num_sms, s) : (epi == 1 ? launch_taps<false, 1>(plan, p, ctx.num_sms, s) : launch_taps<false, 0>(plan, p, ctx.num_sms, s));
   if (rc) return rc;
   SSNB_LAUNCH_CHECK("umma_conv_v2_kernel");
   return 0;
