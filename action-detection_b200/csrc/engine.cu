@@ -116,6 +116,11 @@ struct ssnb_engine {
   std::string error;
   long long launches0 = 0;
   UmmaContext umma_ctx;
+  // experimental (SSNB_GRAPH=1, not yet run on a GPU): the library replays its own forward / backward launch sequences
+  // as CUDA graphs when the caller is not capturing itself (the eager, reference-facing module path)
+  cudaGraphExec_t fwd_exec = nullptr, bwd_exec = nullptr;
+  bool fwd_warm = false, bwd_warm = false;
+  unsigned long long bwd_key = 0;
 
   int fail(int code, const std::string& msg) { error = msg; return code; }
   View view(int val, bool grad) const {
@@ -317,6 +322,26 @@ static void plan(ssnb_engine* e) {
   e->ws_bytes = off;
 }
 
+static bool graphs_enabled() {
+  static const bool on = [] {
+    const char* g = getenv("SSNB_GRAPH");
+    const char* a = getenv("SSNB_PROFILE_FWD_OPS");
+    const char* b = getenv("SSNB_PROFILE_BWD_OPS");
+    return g && g[0] == '1' && !(a && *a) && !(b && *b);
+  }();
+  return on;
+}
+static bool stream_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return true; }    // unknown: stay eager
+  return st != cudaStreamCaptureStatusNone;
+}
+static void drop_graphs(ssnb_engine* e) {
+  if (e->fwd_exec) { cudaGraphExecDestroy(e->fwd_exec); e->fwd_exec = nullptr; }
+  if (e->bwd_exec) { cudaGraphExecDestroy(e->bwd_exec); e->bwd_exec = nullptr; }
+  e->fwd_warm = e->bwd_warm = false;
+}
+
 // ---- op execution --------------------------------------------------------------------------------
 #define DISPATCH(e, call_f, call_h) ((e)->fp16 ? (call_h) : (call_f))
 
@@ -487,6 +512,7 @@ int ssnb_create(const ssnb_config* cfg, ssnb_handle* out) {
 
 int ssnb_destroy(ssnb_handle h) {
   if (!h) return SSNB_OK;
+  drop_graphs(h);
   umma_context_destroy(h->umma_ctx);
   delete h;
   return SSNB_OK;
@@ -500,6 +526,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
   if (((uintptr_t)dev_ptr) % 1024) return h->fail(SSNB_EINVAL, "workspace must be 1024-byte aligned");
   h->ws = (char*)dev_ptr;
   h->weights_ready = false;
+  drop_graphs(h);                       // captured launches hold workspace addresses
   if (h->fp16 && cudaMemset(h->ws + h->bpartial_off, 0, 256) != cudaSuccess) { cudaGetLastError(); /* no device (CPU-only planning) */ }
   // bind tcgen05 plans (tensor maps need final addresses); SSNB_DISABLE_UMMA=1 keeps FAST mode on the SIMT kernels
   const char* dis = getenv("SSNB_DISABLE_UMMA");
@@ -667,14 +694,42 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
   else rc = h->fp16 ? launch_nchw_to_nhwc<__half>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s)
                     : launch_nchw_to_nhwc<float>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s);
   if (rc) { h->s2d_ready = false; return h->fail(rc, "input layout: " + ssnb::thread_error()); }
-  for (const Op& o : h->ops) {
-    if (o.fuse_role == 2) continue;                       // computed by its block's fused launch
-    const bool prof = profiled_op("SSNB_PROFILE_FWD_OPS", o.id);
-    if (prof) cudaProfilerStart();
-    if (o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].fwd, s);
-    else rc = run_fwd(h, o, input_nchw, feat, s);
-    if (prof) cudaProfilerStop();
-    if (rc) { h->s2d_ready = false; return h->fail(rc, "fwd " + o.id + ": " + ssnb::thread_error()); }
+  // every op except the last (global pool -> caller's feat) touches workspace memory only, so its launch sequence can be
+  // replayed as a graph; first call eager (lazy function attributes), second call captures, later calls replay
+  auto run_ops = [&](bool only_last, bool skip_last) -> int {
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+      const Op& o = h->ops[i];
+      const bool last = i + 1 == h->ops.size();
+      if ((only_last && !last) || (skip_last && last)) continue;
+      if (o.fuse_role == 2) continue;                       // computed by its block's fused launch
+      const bool prof = profiled_op("SSNB_PROFILE_FWD_OPS", o.id);
+      if (prof) cudaProfilerStart();
+      int r;
+      if (o.fuse_role == 1) r = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].fwd, s);
+      else r = run_fwd(h, o, input_nchw, feat, s);
+      if (prof) cudaProfilerStop();
+      if (r) { h->s2d_ready = false; return h->fail(r, "fwd " + o.id + ": " + ssnb::thread_error()); }
+    }
+    return 0;
+  };
+  const bool graph = graphs_enabled() && h->fwd_warm && h->ops.back().kind == OP_GPOOL && !stream_capturing(s);
+  if (!graph) {
+    if ((rc = run_ops(false, false))) return rc;
+    h->fwd_warm = true;
+  } else {
+    if (!h->fwd_exec) {
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->s2d_ready = false; return h->fail(SSNB_ECUDA, "fwd graph: begin capture"); }
+      rc = run_ops(false, true);
+      const cudaError_t ce = cudaStreamEndCapture(s, &g);
+      if (rc || ce != cudaSuccess || !g || cudaGraphInstantiate(&h->fwd_exec, g, 0) != cudaSuccess) {
+        cudaGetLastError(); if (g) cudaGraphDestroy(g); h->fwd_exec = nullptr; h->s2d_ready = false;
+        return h->fail(rc ? rc : SSNB_ECUDA, "fwd graph: capture/instantiate failed");
+      }
+      cudaGraphDestroy(g);
+    }
+    if (cudaGraphLaunch(h->fwd_exec, s) != cudaSuccess) { cudaGetLastError(); h->s2d_ready = false; return h->fail(SSNB_ECUDA, "fwd graph: launch"); }
+    if ((rc = run_ops(true, false))) return rc;
   }
   h->s2d_ready = false;
   return SSNB_OK;
@@ -694,17 +749,20 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   ssnb_bind_grads(h, dw, db);
   h->pending_finalize.clear();
   cudaStream_t s = (cudaStream_t)stream;
-  for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
-    const Op& o = h->ops[i];
-    const bool prof = profiled_op("SSNB_PROFILE_BWD_OPS", o.id);
-    if (prof) cudaProfilerStart();
-    int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
-    if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s, h->fold_pools && o.dgrad_masks);   // ... one fused data gradient
-    if (prof) cudaProfilerStop();
-    if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
-  }
-  // one (or two) launches reduce the split-K partials of every tensor-core weight gradient of this backward
-  {
+  // ops [first, last] of the reverse schedule; the global pool's backward (the first of them) reads the caller's dfeat
+  auto run_range = [&](int hi, int lo) -> int {
+    for (int i = hi; i >= lo; --i) {
+      const Op& o = h->ops[i];
+      const bool prof = profiled_op("SSNB_PROFILE_BWD_OPS", o.id);
+      if (prof) cudaProfilerStart();
+      int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
+      if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s, h->fold_pools && o.dgrad_masks);   // ... one fused data gradient
+      if (prof) cudaProfilerStop();
+      if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
+    }
+    return 0;
+  };
+  auto finalize = [&]() -> int {
     const float gs = h->fp16 ? h->cfg.grad_scale : 1.0f;
     FinalizeTable t; t.n = 0; t.total_blocks = 0;
     auto flush = [&]() -> int { int rc = launch_wgrad_finalize_all(t, 1.0f / gs, h->grad_accumulate, s); t.n = 0; t.total_blocks = 0; return rc; };
@@ -721,7 +779,38 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
     }
     h->pending_finalize.clear();
     if (int rc = flush()) return h->fail(rc, "finalize: " + ssnb::thread_error());
+    return 0;
+  };
+  const int last = (int)h->ops.size() - 1;
+  // the gradient pointers are baked into the captured launches: key the graph on them (and on the accumulate flag)
+  unsigned long long key = 1469598103934665603ull ^ (unsigned long long)h->grad_accumulate;
+  for (size_t i = 0; i < h->convs.size(); ++i) {
+    key = (key ^ (unsigned long long)(uintptr_t)(h->dw.size() ? h->dw[i] : nullptr)) * 1099511628211ull;
+    key = (key ^ (unsigned long long)(uintptr_t)(h->db.size() ? h->db[i] : nullptr)) * 1099511628211ull;
   }
+  const bool graph = graphs_enabled() && h->bwd_warm && h->ops[last].kind == OP_GPOOL && !stream_capturing(s);
+  if (!graph) {
+    if (int rc = run_range(last, 0)) return rc;
+    if (int rc = finalize()) return rc;
+    h->bwd_warm = true;
+    return SSNB_OK;
+  }
+  if (int rc = run_range(last, last)) return rc;                   // global-pool backward: reads dfeat, eager
+  if (h->bwd_exec && h->bwd_key != key) { cudaGraphExecDestroy(h->bwd_exec); h->bwd_exec = nullptr; }
+  if (!h->bwd_exec) {
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return h->fail(SSNB_ECUDA, "bwd graph: begin capture"); }
+    int rc = run_range(last - 1, 0);
+    if (!rc) rc = finalize();
+    const cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (rc || ce != cudaSuccess || !g || cudaGraphInstantiate(&h->bwd_exec, g, 0) != cudaSuccess) {
+      cudaGetLastError(); if (g) cudaGraphDestroy(g); h->bwd_exec = nullptr; h->pending_finalize.clear();
+      return h->fail(rc ? rc : SSNB_ECUDA, "bwd graph: capture/instantiate failed");
+    }
+    cudaGraphDestroy(g);
+    h->bwd_key = key;
+  }
+  if (cudaGraphLaunch(h->bwd_exec, s) != cudaSuccess) { cudaGetLastError(); return h->fail(SSNB_ECUDA, "bwd graph: launch"); }
   return SSNB_OK;
 }
 

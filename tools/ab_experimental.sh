@@ -12,5 +12,6 @@ run() {   # name, env assignments...
 run default SSNB_NOP=1
 run epi_deep SSNB_EPI_DEEP=1
 run epi_tma SSNB_EPI_TMA=1
+run lib_graph SSNB_GRAPH=1
 run avgpool_pair SSNB_AVGPOOL=pair
 run all SSNB_EPI_TMA=1 SSNB_AVGPOOL=pair
