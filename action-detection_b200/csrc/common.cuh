@@ -13,11 +13,24 @@ namespace ssnb {
 struct View {
   void* base = nullptr;
   int H = 0, W = 0, C = 0, pitch = 0, coff = 0;
+  // SSNB_EXACT_TC operand planes: `base` is the fp16 HI plane and the LO plane (x - float(hi), fp16) of the same
+  // geometry starts `lo_off` bytes after it; 0 = a plain single-plane view
+  long long lo_off = 0;
 };
 
 extern std::atomic<long long> g_launches;  // every kernel launch of this library bumps it
 void set_thread_error(const std::string& s);
 
+// Per-launch device timing (ssnb_timing_begin / ssnb_timing_report, bench.py's roofline): while a timing session is open
+// on this thread, every launch records a CUDA event behind itself on its stream; a launch's time is the distance to the
+// previous event (launches are back to back on one stream).  The engine tags the launches it is about to make with the
+// pass they belong to and the algorithmic FLOPs of the convolution they compute.
+struct LaunchTag { int phase = 3; double flop = 0.0; };      // phase: 0 forward, 1 data gradient, 2 weight gradient, 3 other
+extern thread_local bool t_timing;
+extern thread_local LaunchTag t_tag;
+void timing_mark(const char* what, cudaStream_t s);
+
+// every launcher names its stream `s`
 #define SSNB_LAUNCH_CHECK(what)                                                       \
   do {                                                                                \
     ssnb::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
@@ -26,6 +39,7 @@ void set_thread_error(const std::string& s);
       ssnb::set_thread_error(std::string(what) + ": " + cudaGetErrorString(_e));      \
       return 2;                                                                       \
     }                                                                                 \
+    if (ssnb::t_timing) ssnb::timing_mark(what, s);                                   \
   } while (0)
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
@@ -100,6 +114,14 @@ int launch_mask_bias_h8(View dy, View y, int F, const float* mult, float out_sca
                         int accumulate, cudaStream_t s);
 int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stride, int pad, const uint8_t* argmax,
                              const float* mult, float out_scale, float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
+// SSNB_EXACT_TC glue (tc_glue.cu): error-compensated fp16 operand planes of fp32 tensors.
+//   hi = fp16(x * scale), lo = fp16(x * scale - float(hi))  =>  hi + lo carries ~22 significand bits of x * scale
+// `flag` (device int, may be null) is set to 1 when |x * scale| exceeds the fp16 range (loss-scale overflow)
+int launch_split_view(View src_f32, int F, float scale, View planes, int* flag, cudaStream_t s);
+int launch_split_flat(const float* src, long long n, __half* hi, __half* lo, cudaStream_t s);
+int launch_planes_to_nchw(View planes, int F, float scale, float* dst, cudaStream_t s);
+int launch_nhwc_to_s2d_split(View src_f32, int F, __half* dst_hi, long long lo_off, int Cs, cudaStream_t s);
+int launch_nchw_to_s2d_split(const float* src, int F, int Cin, int H, int W, __half* dst_hi, long long lo_off, int Cs, cudaStream_t s);
 // FAST-mode layout helpers (s2d_glue.cu)
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s);

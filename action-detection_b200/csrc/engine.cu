@@ -23,6 +23,26 @@ static thread_local std::string t_error;
 void set_thread_error(const std::string& s) { t_error = s; }
 const std::string& thread_error() { return t_error; }
 
+// ---- per-launch timing session (see common.cuh) ---------------------------------------------------
+thread_local bool t_timing = false;
+thread_local LaunchTag t_tag;
+struct TimingMark { const char* what; LaunchTag tag; cudaEvent_t ev; };
+static thread_local std::vector<TimingMark> t_marks;
+static thread_local std::vector<cudaEvent_t> t_event_pool;
+static thread_local std::string t_report;
+static cudaEvent_t timing_event() {
+  if (!t_event_pool.empty()) { cudaEvent_t e = t_event_pool.back(); t_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void timing_mark(const char* what, cudaStream_t s) {
+  TimingMark m{what, t_tag, timing_event()};
+  if (m.ev && cudaEventRecord(m.ev, s) == cudaSuccess) t_marks.push_back(m);
+  else cudaGetLastError();
+  t_tag.flop = 0.0;                 // FLOPs belong to the one launch they were set for
+}
+
 // ---- graph table ---------------------------------------------------------------------------------
 struct BlockSpec { const char* name; int c1, c3r, c3, cdr, cd1, cd2; int pool_max; int cproj; int stride; };
 // bn_inception.yaml:30-551
@@ -56,7 +76,7 @@ static std::vector<ConvSpec> conv_table(int in_ch) {
 }
 
 // ---- planned objects -----------------------------------------------------------------------------
-struct Buffer { std::string name; int H, W, C; size_t off = 0, goff = 0; };
+struct Buffer { std::string name; int H, W, C; size_t off = 0, goff = 0; size_t hoff = 0, ghoff = 0, plane = 0; };   // EXACT_TC: fp16 hi/lo operand planes (lo = hi + plane)
 struct Value { std::string name; int buf, coff, C; };
 enum OpKind { OP_CONV = 0, OP_MAXPOOL = 1, OP_AVGPOOL = 2, OP_GPOOL = 3 };
 struct Op {
@@ -77,7 +97,7 @@ struct Op {
   int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
   int fuse_block = -1;
 };
-struct PackedConv { size_t wf, wd, bias, scale; };
+struct PackedConv { size_t wf, wd, bias, scale; size_t wf16 = 0, wd16 = 0, wplane = 0; };   // EXACT_TC: fp16 hi planes of wf / wd, lo = hi + wplane
 // the 1x1 convolutions of one inception block that read the block input (1x1, 3x3_reduce, double_3x3_reduce)
 struct FusedBlock {
   int op1 = -1, op_r3 = -1, op_rd = -1;   // op indices (op1 = -1 for 3c/4e)
@@ -95,7 +115,11 @@ struct ssnb_engine {
   ssnb_config cfg;
   int F = 0;
   bool fp16 = false;
+  bool tc = false;                  // SSNB_EXACT_TC: fp32 storage + glue, convolutions as split-operand (hi/lo fp16) tcgen05 MMAs
   size_t esz = 4;
+  size_t up_plane = 0, s2d_plane = 0, s2d_w_plane = 0;
+  int* tc_flag = nullptr;           // device int: set when a split pass saw |x * grad_scale| beyond the fp16 range
+  size_t tc_flag_off = 0;
   std::vector<ConvSpec> convs;
   std::vector<Buffer> bufs;
   std::vector<Value> vals;
@@ -116,11 +140,6 @@ struct ssnb_engine {
   std::string error;
   long long launches0 = 0;
   UmmaContext umma_ctx;
-  // experimental (SSNB_GRAPH=1, not yet run on a GPU): the library replays its own forward / backward launch sequences
-  // as CUDA graphs when the caller is not capturing itself (the eager, reference-facing module path)
-  cudaGraphExec_t fwd_exec = nullptr, bwd_exec = nullptr;
-  bool fwd_warm = false, bwd_warm = false;
-  unsigned long long bwd_key = 0;
 
   int fail(int code, const std::string& msg) { error = msg; return code; }
   View view(int val, bool grad) const {
@@ -129,6 +148,15 @@ struct ssnb_engine {
     View w;
     w.base = ws + (grad ? b.goff : b.off);
     w.H = b.H; w.W = b.W; w.C = v.C; w.pitch = b.C; w.coff = v.coff;
+    return w;
+  }
+  // EXACT_TC: the fp16 hi/lo operand planes of a value (activation or gradient)
+  View planes(int val, bool grad) const {
+    const Value& v = vals[val];
+    const Buffer& b = bufs[v.buf];
+    View w;
+    w.base = ws + (grad ? b.ghoff : b.hoff);
+    w.H = b.H; w.W = b.W; w.C = v.C; w.pitch = b.C; w.coff = v.coff; w.lo_off = (long long)b.plane;
     return w;
   }
 };
@@ -220,6 +248,15 @@ static void plan(ssnb_engine* e) {
   for (Buffer& b : e->bufs) { b.off = off; off = align_up(off + F * b.H * b.W * b.C * e->esz, 1024); }
   if (e->cfg.training)
     for (Buffer& b : e->bufs) { b.goff = off; off = align_up(off + F * b.H * b.W * b.C * e->esz, 1024); }
+  if (e->tc) {
+    for (Buffer& b : e->bufs) {
+      if (b.C % 8) continue;                              // the network input (3 / 10 channels) has no planes: conv1 reads its own packed copy
+      b.plane = align_up(F * b.H * b.W * b.C * 2, 1024);
+      b.hoff = off; off += 2 * b.plane;
+      if (e->cfg.training) { b.ghoff = off; off += 2 * b.plane; }
+    }
+    e->tc_flag_off = off; off = align_up(off + 256, 1024);
+  }
   for (Op& o : e->ops)
     if (o.kind == OP_MAXPOOL) {
       const Buffer& ob = e->bufs[e->vals[o.out_val].buf];
@@ -234,6 +271,11 @@ static void plan(ssnb_engine* e) {
     e->packed[i].wd = off; off = align_up(off + n * e->esz, 1024);
     e->packed[i].bias = off; off = align_up(off + c.cout * 4, 256);
     e->packed[i].scale = off; off = align_up(off + c.cout * 4, 256);
+    if (e->tc) {
+      e->packed[i].wplane = align_up(n * 2, 1024);
+      e->packed[i].wf16 = off; off += 2 * e->packed[i].wplane;
+      e->packed[i].wd16 = off; off += 2 * e->packed[i].wplane;
+    }
   }
   // backward bookkeeping: accumulate flags + split-K sizing
   size_t pmax = 0;
@@ -308,13 +350,31 @@ static void plan(ssnb_engine* e) {
       pmax = std::max(pmax, (size_t)128 * 16 * 64 * e->Cs * 4);
     }
   }
+  if (e->tc) {
+    e->Cs = (4 * e->cfg.in_channels + 7) / 8 * 8;
+    e->s2d_plane = align_up(F * 112 * 112 * 4 * e->Cs * 2, 1024);
+    e->s2d_off = off; off += 2 * e->s2d_plane;
+    e->s2d_w_plane = align_up((size_t)16 * 64 * e->Cs * 2, 1024);
+    e->s2d_w_off = off; off += 2 * e->s2d_w_plane;
+    if (e->cfg.training) {
+      size_t up = 0;
+      for (const Op& o : e->ops)
+        if (o.kind == OP_CONV && o.stride == 2 && o.conv != 0) {
+          const Buffer& ib = e->bufs[e->vals[o.in_val].buf];
+          up = std::max(up, F * ib.H * ib.W * (size_t)e->convs[o.conv].cout * 2);
+        }
+      e->up_plane = align_up(up, 1024);
+      e->up_off = off; off += 2 * e->up_plane;
+      pmax = std::max(pmax, (size_t)128 * 16 * 64 * e->Cs * 4);
+    }
+  }
   e->partial_off = off; e->partial_bytes = pmax; off = align_up(off + pmax, 1024);
   if (e->cfg.training)
     for (Op& o : e->ops)
       if (o.kind == OP_CONV) {
         const ConvSpec& c = e->convs[o.conv];
         size_t need = (size_t)o.wsplits * c.k * c.k * c.cout * c.cin * 4;
-        if (o.conv == 0 && e->fp16) need = std::max(need, (size_t)128 * 16 * 64 * e->Cs * 4);
+        if (o.conv == 0 && (e->fp16 || e->tc)) need = std::max(need, (size_t)128 * 16 * 64 * e->Cs * 4);
         o.partial_off = off; off = align_up(off + need, 1024);
         o.bias_partial_off = off; off = align_up(off + (size_t)std::max(o.wsplits, 128) * c.cout * 4, 256);
       }
@@ -322,30 +382,38 @@ static void plan(ssnb_engine* e) {
   e->ws_bytes = off;
 }
 
-static bool graphs_enabled() {
-  static const bool on = [] {
-    const char* g = getenv("SSNB_GRAPH");
-    const char* a = getenv("SSNB_PROFILE_FWD_OPS");
-    const char* b = getenv("SSNB_PROFILE_BWD_OPS");
-    return g && g[0] == '1' && !(a && *a) && !(b && *b);
-  }();
-  return on;
-}
-static bool stream_capturing(cudaStream_t s) {
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return true; }    // unknown: stay eager
-  return st != cudaStreamCaptureStatusNone;
-}
-static void drop_graphs(ssnb_engine* e) {
-  if (e->fwd_exec) { cudaGraphExecDestroy(e->fwd_exec); e->fwd_exec = nullptr; }
-  if (e->bwd_exec) { cudaGraphExecDestroy(e->bwd_exec); e->bwd_exec = nullptr; }
-  e->fwd_warm = e->bwd_warm = false;
-}
-
 // ---- op execution --------------------------------------------------------------------------------
 #define DISPATCH(e, call_f, call_h) ((e)->fp16 ? (call_h) : (call_f))
 
+// timing tags (common.cuh): the next launch is the convolution `o` in pass `phase`
+static double conv_flops(const ssnb_engine* e, const Op& o) {
+  const ConvSpec& c = e->convs[o.conv];
+  const Buffer& ob = e->bufs[e->vals[o.out_val].buf];
+  return 2.0 * e->F * ob.H * ob.W * (double)c.cout * c.cin * c.k * c.k;
+}
+static inline void tag_next(int phase, double flop) { t_tag.phase = phase; t_tag.flop = flop; }
+
+// EXACT_TC: operand planes of a value produced by a kernel that only wrote fp32 (pools, SIMT convolutions, value_write)
+static int tc_split_value(ssnb_engine* e, int val, bool grad, float scale, cudaStream_t s) {
+  if (!e->tc || !e->bufs[e->vals[val].buf].plane) return 0;
+  return launch_split_view(e->view(val, grad), e->F, scale, e->planes(val, grad), grad ? e->tc_flag : nullptr, s);
+}
+
+static int run_fwd_impl(ssnb_engine* e, const Op& o, const float* input_nchw, float* feat, cudaStream_t s);
 static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* feat, cudaStream_t s) {
+  if (e->tc && o.kind == OP_CONV && o.umma.enabled) {
+    // split-operand tcgen05 convolution: reads the input's hi/lo planes, writes fp32 + the output's planes
+    if (o.conv == 0 && !e->s2d_ready)
+      if (int rc = launch_nhwc_to_s2d_split(e->view(o.in_val, false), e->F, (__half*)(e->ws + e->s2d_off), (long long)e->s2d_plane, e->Cs, s)) return rc;
+    tag_next(0, conv_flops(e, o));
+    return umma_conv_launch(e->umma_ctx, o.umma, s);
+  }
+  tag_next(0, 0.0);
+  if (int rc = run_fwd_impl(e, o, input_nchw, feat, s)) return rc;
+  return (e->tc && o.out_val >= 0) ? tc_split_value(e, o.out_val, false, 1.0f, s) : 0;
+}
+
+static int run_fwd_impl(ssnb_engine* e, const Op& o, const float* input_nchw, float* feat, cudaStream_t s) {
   const int F = e->F;
   if (o.kind == OP_CONV) {
     const ConvSpec& c = e->convs[o.conv];
@@ -353,6 +421,7 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
     if (e->fp16 && o.umma.enabled) {
       if (o.conv == 0 && !e->s2d_ready)   // conv1 runs as a 4x4 stride-1 convolution over the space-to-depth input
         if (int rc = launch_nhwc_to_s2d(in, F, (__half*)(e->ws + e->s2d_off), e->Cs, s)) return rc;
+      tag_next(0, conv_flops(e, o));
       return umma_conv_launch(e->umma_ctx, o.umma, s);
     }
     ConvArgs a;
@@ -360,6 +429,7 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
     a.dst = out.base; a.DH = out.H; a.DW = out.W; a.Cdst = out.C; a.dst_pitch = out.pitch; a.dst_coff = out.coff;
     a.wgt = e->ws + e->packed[o.conv].wf; a.bias = (const float*)(e->ws + e->packed[o.conv].bias);
     a.F = F; a.k = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = 1; a.accumulate = 0; a.dgrad = 0;
+    tag_next(0, conv_flops(e, o));
     return DISPATCH(e, launch_conv<float>(a, s), launch_conv<__half>(a, s));
   }
   if (o.kind == OP_MAXPOOL) {
@@ -386,6 +456,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   const int F = e->F;
   const float gs = e->fp16 ? e->cfg.grad_scale : 1.0f;
   int rc = 0;
+  tag_next(3, 0.0);
   if (o.kind == OP_GPOOL) {
     if (!dfeat) return e->fail(SSNB_EINVAL, "global_pool backward needs dfeat");
     const View din = e->view(o.in_val, true);
@@ -415,6 +486,53 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   float* bpartial = (float*)(e->ws + e->bpartial_off);
   const long long M = (long long)F * y.H * y.W;
   float* dbp = (e->db.size() && e->db[o.conv]) ? e->db[o.conv] : nullptr;
+  if (e->tc) {
+    // EXACT_TC: fp32 mask + bias gradient (as EXACT), then dz * grad_scale as hi/lo planes for the tensor-core products
+    const float gst = e->cfg.grad_scale;
+    if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
+    if (dbp) {
+      int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
+      if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f, bpartial, bs, dbp, e->grad_accumulate, s))) return rc;
+    }
+    const bool want_w = e->dw.size() && e->dw[o.conv];
+    const bool want_x = e->vals[o.in_val].name != "data" && !skip_dgrad;
+    const bool tc_w = want_w && o.umma_wgrad.enabled, tc_x = want_x && o.umma_dgrad.enabled;
+    if (tc_w || tc_x)
+      if ((rc = tc_split_value(e, o.out_val, true, gst, s))) return rc;
+    if (tc_x && c.stride == 2 && o.conv != 0) {              // dz at input resolution (zero-upsampled), both planes
+      const View dzp = e->planes(o.out_val, true);
+      View lo = dzp; lo.base = (char*)dzp.base + dzp.lo_off;
+      if ((rc = launch_upsample2_zero(dzp, (__half*)(e->ws + e->up_off), x.H, x.W, F, s))) return rc;
+      if ((rc = launch_upsample2_zero(lo, (__half*)(e->ws + e->up_off + e->up_plane), x.H, x.W, F, s))) return rc;
+    }
+    if (tc_w) {
+      tag_next(2, conv_flops(e, o));
+      if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, nullptr))) return rc;
+      if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gst, e->dw[o.conv], e->grad_accumulate, s);
+      else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gst, e->dw[o.conv], e->grad_accumulate, s);
+      if (rc) return rc;
+    } else if (want_w) {
+      WgradArgs w;
+      w.dz = dy.base; w.OH = y.H; w.OW = y.W; w.Cout = y.C; w.dz_pitch = dy.pitch; w.dz_coff = dy.coff;
+      w.x = x.base; w.IH = x.H; w.IW = x.W; w.Cin = x.C; w.x_pitch = x.pitch; w.x_coff = x.coff;
+      w.partial = partial; w.F = F; w.k = c.k; w.stride = c.stride; w.pad = c.pad;
+      w.rows_per_split = o.wrows; w.splits = o.wsplits;
+      tag_next(2, conv_flops(e, o));
+      if ((rc = launch_wgrad<float>(w, s))) return rc;
+      if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f, e->dw[o.conv], e->grad_accumulate, s))) return rc;
+    }
+    tag_next(1, conv_flops(e, o));
+    if (tc_x) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s);
+    if (want_x) {
+      ConvArgs a;
+      a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
+      a.dst = dx.base; a.DH = dx.H; a.DW = dx.W; a.Cdst = dx.C; a.dst_pitch = dx.pitch; a.dst_coff = dx.coff;
+      a.wgt = e->ws + e->packed[o.conv].wd; a.bias = nullptr;
+      a.F = F; a.k = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = 0; a.accumulate = o.grad_accumulate; a.dgrad = 1;
+      rc = launch_conv<float>(a, s);
+    }
+    return rc;
+  }
   if (e->fp16 && full && e->fold_pools && o.pool_consumer >= 0) {
     // max-pool backward gather + ReLU mask + bias-gradient column sums in one pass (dy is never materialised)
     const Op& po = e->ops[o.pool_consumer];
@@ -438,6 +556,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   if (e->dw.size() && e->dw[o.conv] && e->fp16 && o.umma_wgrad.enabled) {
     const bool bias_w = full && e->fold_pools && o.dy_premasked && o.bias_in_wgrad && dbp;
     float* bp = bias_w ? (float*)(e->ws + o.bias_partial_off) : nullptr;
+    tag_next(2, conv_flops(e, o));
     if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, bp))) return rc;
     if (full && e->fold_pools && o.conv != 0) { e->pending_finalize.push_back((int)(&o - e->ops.data())); rc = 0; }   // batched at the end of the backward
     else if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
@@ -449,10 +568,12 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     w.x = x.base; w.IH = x.H; w.IW = x.W; w.Cin = x.C; w.x_pitch = x.pitch; w.x_coff = x.coff;
     w.partial = partial; w.F = F; w.k = c.k; w.stride = c.stride; w.pad = c.pad;
     w.rows_per_split = o.wrows; w.splits = o.wsplits;
+    tag_next(2, conv_flops(e, o));
     if ((rc = DISPATCH(e, launch_wgrad<float>(w, s), launch_wgrad<__half>(w, s)))) return rc;
     if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s))) return rc;
   }
   if (e->vals[o.in_val].name != "data" && !skip_dgrad) {
+    tag_next(1, conv_flops(e, o));
     if (e->fp16 && o.umma_dgrad.enabled) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s, full && e->fold_pools && o.dgrad_masks);
     ConvArgs a;
     a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
@@ -494,16 +615,17 @@ int ssnb_conv_info(int idx, int in_channels, char* name, int name_cap, int* cin,
 int ssnb_create(const ssnb_config* cfg, ssnb_handle* out) {
   if (!cfg || !out) { set_thread_error("ssnb_create: null argument"); return SSNB_EINVAL; }
   if (cfg->frames <= 0 || cfg->in_channels <= 0 || cfg->in_channels > 64) { set_thread_error("ssnb_create: bad frames/in_channels"); return SSNB_EINVAL; }
-  if (cfg->precision != SSNB_EXACT_FP32 && cfg->precision != SSNB_FAST_FP16) { set_thread_error("ssnb_create: unknown precision"); return SSNB_EINVAL; }
+  if (cfg->precision != SSNB_EXACT_FP32 && cfg->precision != SSNB_FAST_FP16 && cfg->precision != SSNB_EXACT_TC) { set_thread_error("ssnb_create: unknown precision"); return SSNB_EINVAL; }
   ssnb_engine* e = new ssnb_engine();
   e->cfg = *cfg;
   if (!(e->cfg.grad_scale > 0.f)) e->cfg.grad_scale = 1.0f;
   e->F = cfg->frames;
   e->fp16 = cfg->precision == SSNB_FAST_FP16;
+  e->tc = cfg->precision == SSNB_EXACT_TC;
   e->esz = e->fp16 ? 2 : 4;
   build_graph(e);
   if ((int)e->convs.size() != 69) { delete e; set_thread_error("internal: conv table size"); return SSNB_ESTATE; }
-  umma_context_init(e->umma_ctx, e->fp16);
+  umma_context_init(e->umma_ctx, e->fp16 || e->tc);
   plan(e);
   e->launches0 = g_launches.load();
   *out = e;
@@ -512,7 +634,6 @@ int ssnb_create(const ssnb_config* cfg, ssnb_handle* out) {
 
 int ssnb_destroy(ssnb_handle h) {
   if (!h) return SSNB_OK;
-  drop_graphs(h);
   umma_context_destroy(h->umma_ctx);
   delete h;
   return SSNB_OK;
@@ -526,8 +647,68 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
   if (((uintptr_t)dev_ptr) % 1024) return h->fail(SSNB_EINVAL, "workspace must be 1024-byte aligned");
   h->ws = (char*)dev_ptr;
   h->weights_ready = false;
-  drop_graphs(h);                       // captured launches hold workspace addresses
   if (h->fp16 && cudaMemset(h->ws + h->bpartial_off, 0, 256) != cudaSuccess) { cudaGetLastError(); /* no device (CPU-only planning) */ }
+  if (h->tc) {
+    // SSNB_EXACT_TC: split-operand plans over the hi/lo planes.  SSNB_DISABLE_UMMA=1 leaves every convolution on the fp32
+    // SIMT kernels (= SSNB_EXACT_FP32 arithmetic; what the tensor-core launches are diffed against).
+    h->tc_flag = (int*)(h->ws + h->tc_flag_off);
+    if (cudaMemset(h->tc_flag, 0, 256) != cudaSuccess) cudaGetLastError();
+    const char* dis_tc = getenv("SSNB_DISABLE_UMMA");
+    const bool use_tc = !(dis_tc && dis_tc[0] == '1');
+    const char* disw_tc = getenv("SSNB_DISABLE_UMMA_WGRAD");
+    const bool use_wgrad_tc = h->cfg.training && !(disw_tc && disw_tc[0] == '1');
+    const float gs = h->cfg.grad_scale;
+    for (Op& o : h->ops) {
+      o.umma.enabled = false; o.umma_dgrad.enabled = false; o.umma_wgrad.enabled = false;
+      o.fuse_role = 0; o.fuse_block = -1; o.dgrad_masks = false; o.dy_premasked = false; o.bias_in_wgrad = false;
+      if (o.kind != OP_CONV || !use_tc) continue;
+      const ConvSpec& c = h->convs[o.conv];
+      const PackedConv& pk = h->packed[o.conv];
+      const View out32 = h->view(o.out_val, false);
+      int rc = 0;
+      if (o.conv == 0) {
+        // conv1 7x7/2: four vertical taps over the packed space-to-depth input planes (see the FAST binding below)
+        const int Ck = 4 * h->Cs;
+        View xs; xs.base = h->ws + h->s2d_off; xs.H = 112; xs.W = 112; xs.C = Ck; xs.pitch = Ck; xs.coff = 0; xs.lo_off = (long long)h->s2d_plane;
+        int dy[4], dx[4];
+        for (int t = 0; t < 4; ++t) { dy[t] = t - 2; dx[t] = 0; }
+        UmmaTcOpts t; t.w_lo_off = (long long)h->s2d_w_plane; t.out32 = (float*)out32.base; t.alpha = 1.0f;
+        rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, h->planes(o.out_val, false), h->F, Ck, c.cout, 4, dy, dx,
+                                 (const __half*)(h->ws + h->s2d_w_off), (const float*)(h->ws + pk.bias), 1, &t);
+        if (rc) return h->fail(rc, "tc conv1 bind: " + ssnb::thread_error());
+        if (!o.umma.p.v2) o.umma.enabled = false;
+        if (use_wgrad_tc) {
+          rc = umma_wgrad_bind_taps(h->umma_ctx, o.umma_wgrad, h->planes(o.out_val, true), xs, h->F, Ck, c.cout, 4, dy, dx,
+                                    (float*)(h->ws + o.partial_off), 128);
+          if (rc) return h->fail(rc, "tc conv1 wgrad bind: " + ssnb::thread_error());
+        }
+        continue;
+      }
+      if (c.cin % 8 != 0 || c.k * c.k > UMMA_MAX_TAPS) continue;
+      UmmaTcOpts t; t.w_lo_off = (long long)pk.wplane; t.out32 = (float*)out32.base; t.alpha = 1.0f;
+      rc = umma_conv_bind_fwd(h->umma_ctx, o.umma, h->planes(o.in_val, false), h->planes(o.out_val, false), h->F, c.cin, c.cout, c.k, c.pad,
+                              c.stride, (const __half*)(h->ws + pk.wd16), (const float*)(h->ws + pk.bias), &t);
+      if (rc) return h->fail(rc, "tc bind_fwd(" + c.id + "): " + ssnb::thread_error());
+      if (!h->cfg.training) continue;
+      View dz = h->planes(o.out_val, true);
+      const View in = h->view(o.in_val, false);
+      if (c.stride == 2) { dz.base = h->ws + h->up_off; dz.H = in.H; dz.W = in.W; dz.C = c.cout; dz.pitch = c.cout; dz.coff = 0; dz.lo_off = (long long)h->up_plane; }
+      View dxp = h->planes(o.in_val, true); dxp.base = nullptr; dxp.lo_off = 0;          // data gradients: fp32 only (masked and split by their consumer)
+      UmmaTcOpts tg; tg.w_lo_off = (long long)pk.wplane; tg.out32 = (float*)h->view(o.in_val, true).base; tg.alpha = 1.0f / gs;
+      rc = umma_conv_bind_dgrad(h->umma_ctx, o.umma_dgrad, dz, dxp, h->F, c.cin, c.cout, c.k, c.pad, (const __half*)(h->ws + pk.wf16),
+                                o.grad_accumulate, &tg);
+      if (rc) return h->fail(rc, "tc bind_dgrad(" + c.id + "): " + ssnb::thread_error());
+      if (!o.umma_dgrad.p.v2) o.umma_dgrad.enabled = false;
+      if (use_wgrad_tc) {
+        rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->planes(o.out_val, true), h->planes(o.in_val, false), h->F, c.cin, c.cout, c.k, c.pad,
+                             (float*)(h->ws + o.partial_off), o.wsplits, c.stride);
+        if (rc) return h->fail(rc, "tc wgrad_bind(" + c.id + "): " + ssnb::thread_error());
+      }
+    }
+    h->fold_pools = false;
+    for (FusedBlock& fb : h->fused) fb.enabled = false;
+    return SSNB_OK;
+  }
   // bind tcgen05 plans (tensor maps need final addresses); SSNB_DISABLE_UMMA=1 keeps FAST mode on the SIMT kernels
   const char* dis = getenv("SSNB_DISABLE_UMMA");
   const bool use_umma = h->fp16 && !(dis && dis[0] == '1');
@@ -653,6 +834,19 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                                                (float*)(h->ws + p.wf), (float*)(h->ws + p.wd), (float*)(h->ws + p.bias),
                                                (float*)(h->ws + p.scale), s);
     if (rc) return h->fail(rc, "pack_weights(" + c.id + "): " + ssnb::thread_error());
+    if (h->tc) {     // hi/lo fp16 planes of the folded fp32 weights, both kernel layouts
+      const long long n = (long long)c.cout * c.cin * c.k * c.k;
+      if ((rc = launch_split_flat((const float*)(h->ws + p.wf), n, (__half*)(h->ws + p.wf16), (__half*)(h->ws + p.wf16 + p.wplane), s)) ||
+          (rc = launch_split_flat((const float*)(h->ws + p.wd), n, (__half*)(h->ws + p.wd16), (__half*)(h->ws + p.wd16 + p.wplane), s)))
+        return h->fail(rc, "pack_weights split(" + c.id + "): " + ssnb::thread_error());
+    }
+  }
+  if (h->tc && h->ops.size() && h->ops[0].umma.enabled) {
+    for (int pl = 0; pl < 2; ++pl) {
+      int rc = launch_pack_conv1_s2d((const __half*)(h->ws + h->packed[0].wd16 + pl * h->packed[0].wplane), h->convs[0].cout, h->convs[0].cin, h->Cs,
+                                     (__half*)(h->ws + h->s2d_w_off + pl * h->s2d_w_plane), s);
+      if (rc) return h->fail(rc, "pack conv1 s2d (tc): " + ssnb::thread_error());
+    }
   }
   if (h->fp16 && h->ops.size() && h->ops[0].umma.enabled) {
     int rc = launch_pack_conv1_s2d((const __half*)(h->ws + h->packed[0].wd), h->convs[0].cout, h->convs[0].cin, h->Cs,
@@ -689,47 +883,27 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
   cudaStream_t s = (cudaStream_t)stream;
   const View d = h->view(h->val_by_name["data"], false);
   int rc;
-  h->s2d_ready = h->fp16 && h->ops[0].umma.enabled;
-  if (h->s2d_ready) rc = launch_nchw_to_s2d(input_nchw, h->F, d.C, d.H, d.W, (__half*)(h->ws + h->s2d_off), h->Cs, s);
+  h->s2d_ready = (h->fp16 || h->tc) && h->ops[0].umma.enabled;
+  if (h->s2d_ready && h->tc) rc = launch_nchw_to_s2d_split(input_nchw, h->F, d.C, d.H, d.W, (__half*)(h->ws + h->s2d_off), (long long)h->s2d_plane, h->Cs, s);
+  else if (h->s2d_ready) rc = launch_nchw_to_s2d(input_nchw, h->F, d.C, d.H, d.W, (__half*)(h->ws + h->s2d_off), h->Cs, s);
   else rc = h->fp16 ? launch_nchw_to_nhwc<__half>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s)
                     : launch_nchw_to_nhwc<float>(input_nchw, h->F, d.C, d.H, d.W, d, 1.0f, s);
   if (rc) { h->s2d_ready = false; return h->fail(rc, "input layout: " + ssnb::thread_error()); }
-  // every op except the last (global pool -> caller's feat) touches workspace memory only, so its launch sequence can be
-  // replayed as a graph; first call eager (lazy function attributes), second call captures, later calls replay
-  auto run_ops = [&](bool only_last, bool skip_last) -> int {
-    for (size_t i = 0; i < h->ops.size(); ++i) {
-      const Op& o = h->ops[i];
-      const bool last = i + 1 == h->ops.size();
-      if ((only_last && !last) || (skip_last && last)) continue;
-      if (o.fuse_role == 2) continue;                       // computed by its block's fused launch
-      const bool prof = profiled_op("SSNB_PROFILE_FWD_OPS", o.id);
-      if (prof) cudaProfilerStart();
-      int r;
-      if (o.fuse_role == 1) r = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].fwd, s);
-      else r = run_fwd(h, o, input_nchw, feat, s);
-      if (prof) cudaProfilerStop();
-      if (r) { h->s2d_ready = false; return h->fail(r, "fwd " + o.id + ": " + ssnb::thread_error()); }
-    }
-    return 0;
-  };
-  const bool graph = graphs_enabled() && h->fwd_warm && h->ops.back().kind == OP_GPOOL && !stream_capturing(s);
-  if (!graph) {
-    if ((rc = run_ops(false, false))) return rc;
-    h->fwd_warm = true;
-  } else {
-    if (!h->fwd_exec) {
-      cudaGraph_t g = nullptr;
-      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->s2d_ready = false; return h->fail(SSNB_ECUDA, "fwd graph: begin capture"); }
-      rc = run_ops(false, true);
-      const cudaError_t ce = cudaStreamEndCapture(s, &g);
-      if (rc || ce != cudaSuccess || !g || cudaGraphInstantiate(&h->fwd_exec, g, 0) != cudaSuccess) {
-        cudaGetLastError(); if (g) cudaGraphDestroy(g); h->fwd_exec = nullptr; h->s2d_ready = false;
-        return h->fail(rc ? rc : SSNB_ECUDA, "fwd graph: capture/instantiate failed");
-      }
-      cudaGraphDestroy(g);
-    }
-    if (cudaGraphLaunch(h->fwd_exec, s) != cudaSuccess) { cudaGetLastError(); h->s2d_ready = false; return h->fail(SSNB_ECUDA, "fwd graph: launch"); }
-    if ((rc = run_ops(true, false))) return rc;
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    const Op& o = h->ops[i];
+    if (o.fuse_role == 2) continue;                       // computed by its block's fused launch
+    const bool prof = profiled_op("SSNB_PROFILE_FWD_OPS", o.id);
+    if (prof) cudaProfilerStart();
+    int r;
+    if (o.fuse_role == 1) {
+      const FusedBlock& fb = h->fused[o.fuse_block];
+      double fl = 0.0;
+      for (int j : {fb.op1, fb.op_r3, fb.op_rd}) if (j >= 0) fl += conv_flops(h, h->ops[j]);
+      tag_next(0, fl);
+      r = umma_conv_launch(h->umma_ctx, fb.fwd, s);
+    } else r = run_fwd(h, o, input_nchw, feat, s);
+    if (prof) cudaProfilerStop();
+    if (r) { h->s2d_ready = false; return h->fail(r, "fwd " + o.id + ": " + ssnb::thread_error()); }
   }
   h->s2d_ready = false;
   return SSNB_OK;
@@ -756,7 +930,13 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
       const bool prof = profiled_op("SSNB_PROFILE_BWD_OPS", o.id);
       if (prof) cudaProfilerStart();
       int rc = run_bwd(h, o, dfeat, s, o.fuse_role != 0, true);   // siblings: mask/bias/wgrad only ...
-      if (!rc && o.fuse_role == 1) rc = umma_conv_launch(h->umma_ctx, h->fused[o.fuse_block].dgrad, s, h->fold_pools && o.dgrad_masks);   // ... one fused data gradient
+      if (!rc && o.fuse_role == 1) {                                   // ... one fused data gradient
+        const FusedBlock& fb = h->fused[o.fuse_block];
+        double fl = 0.0;
+        for (int j : {fb.op1, fb.op_r3, fb.op_rd}) if (j >= 0) fl += conv_flops(h, h->ops[j]);
+        tag_next(1, fl);
+        rc = umma_conv_launch(h->umma_ctx, fb.dgrad, s, h->fold_pools && o.dgrad_masks);
+      }
       if (prof) cudaProfilerStop();
       if (rc) return h->fail(rc, "bwd " + o.id + ": " + ssnb::thread_error());
     }
@@ -781,37 +961,8 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
     if (int rc = flush()) return h->fail(rc, "finalize: " + ssnb::thread_error());
     return 0;
   };
-  const int last = (int)h->ops.size() - 1;
-  // the gradient pointers are baked into the captured launches: key the graph on them (and on the accumulate flag)
-  unsigned long long key = 1469598103934665603ull ^ (unsigned long long)h->grad_accumulate;
-  for (size_t i = 0; i < h->convs.size(); ++i) {
-    key = (key ^ (unsigned long long)(uintptr_t)(h->dw.size() ? h->dw[i] : nullptr)) * 1099511628211ull;
-    key = (key ^ (unsigned long long)(uintptr_t)(h->db.size() ? h->db[i] : nullptr)) * 1099511628211ull;
-  }
-  const bool graph = graphs_enabled() && h->bwd_warm && h->ops[last].kind == OP_GPOOL && !stream_capturing(s);
-  if (!graph) {
-    if (int rc = run_range(last, 0)) return rc;
-    if (int rc = finalize()) return rc;
-    h->bwd_warm = true;
-    return SSNB_OK;
-  }
-  if (int rc = run_range(last, last)) return rc;                   // global-pool backward: reads dfeat, eager
-  if (h->bwd_exec && h->bwd_key != key) { cudaGraphExecDestroy(h->bwd_exec); h->bwd_exec = nullptr; }
-  if (!h->bwd_exec) {
-    cudaGraph_t g = nullptr;
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return h->fail(SSNB_ECUDA, "bwd graph: begin capture"); }
-    int rc = run_range(last - 1, 0);
-    if (!rc) rc = finalize();
-    const cudaError_t ce = cudaStreamEndCapture(s, &g);
-    if (rc || ce != cudaSuccess || !g || cudaGraphInstantiate(&h->bwd_exec, g, 0) != cudaSuccess) {
-      cudaGetLastError(); if (g) cudaGraphDestroy(g); h->bwd_exec = nullptr; h->pending_finalize.clear();
-      return h->fail(rc ? rc : SSNB_ECUDA, "bwd graph: capture/instantiate failed");
-    }
-    cudaGraphDestroy(g);
-    h->bwd_key = key;
-  }
-  if (cudaGraphLaunch(h->bwd_exec, s) != cudaSuccess) { cudaGetLastError(); return h->fail(SSNB_ECUDA, "bwd graph: launch"); }
-  return SSNB_OK;
+  if (int rc = run_range((int)h->ops.size() - 1, 0)) return rc;
+  return finalize();
 }
 
 int ssnb_set_grad_accumulate(ssnb_handle h, int accumulate) {
@@ -850,6 +1001,7 @@ int ssnb_value_write(ssnb_handle h, const char* name, int grad, const float* src
   const float sc = (grad && h->fp16) ? h->cfg.grad_scale : 1.0f;
   int rc = h->fp16 ? launch_nchw_to_nhwc<__half>(src_nchw, h->F, v.C, v.H, v.W, v, sc, (cudaStream_t)stream)
                    : launch_nchw_to_nhwc<float>(src_nchw, h->F, v.C, v.H, v.W, v, sc, (cudaStream_t)stream);
+  if (!rc && h->tc && !grad) rc = tc_split_value(h, it->second, false, 1.0f, (cudaStream_t)stream);   // activation planes follow the fp32 value
   return rc ? h->fail(rc, ssnb::thread_error()) : SSNB_OK;
 }
 
@@ -858,6 +1010,11 @@ int ssnb_value_read(ssnb_handle h, const char* name, int grad, float* dst_nchw, 
   auto it = h->val_by_name.find(name);
   if (it == h->val_by_name.end()) return h->fail(SSNB_EINVAL, std::string("unknown value ") + name);
   if (grad && !h->cfg.training) return h->fail(SSNB_ESTATE, "no gradient buffers");
+  if (grad & 2) {       // diagnostic: read hi + lo of the value's EXACT_TC operand planes (bit 0: gradient planes, un-scaled)
+    if (!h->tc || !h->bufs[h->vals[it->second].buf].plane) return h->fail(SSNB_ESTATE, "value has no operand planes");
+    int rc = launch_planes_to_nchw(h->planes(it->second, (grad & 1) != 0), h->F, (grad & 1) ? 1.0f / h->cfg.grad_scale : 1.0f, dst_nchw, (cudaStream_t)stream);
+    return rc ? h->fail(rc, ssnb::thread_error()) : SSNB_OK;
+  }
   const View v = h->view(it->second, grad != 0);
   const float sc = (grad && h->fp16) ? 1.0f / h->cfg.grad_scale : 1.0f;
   int rc = h->fp16 ? launch_nhwc_to_nchw<__half>(v, h->F, sc, dst_nchw, (cudaStream_t)stream)
@@ -872,6 +1029,37 @@ int ssnb_run_op(ssnb_handle h, int op, int backward, void* stream) {
   if (o.kind == OP_GPOOL) return h->fail(SSNB_ENOSUPPORT, "run_op: global_pool runs through backbone_fwd/bwd");
   int rc = backward ? run_bwd(h, o, nullptr, (cudaStream_t)stream) : run_fwd(h, o, nullptr, nullptr, (cudaStream_t)stream);
   return rc ? h->fail(rc, o.id + ": " + ssnb::thread_error()) : SSNB_OK;
+}
+
+int ssnb_timing_begin(void* stream) {
+  for (TimingMark& m : ssnb::t_marks) ssnb::t_event_pool.push_back(m.ev);
+  ssnb::t_marks.clear();
+  ssnb::t_tag = LaunchTag();
+  ssnb::t_timing = true;
+  ssnb::timing_mark("(begin)", (cudaStream_t)stream);
+  return SSNB_OK;
+}
+
+const char* ssnb_timing_report(void) {
+  // closes the session, waits for the last launch and aggregates by (kernel, phase): "kernel\tphase\tlaunches\tms\tflop\n"
+  ssnb::t_timing = false;
+  ssnb::t_report.clear();
+  if (ssnb::t_marks.empty()) return ssnb::t_report.c_str();
+  if (cudaEventSynchronize(ssnb::t_marks.back().ev) != cudaSuccess) { cudaGetLastError(); return ssnb::t_report.c_str(); }
+  struct Agg { int n = 0; double ms = 0, flop = 0; };
+  std::map<std::pair<std::string, int>, Agg> agg;
+  for (size_t i = 1; i < ssnb::t_marks.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ssnb::t_marks[i - 1].ev, ssnb::t_marks[i].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+    Agg& a = agg[{ssnb::t_marks[i].what, ssnb::t_marks[i].tag.phase}];
+    a.n += 1; a.ms += ms; a.flop += ssnb::t_marks[i].tag.flop;
+  }
+  char line[256];
+  for (const auto& kv : agg) {
+    snprintf(line, sizeof line, "%s\t%d\t%d\t%.6f\t%.0f\n", kv.first.first.c_str(), kv.first.second, kv.second.n, kv.second.ms, kv.second.flop);
+    ssnb::t_report += line;
+  }
+  return ssnb::t_report.c_str();
 }
 
 int64_t ssnb_launch_count(ssnb_handle h) { return h ? (int64_t)(g_launches.load() - h->launches0) : 0; }

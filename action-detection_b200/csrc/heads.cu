@@ -545,12 +545,13 @@ extern "C" {
 int ssnb_stpp_fwd(const float* ft, const float* scaling, int n, int n_seg, int D, int n_parts, const int* part_lo,
                   const int* part_hi, const int* part_norm, const int* part_scale_col, int course_lo, int course_hi,
                   float* course_ft, float* stpp_ft, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!ft || !scaling || !course_ft || !stpp_ft || n < 0 || D <= 0) { set_thread_error("stpp_fwd: bad argument"); return SSNB_EINVAL; }
   PartTable pt;
   if (int rc = fill_parts(pt, n_parts, part_lo, part_hi, part_norm, part_scale_col, course_lo, course_hi, n_seg)) return rc;
   if (n == 0) return SSNB_OK;
   const long long tot = (long long)n * D;
-  stpp_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ft, scaling, n, n_seg, D, pt, course_ft, stpp_ft);
+  stpp_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ft, scaling, n, n_seg, D, pt, course_ft, stpp_ft);
   SSNB_LAUNCH_CHECK("stpp_fwd_kernel");
   return SSNB_OK;
 }
@@ -558,12 +559,13 @@ int ssnb_stpp_fwd(const float* ft, const float* scaling, int n, int n_seg, int D
 int ssnb_stpp_bwd(const float* d_course, const float* d_stpp, const float* scaling, int n, int n_seg, int D, int n_parts,
                   const int* part_lo, const int* part_hi, const int* part_norm, const int* part_scale_col, int course_lo,
                   int course_hi, float* d_ft, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!d_stpp || !scaling || !d_ft || n < 0 || D <= 0) { set_thread_error("stpp_bwd: bad argument"); return SSNB_EINVAL; }
   PartTable pt;
   if (int rc = fill_parts(pt, n_parts, part_lo, part_hi, part_norm, part_scale_col, course_lo, course_hi, n_seg)) return rc;
   if (n == 0) return SSNB_OK;
   const long long tot = (long long)n * n_seg * D;
-  stpp_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_course, d_stpp, scaling, n, n_seg, D, pt, d_ft);
+  stpp_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_course, d_stpp, scaling, n, n_seg, D, pt, d_ft);
   SSNB_LAUNCH_CHECK("stpp_bwd_kernel");
   return SSNB_OK;
 }
@@ -572,6 +574,7 @@ int ssnb_stpp_bwd(const float* d_course, const float* d_stpp, const float* scali
 int ssnb_gpool_stpp_fwd(ssnb_handle h, const float* drop_mask, const float* scaling, int n_seg, int n_parts,
                         const int* part_lo, const int* part_hi, const int* part_norm, const int* part_scale_col,
                         int course_lo, int course_hi, float* feat, float* course_ft, float* stpp_ft, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   View v; int F = 0, fp16 = 0;
   if (!h || !scaling || !feat || !course_ft || !stpp_ft) { set_thread_error("gpool_stpp: null argument"); return SSNB_EINVAL; }
   if (int rc = engine_tail_view(h, &v, &F, &fp16)) return rc;
@@ -580,8 +583,8 @@ int ssnb_gpool_stpp_fwd(ssnb_handle h, const float* drop_mask, const float* scal
   if (int rc = fill_parts(pt, n_parts, part_lo, part_hi, part_norm, part_scale_col, course_lo, course_hi, n_seg)) return rc;
   const int n = F / n_seg;
   const long long tot = (long long)n * v.C;
-  if (fp16) gpool_stpp_kernel<__half><<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const __half*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
-  else gpool_stpp_kernel<float><<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
+  if (fp16) gpool_stpp_kernel<__half><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>((const __half*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
+  else gpool_stpp_kernel<float><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>((const float*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
   SSNB_LAUNCH_CHECK("gpool_stpp_kernel");
   return SSNB_OK;
 }
@@ -589,6 +592,7 @@ int ssnb_gpool_stpp_fwd(ssnb_handle h, const float* drop_mask, const float* scal
 int ssnb_stpp_reorg(const float* scores, int T, int D, const int32_t* ticks, const float* scaling, int N, int act_len,
                     int comp_len, int reg_len, const int* level_counts, const int* levels, float* out_act,
                     float* out_comp, float* out_reg, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!scores || !ticks || !scaling || !out_act || !out_comp || !out_reg || T <= 0) { set_thread_error("stpp_reorg: bad argument"); return SSNB_EINVAL; }
   ReorgCfg cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.nstage = 3;
@@ -601,16 +605,17 @@ int ssnb_stpp_reorg(const float* scores, int T, int D, const int32_t* ticks, con
   }
   if (D != act_len + mult * (comp_len + reg_len)) { set_thread_error("stpp_reorg: D does not match act+M*(comp+reg)"); return SSNB_EINVAL; }
   if (N == 0) return SSNB_OK;
-  stpp_reorg_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(scores, T, D, ticks, scaling, N, act_len, comp_len, reg_len, cfg, mult, out_act, out_comp, out_reg);
+  stpp_reorg_kernel<<<N, 128, 0, s>>>(scores, T, D, ticks, scaling, N, act_len, comp_len, reg_len, cfg, mult, out_act, out_comp, out_reg);
   SSNB_LAUNCH_CHECK("stpp_reorg_kernel");
   return SSNB_OK;
 }
 
 int ssnb_linear_fwd(const float* x, const float* w, const float* b, int n, int in_dim, int out_dim, float* y, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!x || !w || !y) { set_thread_error("linear_fwd: null"); return SSNB_EINVAL; }
   if (n == 0) return SSNB_OK;
   const long long warps = (long long)n * out_dim;
-  linear_fwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, b, n, in_dim, out_dim, y);
+  linear_fwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(x, w, b, n, in_dim, out_dim, y);
   SSNB_LAUNCH_CHECK("linear_fwd_kernel");
   return SSNB_OK;
 }
@@ -634,36 +639,40 @@ int ssnb_linear_bwd(const float* x, const float* w, const float* dy, int n, int 
 
 int ssnb_ohem_hinge_fwd(const float* pred, const int64_t* labels, int m, int K, int is_positive, int group_size,
                         int keep_num, float* loss, uint8_t* kept, float* slopes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!pred || !labels || !loss || !kept || !slopes || group_size <= 0 || m % group_size) { set_thread_error("ohem_fwd: bad argument"); return SSNB_EINVAL; }
   // slopes doubles as the loss scratch? no: keep a separate scratch appended after slopes by the caller
-  ohem_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, labels, m, K, (float)is_positive, group_size, keep_num, loss, kept, slopes, slopes + m);
+  ohem_fwd_kernel<<<1, 256, 0, s>>>(pred, labels, m, K, (float)is_positive, group_size, keep_num, loss, kept, slopes, slopes + m);
   SSNB_LAUNCH_CHECK("ohem_fwd_kernel");
   return SSNB_OK;
 }
 
 int ssnb_ohem_hinge_bwd(const int64_t* labels, const uint8_t* kept, const float* slopes, const float* grad_out, int m, int K,
                         float* grad_pred, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!labels || !kept || !slopes || !grad_out || !grad_pred) { set_thread_error("ohem_bwd: null"); return SSNB_EINVAL; }
   if (m == 0) return SSNB_OK;
   const long long tot = (long long)m * K;
-  ohem_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, kept, slopes, grad_out, m, K, grad_pred);
+  ohem_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(labels, kept, slopes, grad_out, m, K, grad_pred);
   SSNB_LAUNCH_CHECK("ohem_bwd_kernel");
   return SSNB_OK;
 }
 
 int ssnb_classwise_reg_fwd(const float* pred, const int64_t* labels, const float* targets, int n, int K, float* loss, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!pred || !labels || !targets || !loss) { set_thread_error("reg_fwd: null"); return SSNB_EINVAL; }
-  reg_fwd_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pred, labels, targets, n, K, loss);
+  reg_fwd_kernel<<<1, 32, 0, s>>>(pred, labels, targets, n, K, loss);
   SSNB_LAUNCH_CHECK("reg_fwd_kernel");
   return SSNB_OK;
 }
 
 int ssnb_classwise_reg_bwd(const float* pred, const int64_t* labels, const float* targets, const float* grad_out, int n, int K,
                            float* grad_pred, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!pred || !labels || !targets || !grad_out || !grad_pred) { set_thread_error("reg_bwd: null"); return SSNB_EINVAL; }
   if (n == 0) return SSNB_OK;
   const long long tot = (long long)n * K * 2;
-  reg_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, labels, targets, grad_out, n, K, grad_pred);
+  reg_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(pred, labels, targets, grad_out, n, K, grad_pred);
   SSNB_LAUNCH_CHECK("reg_bwd_kernel");
   return SSNB_OK;
 }
@@ -709,9 +718,10 @@ int ssnb_heads_loss_fwd_bwd(const ssnb_heads_cfg* cfg, const float* course_ft, c
 
 int ssnb_sgd_step(float* param, const float* grad, float* momentum_buf, size_t n, float lr, float momentum, float weight_decay,
                   float grad_mult, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (!param || !grad || !momentum_buf) { set_thread_error("sgd: null"); return SSNB_EINVAL; }
   if (n == 0) return SSNB_OK;
-  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_mult);
+  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_mult);
   SSNB_LAUNCH_CHECK("sgd_kernel");
   return SSNB_OK;
 }

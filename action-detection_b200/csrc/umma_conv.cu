@@ -16,6 +16,7 @@
 
 #include "umma_conv.cuh"
 #include "umma_dev.cuh"
+#include "umma_epi32.cuh"
 
 namespace ssnb {
 
@@ -111,6 +112,26 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+    if (p.out_f32) {
+      // SSNB_EXACT_TC: fp32 epilogue + the result's fp16 hi / lo operand planes (umma_epi32.cuh)
+      float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
+      __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
+      for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
+        const bool two = c0 + 16 < p.block_n;
+        const int cola = t.n0 + c0, colb = cola + 16;
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr + c0, ra);
+        if (two) tmem_ld16(taddr + c0 + 16, rb);
+        tmem_ld_wait();
+        if (valid && cola < p.Cout) store_chunk32(p, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr);
+        if (two && valid && colb < p.Cout) store_chunk32(p, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      continue;
+    }
     // two 16-column chunks per iteration: the global loads of both (accumulate / mask operands) and both TMEM
     // loads are in flight before the first use
     for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
@@ -147,7 +168,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                 const __grid_constant__ CUtensorMap tmap_b, const UmmaConvParams p) {
+                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a_lo,
+                 const __grid_constant__ CUtensorMap tmap_a2_lo, const __grid_constant__ CUtensorMap tmap_b_lo, const UmmaConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -162,7 +184,8 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
-  const int ksteps = p.ntaps * p.kchunks;
+  const int nseg = p.nseg > 1 ? p.nseg : 1;          // SSNB_EXACT_TC: (A_lo, B_hi), (A_hi, B_lo), (A_hi, B_hi) per (tap, K chunk)
+  const int ksteps = p.ntaps * p.kchunks * nseg;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -189,17 +212,21 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bf + p.block_n) * BLOCK_K * 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
+        for (int seg = 3 - nseg; seg < 3; ++seg)
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int kc = 0; kc < p.kchunks; ++kc) {
+            const CUtensorMap* ma = seg == 0 ? &tmap_a_lo : &tmap_a;
+            const CUtensorMap* ma2 = seg == 0 ? &tmap_a2_lo : &tmap_a2;
+            const CUtensorMap* mb = seg == 1 ? &tmap_b_lo : &tmap_b;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
             const uint32_t a_bytes = (uint32_t)(p.bw * p.bh * p.bf) * BLOCK_K * 2;
             mbar_expect_tx(&full_bar[stage], ((p.ablate & 32) ? 0u : a_bytes) + ((p.ablate & 16) ? 0u : tx_bytes - a_bytes));
             if (p.ablate & 32) {}
-            else if (kc < p.kchunks_a1) tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, t.w0 * p.a_stride + p.tap_dx[tap], t.h0 * p.a_stride + p.tap_dy[tap], t.f0);
-            else tma_load_4d(sa, &tmap_a2, &full_bar[stage], (kc - p.kchunks_a1) * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
-            if (!(p.ablate & 16)) tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, t.n0, tap);
+            else if (kc < p.kchunks_a1) tma_load_4d(sa, ma, &full_bar[stage], kc * BLOCK_K, t.w0 * p.a_stride + p.tap_dx[tap], t.h0 * p.a_stride + p.tap_dy[tap], t.f0);
+            else tma_load_4d(sa, ma2, &full_bar[stage], (kc - p.kchunks_a1) * BLOCK_K, t.w0 + p.tap_dx[tap], t.h0 + p.tap_dy[tap], t.f0);
+            if (!(p.ablate & 16)) tma_load_3d(sb, mb, &full_bar[stage], kc * BLOCK_K, t.n0, tap);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -299,13 +326,13 @@ void pick_box(int W, int& bw, int& bh, int& bf) {
 }
 
 int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int K, int N, int ntaps, int out_stride, const __half* w,
-                int a_stride = 1) {
+                int a_stride = 1, const UmmaTcOpts* tc = nullptr) {
   plan.enabled = false;
   if (int rc = resolve_encode(ctx)) return rc;
   if (a_stride == 2) {
     // strided TMA: tiles enumerate OUTPUT pixels, the A box steps over the input with stride 2
     View ao = a; ao.H = o.H; ao.W = o.W;
-    if (int rc = bind_common(ctx, plan, ao, o, F, K, N, ntaps, 1, w, 1)) return rc;
+    if (int rc = bind_common(ctx, plan, ao, o, F, K, N, ntaps, 1, w, 1, tc)) return rc;
     plan.enabled = false;
     UmmaConvParams& q = plan.p;
     q.a_stride = 2;
@@ -313,7 +340,10 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
     cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(2 * q.bw), (cuuint32_t)(2 * q.bh), (cuuint32_t)q.bf};
     if (int rc = encode(ctx, &plan.tmap_a, 4, reinterpret_cast<__half*>(a.base) + a.coff, dims, str, box, 2)) return rc;
-    plan.tmap_a2 = plan.tmap_a;
+    plan.tmap_a_lo = plan.tmap_a;
+    if (a.lo_off)
+      if (int rc = encode(ctx, &plan.tmap_a_lo, 4, reinterpret_cast<__half*>(reinterpret_cast<char*>(a.base) + a.lo_off) + a.coff, dims, str, box, 2)) return rc;
+    plan.tmap_a2 = plan.tmap_a; plan.tmap_a2_lo = plan.tmap_a_lo;
     plan.enabled = true;
     return 0;
   }
@@ -342,6 +372,9 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
     cuuint64_t str[3] = {(cuuint64_t)a.pitch * 2, (cuuint64_t)a.W * a.pitch * 2, (cuuint64_t)a.H * a.W * a.pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
     if (int rc = encode(ctx, &plan.tmap_a, 4, reinterpret_cast<__half*>(a.base) + a.coff, dims, str, box)) return rc;
+    plan.tmap_a_lo = plan.tmap_a;
+    if (a.lo_off)
+      if (int rc = encode(ctx, &plan.tmap_a_lo, 4, reinterpret_cast<__half*>(reinterpret_cast<char*>(a.base) + a.lo_off) + a.coff, dims, str, box)) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)ntaps};
@@ -349,10 +382,18 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
     cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n, 1};
     if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(w), dims, str, box)) return rc;
     plan.b_ptr = w;
+    plan.b_lo_off = tc ? tc->w_lo_off : 0;
+    plan.tmap_b_lo = plan.tmap_b;
+    if (plan.b_lo_off)
+      if (int rc = encode(ctx, &plan.tmap_b_lo, 3, reinterpret_cast<__half*>(reinterpret_cast<char*>(const_cast<__half*>(w)) + plan.b_lo_off), dims, str, box)) return rc;
     for (int i = 0; i < 3; ++i) plan.b_dims[i] = dims[i];
     for (int i = 0; i < 2; ++i) plan.b_strides[i] = str[i];
   }
-  plan.tmap_a2 = plan.tmap_a;
+  plan.tmap_a2 = plan.tmap_a; plan.tmap_a2_lo = plan.tmap_a_lo;
+  // SSNB_EXACT_TC: three operand segments per K chunk, fp32 epilogue (+ fp16 operand planes of the result)
+  p.nseg = tc ? 3 : 1; p.out_f32 = tc ? 1 : 0; p.alpha = tc ? tc->alpha : 1.0f;
+  p.out32 = tc ? tc->out32 : nullptr; p.out_hi = tc ? reinterpret_cast<__half*>(o.base) : nullptr; p.out_lo_off = tc ? o.lo_off : 0;
+  if (tc && (!tc->out32 || !a.lo_off || !tc->w_lo_off)) { set_thread_error("umma conv: split-operand bind needs operand planes and an fp32 output"); return 1; }
   plan.enabled = true;
   return 0;
 }
@@ -403,10 +444,11 @@ int try_halo(UmmaContext& ctx, UmmaConvPlan& plan, View a, int F, const View* a2
   else pw = 16;
   const int bhh = bh + yh;
   if (loads > 4 || bhh > 256 || bf > 256) return 0;
-  // experimental TMA-fed epilogue (SSNB_EPI_TMA=1) for data gradients: a ring of 3 x (old-gradient + activation chunk) at the
+  // TMA-fed epilogue for data gradients (default; SSNB_EPI_TMA=0 keeps the register-prefetch epilogue -- measured on B200,
+  // round 2: 9.82 vs 10.00 ms per training step, 0 mismatching launches in tools/umma_diag.py): a ring of 3 x (old-gradient + activation chunk) at the
   // top of the staging area; the operand rings get what is left
   const char* te = getenv("SSNB_EPI_TMA");
-  const bool want_ring = te && te[0] == '1' && !p.bias && !p.relu;
+  const bool want_ring = !(te && te[0] == '0') && !p.bias && !p.relu && !p.out_f32;
   constexpr int EPI_STAGE = 2 * 128 * 128, EPI_STAGES = 3;
   int pipe = UMMA_V2_PIPE_BYTES - (want_ring ? EPI_STAGES * EPI_STAGE : 0);
   bool ring = want_ring;
@@ -452,11 +494,17 @@ retry_without_ring:
     cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)pw, (cuuint32_t)bf, (cuuint32_t)bhh};
     return encode(ctx, m, 4, reinterpret_cast<__half*>(v.base) + v.coff, dims, str, box);
   };
+  auto lo_of = [](View v) { v.base = reinterpret_cast<char*>(v.base) + v.lo_off; return v; };
   if (int rc = encode_a(&plan.tmap_a, a, p.K1)) { plan.enabled = false; return rc; }
-  if (p.kchunks_a1 != p.kchunks) { if (int rc = encode_a(&plan.tmap_a2, *a2, p.K - p.K1)) { plan.enabled = false; return rc; } }
-  else plan.tmap_a2 = plan.tmap_a;
+  plan.tmap_a_lo = plan.tmap_a;
+  if (a.lo_off) if (int rc = encode_a(&plan.tmap_a_lo, lo_of(a), p.K1)) { plan.enabled = false; return rc; }
+  if (p.kchunks_a1 != p.kchunks) {
+    if (int rc = encode_a(&plan.tmap_a2, *a2, p.K - p.K1)) { plan.enabled = false; return rc; }
+    plan.tmap_a2_lo = plan.tmap_a2;
+    if (a2->lo_off) if (int rc = encode_a(&plan.tmap_a2_lo, lo_of(*a2), p.K - p.K1)) { plan.enabled = false; return rc; }
+  } else { plan.tmap_a2 = plan.tmap_a; plan.tmap_a2_lo = plan.tmap_a_lo; }
   p.epi_stages = 0; p.epi_stage_bytes = 0; plan.epi_maps_ready = false; plan.epi_mask_ready = false;
-  if (ring) {                                               // experimental TMA-fed epilogue: [128 rows][64 ch] boxes of the output view
+  if (ring) {                                               // TMA-fed epilogue: [128 rows][64 ch] boxes of the output view
     p.epi_stages = EPI_STAGES; p.epi_stage_bytes = EPI_STAGE;
     plan.epi_box[0] = bw; plan.epi_box[1] = bf; plan.epi_box[2] = bh; plan.epi_F = F;
     cuuint64_t od[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.OW, (cuuint64_t)F, (cuuint64_t)p.OH};
@@ -473,6 +521,10 @@ retry_without_ring:
     cuuint64_t bs[2] = {plan.b_strides[0], plan.b_strides[1]};
     cuuint32_t bb[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)b_rows, (cuuint32_t)b_taps};
     if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(plan.b_ptr), bd, bs, bb)) { plan.enabled = false; return rc; }
+    plan.tmap_b_lo = plan.tmap_b;
+    if (plan.b_lo_off)
+      if (int rc = encode(ctx, &plan.tmap_b_lo, 3, reinterpret_cast<__half*>(reinterpret_cast<char*>(const_cast<__half*>(plan.b_ptr)) + plan.b_lo_off), bd, bs, bb)) {
+        plan.enabled = false; return rc; }
   }
   return 0;
 }
@@ -489,21 +541,21 @@ void umma_context_init(UmmaContext& ctx, bool fp16) { ctx.active = fp16; }
 void umma_context_destroy(UmmaContext&) {}
 
 int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int ntaps,
-                        const int* dy, const int* dx, const __half* w_tap_n_k, const float* bias, int relu) {
-  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, ntaps, 1, w_tap_n_k)) return rc;
+                        const int* dy, const int* dx, const __half* w_tap_n_k, const float* bias, int relu, const UmmaTcOpts* tc) {
+  if (int rc = bind_common(ctx, plan, in, out, F, cin, cout, ntaps, 1, w_tap_n_k, 1, tc)) return rc;
   for (int t = 0; t < ntaps; ++t) { plan.p.tap_dy[t] = dy[t]; plan.p.tap_dx[t] = dx[t]; }
   plan.p.bias = bias; plan.p.relu = relu; plan.p.accumulate = 0;
   return try_halo(ctx, plan, in, F);
 }
 
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
-                       int stride, const __half* w_tap_n_k, const float* bias) {
+                       int stride, const __half* w_tap_n_k, const float* bias, const UmmaTcOpts* tc) {
   // a stride-2 layer (k=3, pad=1): tiles over OUTPUT pixels whose A boxes step over the input with TMA element
   // stride 2 (default), or the stride-1 convolution sampled at even pixels (4x redundant MMAs, SSNB_TMA_STRIDED=0)
   const char* st = getenv("SSNB_TMA_STRIDED");           // default on; "0" falls back to the sampled-epilogue variant
   const bool strided = stride == 2 && !(st && st[0] == '0');
-  if (int rc = strided ? bind_common(ctx, plan, in, out, F, cin, cout, k * k, 1, w_tap_n_k, 2)
-                       : bind_common(ctx, plan, in, out, F, cin, cout, k * k, stride, w_tap_n_k)) return rc;
+  if (int rc = strided ? bind_common(ctx, plan, in, out, F, cin, cout, k * k, 1, w_tap_n_k, 2, tc)
+                       : bind_common(ctx, plan, in, out, F, cin, cout, k * k, stride, w_tap_n_k, 1, tc)) return rc;
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = r - pad; plan.p.tap_dx[r * k + s] = s - pad; }
   plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;
@@ -511,9 +563,9 @@ int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, 
 }
 
 int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
-                         const __half* w_tap_k_n, int accumulate) {
+                         const __half* w_tap_k_n, int accumulate, const UmmaTcOpts* tc) {
   // dx[p, ci] = sum_{r,s,co} dz[p + (pad-r, pad-s), co] * W[co][ci][r][s] : K = cout, N = cin
-  if (int rc = bind_common(ctx, plan, dz, dx, F, cout, cin, k * k, 1, w_tap_k_n)) return rc;
+  if (int rc = bind_common(ctx, plan, dz, dx, F, cout, cin, k * k, 1, w_tap_k_n, 1, tc)) return rc;
   for (int r = 0; r < k; ++r)
     for (int s = 0; s < k; ++s) { plan.p.tap_dy[r * k + s] = pad - r; plan.p.tap_dx[r * k + s] = pad - s; }
   plan.p.bias = nullptr; plan.p.relu = 0; plan.p.accumulate = accumulate;
@@ -563,7 +615,7 @@ int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, V
 void umma_conv_set_mask(UmmaContext& ctx, UmmaConvPlan& plan, View y) {
   plan.mask_y = reinterpret_cast<const __half*>(y.base); plan.mask_pitch = y.pitch; plan.mask_coff = y.coff;
   plan.epi_mask_ready = false;
-  if (plan.epi_maps_ready) {                                 // experimental TMA-fed epilogue: the activation tiles come through TMA too
+  if (plan.epi_maps_ready) {                                 // TMA-fed epilogue: the activation tiles come through TMA too
     cuuint64_t d[4] = {(cuuint64_t)plan.p.Cout, (cuuint64_t)y.W, (cuuint64_t)plan.epi_F, (cuuint64_t)y.H};
     cuuint64_t st[3] = {(cuuint64_t)y.pitch * 2, (cuuint64_t)y.H * y.W * y.pitch * 2, (cuuint64_t)y.W * y.pitch * 2};
     cuuint32_t b[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)plan.epi_box[0], (cuuint32_t)plan.epi_box[1], (cuuint32_t)plan.epi_box[2]};
@@ -583,9 +635,10 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
   static const int ablate = [] { const char* e = getenv("SSNB_ABLATE"); return e ? atoi(e) : 0; }();     // timing experiments only
   p.ablate = ablate;
   if (p.v2) return umma_conv_v2_launch(ctx, plan, p, s);
+  if (p.out_f32 && (p.mask_y || p.n_split < p.Cout || p.out_stride != 1)) { set_thread_error("umma conv: the fp32 epilogue has no mask / second destination / sampling"); return 3; }
   const int total = p.tiles_w * p.tiles_h * p.tiles_f * p.n_tiles;
   const int grid = total < ctx.num_sms ? total : ctx.num_sms;
-  umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, p);
+  umma_conv_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_b, plan.tmap_a_lo, plan.tmap_a2_lo, plan.tmap_b_lo, p);
   SSNB_LAUNCH_CHECK("umma_conv_kernel");
   return 0;
 }

@@ -57,12 +57,21 @@ struct UmmaConvParams {
   int tap_aoff[UMMA_MAX_TAPS];    // byte offset of each tap's view inside the A stage
   // data gradient that is the LAST writer of its output: fuse dz = dy * (y > 0), y = activation of the same value
   const __half* mask_y; int mask_pitch, mask_coff;
+  // SSNB_EXACT_TC (error-compensated split operands): nseg = 3 runs every K chunk three times,
+  //   (A_lo, B_hi), (A_hi, B_lo), (A_hi, B_hi), into the same TMEM accumulator; nseg = 1 is the plain fp16 product.
+  // out_f32: the epilogue works in fp32 -- out32 = alpha * acc (+ bias, ReLU | + old out32) -- and, when out_hi is set,
+  // also writes the result's fp16 hi / lo operand planes (same pitch / channel offset, lo plane out_lo_off bytes later).
+  int nseg, out_f32;
+  float alpha;
+  float* out32; __half* out_hi; long long out_lo_off;
 };
 
 struct UmmaConvPlan {
   bool enabled = false;
   const __half* mask_y = nullptr; int mask_pitch = 0, mask_coff = 0;   // applied only when launched with mask=true
   CUtensorMap tmap_a, tmap_a2, tmap_b;
+  CUtensorMap tmap_a_lo, tmap_a2_lo, tmap_b_lo;   // SSNB_EXACT_TC: LO planes of the three operands (copies of the HI maps otherwise)
+  long long b_lo_off = 0;                        // byte offset of the LO weight plane (0: single plane)
   CUtensorMap tmap_old, tmap_y;   // experimental TMA-fed epilogue: output (old gradient) and mask-activation tiles, [128 rows][64 ch] boxes
   bool epi_maps_ready = false, epi_mask_ready = false;
   int epi_box[3] = {0, 0, 0}, epi_F = 0;     // box {W, F, H} extents and frame count for encoding tmap_y when the mask is attached
@@ -71,17 +80,21 @@ struct UmmaConvPlan {
   UmmaConvParams p;
 };
 
+// SSNB_EXACT_TC binding options: split weights (LO plane `w_lo_off` bytes after the HI plane), fp32 output view `out32`
+// (the bind call's own out/dx view then names the fp16 HI plane of the result, lo_off its LO plane; base == nullptr: no
+// planes are written), accumulator scale alpha
+struct UmmaTcOpts { long long w_lo_off = 0; float* out32 = nullptr; float alpha = 1.0f; };
 void umma_context_init(UmmaContext& ctx, bool fp16);
 void umma_context_destroy(UmmaContext& ctx);
 // forward convolution plan (stride 1): in/out views, weights wd = [tap][cout][cin] fp16
 int umma_conv_bind_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int k, int pad,
-                       int stride, const __half* w_tap_n_k, const float* bias);
+                       int stride, const __half* w_tap_n_k, const float* bias, const UmmaTcOpts* tc = nullptr);
 // generic tap table variant (conv1 in space-to-depth form: 16 taps of a 4x4 stride-1 convolution)
 int umma_conv_bind_taps(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out, int F, int cin, int cout, int ntaps,
-                        const int* dy, const int* dx, const __half* w_tap_n_k, const float* bias, int relu);
+                        const int* dy, const int* dx, const __half* w_tap_n_k, const float* bias, int relu, const UmmaTcOpts* tc = nullptr);
 // data-gradient plan (stride 1): dz/dx gradient views, weights wf = [tap][cin][cout] fp16
 int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx, int F, int cin, int cout, int k, int pad,
-                         const __half* w_tap_k_n, int accumulate);
+                         const __half* w_tap_k_n, int accumulate, const UmmaTcOpts* tc = nullptr);
 // fused forward of sibling 1x1 convs: one input view, weights [n1+n2][cin] (rows stacked), columns [0,n1) -> out1, rest -> out2
 int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out1, View out2, int F, int cin, int n1, int n2,
                              const __half* w_n_k, const float* bias);
@@ -117,10 +130,12 @@ struct UmmaWgradParams {
   int run_len, run_stride;        // halo: the CTA's taps are one run of equally spaced views taken by a single MMA (N = run_len*64)
   int x_box_bytes, x_box_tx, x_sbo, halo_x0, halo_y0, tap_xoff[UMMA_MAX_TAPS];   // box stride in smem / bytes one box delivers
   float* partial;
+  int nseg;                       // 3: SSNB_EXACT_TC, every pixel tile runs (dz_lo, x_hi), (dz_hi, x_lo), (dz_hi, x_hi)
 };
 struct UmmaWgradPlan {
   bool enabled = false;
   CUtensorMap tmap_dz, tmap_x;
+  CUtensorMap tmap_dz_lo, tmap_x_lo;              // SSNB_EXACT_TC: LO planes (View::lo_off of the bound views)
   UmmaWgradParams p;
 };
 // returns the number of splits chosen through *splits (the caller sizes `partial` from it)

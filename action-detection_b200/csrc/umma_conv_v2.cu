@@ -21,6 +21,7 @@
 
 #include "umma_conv.cuh"
 #include "umma_dev.cuh"
+#include "umma_epi32.cuh"
 
 namespace ssnb {
 namespace {
@@ -72,29 +73,6 @@ __device__ __forceinline__ void mma_lohi(uint32_t d, uint32_t alo, uint32_t ahi,
   if (PAIR) umma_f16_lohi_pair(d, alo, ahi, blo, bhi, idesc, acc); else umma_f16_lohi(d, alo, ahi, blo, bhi, idesc, acc);
 }
 
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction per thread per 16 fp16 columns instead of two
-// 128-bit ones -- the scattered row accesses of the epilogue are bound by LSU wavefronts, not bytes
-struct U8 { uint32_t v[8]; };
-__device__ __forceinline__ U8 ldg256(const void* p) {
-  U8 r;
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ U8 ldg256_nc(const void* p) {
-  U8 r;
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void stg256(void* p, const U8& a) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]),
-               "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7])
-               : "memory");
-}
-
 // one 16-column chunk of an accumulator row: bias / accumulate / ReLU / ReLU-gradient mask, fp16 store (32 bytes)
 template <bool HAS_BIAS>
 __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint32_t* r, const float4* bias, __half* dst, const U8& old,
@@ -134,17 +112,21 @@ __device__ __forceinline__ void store_chunk(const UmmaConvParams& p, const uint3
 
 // register budget: 10 warps on 4 sub-partitions = 3 warps on one of them, 16384 / (3 * 32) = 170 -> ptxas caps at 168
 // (a __maxnreg__(200) build compiles but cannot launch); two prefetch buffers fit, three spill
-// EPI selects the epilogue: 0 default; 1 data-gradient specialisation (SSNB_EPI_DEEP=1: no bias / ReLU code, three
-// register prefetch buffers); 2 TMA-fed (SSNB_EPI_TMA=1: an eleventh warp streams the old-gradient / activation tiles
-// of every 64-column chunk into a shared-memory ring with TMA, the epilogue warps read them with conflict-free LDS
-// instead of scattered global loads).  Variants 1 and 2 are experimental: written in round 1 after the GPU budget was
-// spent, not yet run.  The default instantiations' SASS is unchanged by their presence (same instruction counts).
+// EPI selects the epilogue: 0 register-prefetch (forward; data gradients under SSNB_EPI_TMA=0); 2 TMA-fed (data gradients
+// that read the old gradient / the mask activation: an eleventh warp streams those tiles of every 64-column chunk into a
+// shared-memory ring with TMA, the epilogue warps read them with conflict-free LDS instead of scattered global loads;
+// validated and measured on B200 in round 2: -0.18 ms per training step).
+// EPI == 3: SSNB_EXACT_TC.  The producer walks every K chunk three times -- (A_lo, B_hi), (A_hi, B_lo), (A_hi, B_hi): the
+// error-compensated fp16 product, ~22 significand bits per operand -- and the epilogue works in fp32 (out32 = alpha * acc
+// + bias, ReLU | + old) and emits the result's own hi / lo operand planes for the consuming convolutions.
 template <bool PAIR, int NTAPS, int EPI>
 __global__ void __launch_bounds__(EPI == 2 ? NUM_THREADS + 32 : NUM_THREADS, 1)
 umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_old,
-                    const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ UmmaConvParams p) {
-  constexpr bool DG = EPI == 1, TMAE = EPI == 2;
+                    const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_a_lo,
+                    const __grid_constant__ CUtensorMap tmap_a2_lo, const __grid_constant__ CUtensorMap tmap_b_lo,
+                    const __grid_constant__ UmmaConvParams p) {
+  constexpr bool TMAE = EPI == 2, TC = EPI == 3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
@@ -177,6 +159,11 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    if (TC) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b_lo)) : "memory");
+    }
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * EPI_WARPS); }
     if (TMAE) {
@@ -213,22 +200,25 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int w0 = it.mw * p.bw + p.halo_x0, h0 = it.mh * p.bh + p.halo_y0;
       const int f0 = (PAIR ? 2 * it.mq + (int)rank : it.mq) * p.bf;
       const int n0 = it.nt * p.block_n + (PAIR ? (int)rank * rows_b : 0);
+      const int nseg = TC ? p.nseg : 1;
+      for (int seg = 3 - nseg; seg < 3; ++seg)
       for (int kc = 0; kc < p.kchunks; ++kc) {
+        const CUtensorMap* bmap = (TC && seg == 1) ? &tmap_b_lo : &tmap_b;
         mbar_wait(&a_empty[as], aph ^ 1);
         if (el) {
           uint8_t* sa = smem + as * p.a_stage_bytes;
           const bool src1 = kc < p.kchunks_a1;
-          const CUtensorMap* map = src1 ? &tmap_a : &tmap_a2;
+          const CUtensorMap* map = (TC && seg == 0) ? (src1 ? &tmap_a_lo : &tmap_a2_lo) : (src1 ? &tmap_a : &tmap_a2);
           const int c0 = (src1 ? kc : kc - p.kchunks_a1) * BLOCK_K;
           if (PAIR) {
             if (leader) mbar_expect_tx(&a_full[as], ONE_RING ? a_tx + b_tx : a_tx);
             const uint32_t bar = mapa_shared(smem_u32(&a_full[as]), 0);
             for (int l = 0; l < p.a_loads; ++l) tma_load_4d_pair(sa + l * p.a_load_bytes, map, bar, c0, w0 + p.a_load_dx[l], f0, h0);
-            if (ONE_RING) tma_load_3d_pair(smem_b + as * p.b_stage_bytes, &tmap_b, bar, kc * BLOCK_K, n0, 0);
+            if (ONE_RING) tma_load_3d_pair(smem_b + as * p.b_stage_bytes, bmap, bar, kc * BLOCK_K, n0, 0);
           } else {
             mbar_expect_tx(&a_full[as], ONE_RING ? a_tx + b_tx : a_tx);
             for (int l = 0; l < p.a_loads; ++l) tma_load_4d(sa + l * p.a_load_bytes, map, &a_full[as], c0, w0 + p.a_load_dx[l], f0, h0);
-            if (ONE_RING) tma_load_3d(smem_b + as * p.b_stage_bytes, &tmap_b, &a_full[as], kc * BLOCK_K, n0, 0);
+            if (ONE_RING) tma_load_3d(smem_b + as * p.b_stage_bytes, bmap, &a_full[as], kc * BLOCK_K, n0, 0);
           }
         }
         if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1; }
@@ -239,10 +229,10 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               uint8_t* sb = smem_b + bs * p.b_stage_bytes;
               if (PAIR) {
                 if (leader) mbar_expect_tx(&b_full[bs], b_tx);
-                tma_load_3d_pair(sb, &tmap_b, mapa_shared(smem_u32(&b_full[bs]), 0), kc * BLOCK_K, n0, g * p.b_taps);
+                tma_load_3d_pair(sb, bmap, mapa_shared(smem_u32(&b_full[bs]), 0), kc * BLOCK_K, n0, g * p.b_taps);
               } else {
                 mbar_expect_tx(&b_full[bs], b_tx);
-                tma_load_3d(sb, &tmap_b, &b_full[bs], kc * BLOCK_K, n0, g * p.b_taps);
+                tma_load_3d(sb, bmap, &b_full[bs], kc * BLOCK_K, n0, g * p.b_taps);
               }
             }
             if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1; }
@@ -266,6 +256,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        const int nseg = TC ? p.nseg : 1;
+        for (int seg = 0; seg < nseg; ++seg)
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
@@ -285,7 +277,7 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const uint32_t a_lo = a_lo0 + ((uint32_t)p.tap_aoff[tap] >> 4);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                if (k < nk) mma_lohi<PAIR>(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (kc | tap | k) ? 1u : 0u);
+                if (k < nk) mma_lohi<PAIR>(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (seg | kc | tap | k) ? 1u : 0u);
             }
             b_lo += slab_lo;
             if (!ONE_RING && ++gi == btaps) {
@@ -342,7 +334,38 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (vb) q.yb = ldg256_nc(mrow + colb);
         }
       };
-      if (TMAE) {
+      if (TC) {
+        // ---- SSNB_EXACT_TC: fp32 epilogue (no software pipelining of the old-gradient reads yet) ----
+        float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
+        __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
+        if (cpar * 32 >= ncol) {                                    // narrow tile: this warp has no columns, release at once
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+        for (int c0 = cpar * 32; c0 < ncol; c0 += 64) {
+          const bool two = c0 + 16 < p.block_n;                     // warp-uniform
+          const int cola = n0 + c0, colb = cola + 16;
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr + c0, ra);
+          if (two) tmem_ld16(taddr + c0 + 16, rb);
+          tmem_ld_wait();
+          if (c0 + 64 >= p.block_n) {                               // last TMEM read of this tile: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
+            }
+          }
+          if (valid && cola < p.Cout) store_chunk32(p, ra, bias_s + c0 + it.nt * p.block_n, orow32 + cola, hrow ? hrow + cola : nullptr);
+          if (two && valid && colb < p.Cout) store_chunk32(p, rb, bias_s + c0 + 16 + it.nt * p.block_n, orow32 + colb, hrow ? hrow + colb : nullptr);
+        }
+      } else if (TMAE) {
         // ---- TMA-fed: the operands of 64-column chunk i of this tile are in ring stage `es` (old gradient at +0, activation
         //      at +16 KiB, rows in TMEM lane order, 128-byte rows with the TMA 128-byte swizzle) ----
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -393,12 +416,10 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       } else {
-        // DG (data-gradient specialisation, no bias table / ReLU code): three rotating buffers = two groups in flight;
-        // otherwise two (the bias registers of the forward path leave no room for a third under the 168-register cap)
-        constexpr int NB = DG ? 3 : 2;
+        // two rotating prefetch buffers (a third spills under the 168-register cap: measured no faster)
+        constexpr int NB = 2;
         Pre pp[NB] = {};                                               // indices are compile-time after unrolling: no register copies
         if (cpar * 32 < ncol) prefetch(cpar * 32, pp[0]);
-        if (NB == 3 && cpar * 32 + 64 < ncol) prefetch(cpar * 32 + 64, pp[1]);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -422,7 +443,7 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               __half* db2 = (colb < p.n_split ? orow : orow2) + colb;
               if (c0 + 64 * (NB - 1) < ncol) prefetch(c0 + 64 * (NB - 1), pp[(u + NB - 1) % NB]);
               float4 ba[4], bb[4];
-              if (!DG && p.bias) {
+              if (p.bias) {
   #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   ba[j] = *reinterpret_cast<const float4*>(bias_s + cola + 4 * j);
@@ -440,8 +461,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
                 }
               }
-              if (va) store_chunk<!DG>(p, ra, ba, da, pp[u].oa, pp[u].ya);
-              if (vb) store_chunk<!DG>(p, rb, bb, db2, pp[u].ob, pp[u].yb);
+              if (va) store_chunk<true>(p, ra, ba, da, pp[u].oa, pp[u].ya);
+              if (vb) store_chunk<true>(p, rb, bb, db2, pp[u].ob, pp[u].yb);
             }
           }
         }
@@ -512,7 +533,8 @@ int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, c
   } else {
     cfg.gridDim = dim3(std::min(total, num_sms));
   }
-  if (cudaLaunchKernelEx(&cfg, kern, plan.tmap_a, plan.tmap_a2, plan.tmap_b, plan.tmap_old, plan.tmap_y, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, kern, plan.tmap_a, plan.tmap_a2, plan.tmap_b, plan.tmap_old, plan.tmap_y, plan.tmap_a_lo, plan.tmap_a2_lo,
+                         plan.tmap_b_lo, p) != cudaSuccess) {
     set_thread_error(std::string("umma_conv_v2_kernel launch: ") + cudaGetErrorString(cudaGetLastError())); return 2; }
   return 0;
 }
@@ -529,14 +551,15 @@ int launch_taps(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, 
 bool umma_conv_v2_supported(int ntaps) { return ntaps == 1 || ntaps == 4 || ntaps == 9; }
 
 int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s) {
-  // experimental epilogues for data gradients whose epilogue reads global operands (old gradient / activation):
-  // SSNB_EPI_TMA=1 (plan bound with the ring: p.epi_stages > 0) or SSNB_EPI_DEEP=1
-  static const bool deep = [] { const char* e = getenv("SSNB_EPI_DEEP"); return e && e[0] == '1'; }();
+  // data gradients whose epilogue reads global operands (old gradient / activation) and whose plan was bound with the
+  // shared-memory ring (p.epi_stages > 0) take the TMA-fed epilogue
   const bool reads = !p.bias && !p.relu && (p.accumulate || p.mask_y);
-  const int epi = (reads && p.epi_stages > 0 && plan.epi_maps_ready && (!p.mask_y || plan.epi_mask_ready)) ? 2 : ((reads && deep) ? 1 : 0);
+  const int epi = p.out_f32 ? 3 : ((reads && p.epi_stages > 0 && plan.epi_maps_ready && (!p.mask_y || plan.epi_mask_ready)) ? 2 : 0);
+  if (p.out_f32 && (p.mask_y || p.n_split < p.Cout)) { set_thread_error("umma conv v2: the fp32 epilogue has no mask / second destination"); return 3; }
   int rc;
-  if (p.pair) rc = epi == 2 ? launch_taps<true, 2>(plan, p, ctx.num_sms, s) : (epi == 1 ? launch_taps<true, 1>(plan, p, ctx.num_sms, s) : launch_taps<true, 0>(plan, p, ctx.num_sms, s));
-  else rc = epi == 2 ? launch_taps<false, 2>(plan, p, ctx.num_sms, s) : (epi == 1 ? launch_taps<false, 1>(plan, p, ctx.num_sms, s) : launch_taps<false, 0>(plan, p, ctx.num_sms, s));
+  if (epi == 3) rc = p.pair ? launch_taps<true, 3>(plan, p, ctx.num_sms, s) : launch_taps<false, 3>(plan, p, ctx.num_sms, s);
+  else if (p.pair) rc = epi == 2 ? launch_taps<true, 2>(plan, p, ctx.num_sms, s) : launch_taps<true, 0>(plan, p, ctx.num_sms, s);
+  else rc = epi == 2 ? launch_taps<false, 2>(plan, p, ctx.num_sms, s) : launch_taps<false, 0>(plan, p, ctx.num_sms, s);
   if (rc) return rc;
   SSNB_LAUNCH_CHECK("umma_conv_v2_kernel");
   return 0;

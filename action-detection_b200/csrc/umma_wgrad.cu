@@ -28,6 +28,7 @@ constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
+                  const __grid_constant__ CUtensorMap tmap_dz_lo, const __grid_constant__ CUtensorMap tmap_x_lo,
                   const UmmaWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -88,6 +89,10 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     int tw = pt0 % p.tiles_w, th = (pt0 / p.tiles_w) % p.tiles_h, tf = pt0 / (p.tiles_w * p.tiles_h);
     for (int pt = pt0; pt < pt1; ++pt) {
       const int w0 = tw * p.bw, h0 = th * p.bh, f0 = tf * p.bf;
+      // SSNB_EXACT_TC (nseg = 3): the tile is staged three times, (dz_lo, x_hi), (dz_hi, x_lo), (dz_hi, x_hi)
+      for (int seg = 3 - p.nseg; seg < 3; ++seg) {
+      const CUtensorMap* mdz = seg == 0 ? &tmap_dz_lo : &tmap_dz;
+      const CUtensorMap* mx = seg == 1 ? &tmap_x_lo : &tmap_x;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (el) {
         uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -96,20 +101,21 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         if (p.halo) {
           // halo layout: tensor-map dims {C, W, F, H}; ONE x box per 64 input channels covers the tile plus the filter
           // border, every tap of this CTA is a shifted descriptor view into it
-          tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, f0, h0);
-          tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, f0, h0);
+          tma_load_4d(sa, mdz, &full_bar[stage], m0, w0, f0, h0);
+          tma_load_4d(sa + BOX_BYTES, mdz, &full_bar[stage], m0 + 64, w0, f0, h0);
           for (int b = 0; b < nboxes_b; ++b)
-            tma_load_4d(sb + b * p.x_box_bytes, &tmap_x, &full_bar[stage], n0 + b * 64, w0 + p.halo_x0, f0, h0 + p.halo_y0);
+            tma_load_4d(sb + b * p.x_box_bytes, mx, &full_bar[stage], n0 + b * 64, w0 + p.halo_x0, f0, h0 + p.halo_y0);
         } else {
-          tma_load_4d(sa, &tmap_dz, &full_bar[stage], m0, w0, h0, f0);
-          tma_load_4d(sa + BOX_BYTES, &tmap_dz, &full_bar[stage], m0 + 64, w0, h0, f0);
+          tma_load_4d(sa, mdz, &full_bar[stage], m0, w0, h0, f0);
+          tma_load_4d(sa + BOX_BYTES, mdz, &full_bar[stage], m0 + 64, w0, h0, f0);
           for (int t = 0; t < ntap; ++t)
             for (int b = 0; b < nboxes_b; ++b)
-              tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, &tmap_x, &full_bar[stage], n0 + b * 64,
+              tma_load_4d(sb + (t * nboxes_b + b) * BOX_BYTES, mx, &full_bar[stage], n0 + b * 64,
                           w0 * p.x_stride + p.tap_dx[tap0 + t], h0 * p.x_stride + p.tap_dy[tap0 + t], f0);
         }
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
       if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tf; } }
     }
   } else if (warp == 1) {
@@ -127,13 +133,14 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     const uint32_t lbo_x = p.halo ? ((uint32_t)((p.x_box_bytes >> 4) & 0x3FFF) << 16) : lbo;
     const uint32_t kstep_x = p.halo ? (uint32_t)(2 * p.x_sbo) >> 4 : kstep_lo;
     uint32_t stage = 0, phase = 0;
-    for (int pt = pt0; pt < pt1; ++pt) {
+    for (int pt = pt0; pt < pt1; ++pt)
+    for (int seg = 3 - p.nseg; seg < 3; ++seg) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t sa_lo = base_lo + stage * ((uint32_t)STAGE_BYTES >> 4);
       const uint32_t sb_lo = ((sa_lo + (A_BYTES >> 4)) & 0xFFFFu) | lbo_x;
       if (el) {
-        const uint32_t first = pt > pt0 ? 1u : 0u;
+        const uint32_t first = (pt > pt0 || seg > 3 - p.nseg) ? 1u : 0u;
         if (p.run_len > 1) {
           // the taps of this CTA form ONE run whose views are `run_stride` bytes apart: a single MMA takes them as
           // consecutive 64-channel N atoms (LBO = run_stride), so the dz tile is read once per K step instead of once
@@ -150,7 +157,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
             umma_f16_lohi(tmem_base + t * p.mma_n, sa_lo + k * kstep_lo, hi, xb_lo + k * kstep_x, hi_x, idesc, first | (uint32_t)k);
         }
         }
-        if (do_bias) {
+        if (do_bias && seg != 1) {          // column sums of dz: hi and lo planes once each (seg 1 re-stages dz_hi against x_lo)
 #pragma unroll
           for (int k = 0; k < 64 / UMMA_K; ++k)
             umma_f16_lohi(tmem_base + bias_col, sa_lo + k * kstep_lo, hi, ones_lo + k * kstep_lo, hi, idesc_bias, first | (uint32_t)k);
@@ -311,6 +318,9 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
   p.ptiles_per_split = (ptiles + splits - 1) / splits;
   p.splits = (ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
   p.partial = partial; p.bias_partial = nullptr;
+  p.nseg = (dz.lo_off && x.lo_off) ? 3 : 1;
+  if ((dz.lo_off != 0) != (x.lo_off != 0)) { set_thread_error("umma wgrad: both operands or neither must carry LO planes"); return 1; }
+  auto lo_ptr = [](const View& v) { return reinterpret_cast<__half*>(reinterpret_cast<char*>(v.base) + v.lo_off) + v.coff; };
   if (halo) {
     cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)dz.W, (cuuint64_t)F, (cuuint64_t)dz.H};
     cuuint64_t str[3] = {(cuuint64_t)dz.pitch * 2, (cuuint64_t)dz.H * dz.W * dz.pitch * 2, (cuuint64_t)dz.W * dz.pitch * 2};
@@ -320,6 +330,11 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
     cuuint64_t xs[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.H * x.W * x.pitch * 2, (cuuint64_t)x.W * x.pitch * 2};
     cuuint32_t xb[4] = {64, (cuuint32_t)pw, (cuuint32_t)p.bf, (cuuint32_t)(p.bh + (y1 - y0))};
     if (int rc = umma_encode_f16(ctx, &plan.tmap_x, 4, reinterpret_cast<__half*>(x.base) + x.coff, xd, xs, xb)) return rc;
+    plan.tmap_dz_lo = plan.tmap_dz; plan.tmap_x_lo = plan.tmap_x;
+    if (p.nseg == 3) {
+      if (int rc = umma_encode_f16(ctx, &plan.tmap_dz_lo, 4, lo_ptr(dz), dims, str, box)) return rc;
+      if (int rc = umma_encode_f16(ctx, &plan.tmap_x_lo, 4, lo_ptr(x), xd, xs, xb)) return rc;
+    }
     plan.enabled = true;
     return 0;
   }
@@ -328,12 +343,16 @@ int umma_wgrad_bind_taps(UmmaContext& ctx, UmmaWgradPlan& plan, View dz, View x,
     cuuint64_t str[3] = {(cuuint64_t)dz.pitch * 2, (cuuint64_t)dz.W * dz.pitch * 2, (cuuint64_t)dz.H * dz.W * dz.pitch * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bf};
     if (int rc = umma_encode_f16(ctx, &plan.tmap_dz, 4, reinterpret_cast<__half*>(dz.base) + dz.coff, dims, str, box)) return rc;
+    plan.tmap_dz_lo = plan.tmap_dz;
+    if (p.nseg == 3) if (int rc = umma_encode_f16(ctx, &plan.tmap_dz_lo, 4, lo_ptr(dz), dims, str, box)) return rc;
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)x.W, (cuuint64_t)x.H, (cuuint64_t)F};
     cuuint64_t str[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.W * x.pitch * 2, (cuuint64_t)x.H * x.W * x.pitch * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * x_stride), (cuuint32_t)(p.bh * x_stride), (cuuint32_t)p.bf};
     if (int rc = umma_encode_f16(ctx, &plan.tmap_x, 4, reinterpret_cast<__half*>(x.base) + x.coff, dims, str, box, x_stride)) return rc;
+    plan.tmap_x_lo = plan.tmap_x;
+    if (p.nseg == 3) if (int rc = umma_encode_f16(ctx, &plan.tmap_x_lo, 4, lo_ptr(x), dims, str, box, x_stride)) return rc;
   }
   plan.enabled = true;
   return 0;
@@ -352,7 +371,7 @@ int umma_wgrad_launch(UmmaContext& ctx, const UmmaWgradPlan& plan, cudaStream_t 
   UmmaWgradParams p = plan.p;
   p.bias_partial = bias_partial;
   dim3 grid((unsigned)(p.m_tiles * p.n_tiles * p.tap_groups), (unsigned)p.splits);
-  umma_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_dz, plan.tmap_x, p);
+  umma_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(plan.tmap_dz, plan.tmap_x, plan.tmap_dz_lo, plan.tmap_x_lo, p);
   SSNB_LAUNCH_CHECK("umma_wgrad_kernel");
   return 0;
 }

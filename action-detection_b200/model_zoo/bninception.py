@@ -31,7 +31,8 @@ class BNInception(nn.Module):
 
     # ---- engine management --------------------------------------------------------------------
     def set_precision(self, precision, grad_scale=None):
-        """precision: ssn_b200.EXACT_FP32 (fp32 SIMT) or ssn_b200.FAST_FP16 (tcgen05)."""
+        """precision: ssn_b200.EXACT_FP32 (fp32 SIMT), ssn_b200.FAST_FP16 (tcgen05, fp16 operands) or
+        ssn_b200.EXACT_TC (tcgen05, error-compensated split fp16 operands: fp32-grade results)."""
         self.precision = precision
         if grad_scale is not None:
             self.grad_scale = float(grad_scale)

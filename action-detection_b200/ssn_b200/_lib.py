@@ -16,7 +16,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-EXACT_FP32, FAST_FP16 = 0, 1
+EXACT_FP32, FAST_FP16, EXACT_TC = 0, 1, 2
 
 
 class Config(C.Structure):
@@ -71,6 +71,8 @@ SIGNATURES = {
     "ssnb_classwise_reg_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "ssnb_heads_loss_workspace_bytes": (_sz, [C.POINTER(HeadsCfg)]),
     "ssnb_heads_loss_fwd_bwd": (_i, [C.POINTER(HeadsCfg)] + [_vp] * 25),
+    "ssnb_timing_begin": (_i, [_vp]),
+    "ssnb_timing_report": (C.c_char_p, []),
     "ssnb_sgd_step": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp]),
 }
 

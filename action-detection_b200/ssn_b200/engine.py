@@ -100,11 +100,13 @@ class BackboneEngine:
         with torch.cuda.device(self.device):
             check(lib.ssnb_value_write(self.h, name.encode(), int(grad), C.c_void_p(t.data_ptr()), _stream()), self.h, "value_write")
 
-    def read(self, name, grad=False):
+    def read(self, name, grad=False, planes=False):
+        """planes=True (EXACT_TC only): hi + lo of the value's fp16 operand planes instead of the fp32 tensor."""
         c, h, w = self.value_shape(name)
         t = torch.empty(self.frames, c, h, w, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib.ssnb_value_read(self.h, name.encode(), int(grad), C.c_void_p(t.data_ptr()), _stream()), self.h, "value_read")
+            check(lib.ssnb_value_read(self.h, name.encode(), int(grad) | (2 if planes else 0), C.c_void_p(t.data_ptr()), _stream()),
+                  self.h, "value_read")
         return t
 
     def run_op(self, idx, backward=False):

@@ -24,15 +24,19 @@ enum { SSNB_OK = 0, SSNB_EINVAL = 1, SSNB_ECUDA = 2, SSNB_ESTATE = 3, SSNB_ENOSU
 /* precision modes of the backbone */
 enum {
   SSNB_EXACT_FP32 = 0, /* fp32 storage, fp32 SIMT FMA: end-to-end parity mode */
-  SSNB_FAST_FP16 = 1   /* fp16 storage, tcgen05 kind::f16 MMA with fp32 TMEM accumulators */
+  SSNB_FAST_FP16 = 1,  /* fp16 storage, tcgen05 kind::f16 MMA with fp32 TMEM accumulators */
+  SSNB_EXACT_TC = 2    /* fp32 storage; every convolution product as error-compensated split fp16 operands
+                          (x = hi + lo, three tcgen05 MMAs a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate):
+                          fp32-grade results (layer_factory.py:25-39 computes in fp32) on the tensor cores */
 };
 
 typedef struct {
   int32_t in_channels; /* 3 (RGB) or 10 (Flow 2x5), ssn_models.py:260 sample_len */
   int32_t frames;      /* F = proposals * segments processed per call */
-  int32_t precision;   /* SSNB_EXACT_FP32 | SSNB_FAST_FP16 */
+  int32_t precision;   /* SSNB_EXACT_FP32 | SSNB_FAST_FP16 | SSNB_EXACT_TC */
   int32_t training;    /* 1: keep activations + allocate gradient buffers */
-  float grad_scale;    /* power-of-two loss scale applied to dfeat in FAST mode (fp16 gradients) */
+  float grad_scale;    /* power-of-two loss scale: FAST scales dfeat (fp16 gradient storage); EXACT_TC scales the
+                          fp16 operand planes of the output gradients (fp32 gradients themselves are unscaled) */
   int32_t reserved[3];
 } ssnb_config;
 
@@ -77,6 +81,12 @@ int ssnb_value_shape(ssnb_handle h, const char* name, int* c, int* hh, int* ww);
 int ssnb_value_write(ssnb_handle h, const char* name, int grad, const float* src_nchw, void* stream);
 int ssnb_value_read(ssnb_handle h, const char* name, int grad, float* dst_nchw, void* stream);
 int ssnb_run_op(ssnb_handle h, int op, int backward, void* stream);
+/* Per-launch device timing for the roofline figures (bench.py): ssnb_timing_begin opens a session on the calling thread
+ * (every library launch then records a CUDA event on its stream); ssnb_timing_report closes it, waits for the last
+ * launch and returns lines "kernel\tphase\tlaunches\tms\talgorithmic_flop\n" aggregated by kernel and pass
+ * (phase 0 forward, 1 data gradient, 2 weight gradient, 3 other).  The string is owned by the library (thread-local). */
+int ssnb_timing_begin(void* stream);
+const char* ssnb_timing_report(void);
 /* per-kernel-family launch counters since creation (bench.py's gpu_launches claim) */
 int64_t ssnb_launch_count(ssnb_handle h);
 int64_t ssnb_global_launch_count(void);

@@ -201,13 +201,21 @@ def backbone_rgb():
     return synth.synth_backbone(3, seed=0)
 
 
-def test_backbone_exact_golden(golden_dir, backbone_rgb):
-    """EXACT mode, whole backbone, 18 frames: against the reference's own output (golden)."""
+def _prec(name):
+    from ssn_b200 import _lib
+    return {"exact": _lib.EXACT_FP32, "fast": _lib.FAST_FP16, "exact_tc": _lib.EXACT_TC}[name]
+
+
+@pytest.mark.parametrize("precision", ["exact", "exact_tc"])
+def test_backbone_exact_golden(golden_dir, backbone_rgb, precision):
+    """EXACT (fp32 SIMT) and EXACT_TC (split-operand tcgen05) modes, whole backbone, 18 frames: against the
+    reference's own output (golden)."""
     dev = _cuda()
     import model_zoo
     from ops.ssn_ops import Identity
     z = _load(golden_dir, "ssn_e2e.npz")
     net = model_zoo.BNInception()
+    net.set_precision(_prec(precision), 1024.0)
     net.fc = Identity()
     _load_backbone(net, backbone_rgb, dev).eval()
     x, *_ = synth.synth_batch(2, 4, 3, seed=0)
@@ -215,10 +223,11 @@ def test_backbone_exact_golden(golden_dir, backbone_rgb):
     with torch.no_grad():
         out = net(frames)
     err = rel_l2(out, torch.tensor(z["rgb_base_out18"]))
+    print("backbone 18 frames (%s) rel-L2 vs reference golden: %.3e" % (precision, err))
     assert err < 1e-4, err     # tolerance: 1e-3 relative fp32 (north_star); measured ~1e-6
 
 
-@pytest.mark.parametrize("precision", ["exact", "fast"])
+@pytest.mark.parametrize("precision", ["exact", "exact_tc", "fast"])
 def test_backbone_per_layer(backbone_rgb, precision):
     """each op fed the ORACLE's input for that op; forward outputs and (training) backward
     gradients compared per kernel boundary.  exact: 2e-5; fast (fp16 operands, fp32 accumulate): 3e-3 rel-L2
@@ -227,7 +236,7 @@ def test_backbone_per_layer(backbone_rgb, precision):
     from ssn_b200 import _lib
     from ssn_b200.engine import BackboneEngine
     Fn = 2
-    tol = 2e-5 if precision == "exact" else 3e-3
+    tol = 3e-3 if precision == "fast" else 2e-5
     x = synth.synth_frames(Fn, 3, seed=3)
     bb = {k: v.clone() for k, v in backbone_rgb.items()}
     for k in bb:
@@ -243,7 +252,7 @@ def test_backbone_per_layer(backbone_rgb, precision):
     g = torch.Generator().manual_seed(9)
     dfeat = torch.randn(feat.shape, generator=g) * 0.01
     feat.backward(dfeat)
-    eng = BackboneEngine(3, Fn, _lib.EXACT_FP32 if precision == "exact" else _lib.FAST_FP16, True, 1024.0, dev)
+    eng = BackboneEngine(3, Fn, _prec(precision), True, 1024.0, dev)
     names = [n for (n, *_r) in O.conv_layers(3)]
     eng.pack([bb[n + ".weight"].detach().to(dev) for n in names], [bb[n + ".bias"].detach().to(dev) for n in names],
              [bb[n + "_bn.weight"].to(dev) for n in names], [bb[n + "_bn.bias"].to(dev) for n in names],
@@ -262,6 +271,10 @@ def test_backbone_per_layer(backbone_rgb, precision):
         e = rel_l2(got, taps[oname].detach())
         worst["fwd " + oname] = e
         assert e < tol, ("fwd", oname, e)
+        if precision == "exact_tc":
+            # the fp16 hi/lo operand planes the next convolution reads carry the fp32 value to ~2^-22
+            ep = rel_l2(eng.read(oname, planes=True), got)
+            assert ep < 2e-6, ("planes", oname, ep)
         # backward of this op: feed oracle activations (already there) and oracle output-gradient
         gout = taps[oname].grad
         eng.write(oname, taps[oname].detach().to(dev))            # the op's true output (ReLU mask source)
@@ -319,8 +332,9 @@ def _oracle_single_op(bb, kind, oname, xin):
     raise KeyError(oname)
 
 
-def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
-    """whole SSN, B=2 videos (144 frames), EXACT mode, through the reference-shaped module surface
+@pytest.mark.parametrize("precision", ["exact", "exact_tc"])
+def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb, precision):
+    """whole SSN, B=2 videos (144 frames), EXACT / EXACT_TC mode, through the reference-shaped module surface
     and the reference's training-loop calls (ssn_train.py:207-236): outputs, losses and every
     gradient against the oracle (itself pinned to the reference by tests/golden/ssn_e2e.npz)."""
     dev = _cuda()
@@ -336,6 +350,7 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
         sd[k].copy_(v)
     model = model.to(dev)
     model.train()
+    model.set_precision(_prec(precision), 1024.0)
     x, sc, tgt, rtgt, ptype = synth.synth_batch(2, K, 3, seed=0)
     outs = model(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
     act, act_t, comp, comp_t, reg, reg_l, reg_t = outs
@@ -373,7 +388,7 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
         ref = bbo[n_[len("base_model."):]].grad if n_.startswith("base_model.") else hdo[n_].grad
         errs[n_] = rel_l2(p.grad, ref)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-    print("e2e exact grad rel-L2 vs live fp32 oracle, worst:", worst)
+    print("e2e %s grad rel-L2 vs live fp32 oracle, worst:" % precision, worst)
     # Noise floor: the same oracle in float64.  A ReLU whose pre-activation is ~1e-5 from zero flips
     # between any two fp32 evaluation orders and changes that layer's gradient by O(1/sqrt(#active));
     # the fp32 reference itself is therefore only ~1e-2 from the true gradient below the first few
@@ -395,7 +410,7 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
         return (num / den) ** 0.5
     ours64 = agg(lambda n_: params[n_].grad)
     ref64 = agg(lambda n_: (bbo[n_[len("base_model."):]] if n_.startswith("base_model.") else hdo[n_]).grad)
-    print("e2e exact aggregate gradient rel-L2 vs float64 oracle: ours %.3e, fp32 reference %.3e" % (ours64, ref64))
+    print("e2e %s aggregate gradient rel-L2 vs float64 oracle: ours %.3e, fp32 reference %.3e" % (precision, ours64, ref64))
     assert ours64 <= 2.0 * ref64 + 1e-4, (ours64, ref64)
     for n_ in ("activity_fc.weight", "completeness_fc.weight", "regressor_fc.weight"):
         assert errs[n_] < 1e-3, (n_, errs[n_])
@@ -404,6 +419,7 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
     model2 = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
     model2.load_state_dict(model.state_dict())
     model2 = model2.to(dev).train()
+    model2.set_precision(_prec(precision), 1024.0)
     losses = model2.fused_step(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
     np.testing.assert_allclose(losses.cpu().numpy(), [la.item(), lc.item(), lr.item(), loss.item()], rtol=1e-5)
     p2 = dict(model2.named_parameters())
@@ -412,7 +428,8 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb):
             assert rel_l2(p2[n_].grad, p.grad) < 1e-4, n_
 
 
-def test_flow_forward_exact(golden_dir):
+@pytest.mark.parametrize("precision", ["exact", "exact_tc"])
+def test_flow_forward_exact(golden_dir, precision):
     dev = _cuda()
     import ssn_models
     z = _load(golden_dir, "ssn_e2e.npz")
@@ -426,6 +443,7 @@ def test_flow_forward_exact(golden_dir):
     for k, v in hd.items():
         sd[k].copy_(v)
     model = model.to(dev).train()
+    model.set_precision(_prec(precision), 1024.0)
     x, sc, tgt, rtgt, ptype = synth.synth_batch(2, K, 10, seed=0)
     with torch.no_grad():
         outs = model(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))

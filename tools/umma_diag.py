@@ -18,6 +18,9 @@ def rel(a, b):
 
 def main():
     Fn = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+    # mode "tc": SSNB_EXACT_TC (split-operand tcgen05) against the fp32 SIMT kernels, bar 2e-5; default: FAST vs SIMT fp16
+    tc = len(sys.argv) > 2 and sys.argv[2] == "tc"
+    prec, bar = (_lib.EXACT_TC, 2e-5) if tc else (_lib.FAST_FP16, 2e-3)
     dev = torch.device("cuda:0")
     bb = synth.synth_backbone(3, seed=0, calib_frames=2)
     names = [n for (n, *_r) in O.conv_layers(3)]
@@ -25,7 +28,7 @@ def main():
 
     def make(disable):
         os.environ["SSNB_DISABLE_UMMA"] = "1" if disable else "0"
-        e = BackboneEngine(3, Fn, _lib.FAST_FP16, True, 1024.0, dev)
+        e = BackboneEngine(3, Fn, prec, True, 1024.0, dev)
         e.pack([bb[n + ".weight"].to(dev) for n in names], [bb[n + ".bias"].to(dev) for n in names],
                [bb[n + "_bn.weight"].to(dev) for n in names], [bb[n + "_bn.bias"].to(dev) for n in names],
                [bb[n + "_bn.running_mean"].to(dev) for n in names], [bb[n + "_bn.running_var"].to(dev) for n in names])
@@ -55,9 +58,9 @@ def main():
             print("FWD %s: CUDA error %s" % (oname, ex)); return
         a, b = umma.read(oname), simt.read(oname)
         r = rel(a, b)
-        tag = "ok " if r < 2e-3 else "BAD"
+        tag = "ok " if r < bar else "BAD"
         print("%s fwd   %-34s cin %4d cout %4d k%d hw %3d  rel %.3e" % (tag, oname, ci, co, k, h, r))
-        if r >= 2e-3:
+        if r >= bar:
             bad += 1
             d = (a - b).abs()
             print("    err by 16-ch group:", [round(float(d[:, j:j + 16].mean()), 4) for j in range(0, co, 16)][:24])
@@ -80,16 +83,17 @@ def main():
             print("DGRAD %s: CUDA error %s" % (oname, ex)); return
         a, b = umma.read(iname, grad=True), simt.read(iname, grad=True)
         r = rel(a, b)
-        tag = "ok " if r < 2e-3 else "BAD"
+        tag = "ok " if r < bar else "BAD"
         print("%s dgrad %-34s rel %.3e" % (tag, oname, r))
-        if r >= 2e-3:
+        if r >= bar:
             bad += 1
         ci_ = names.index(oname[:-3])
         a, b = grads[id(umma)][0][ci_], grads[id(simt)][0][ci_]
         r = rel(a, b)
-        tag = "ok " if r < 2e-3 else "BAD"
+        wbar = 2e-4 if tc else bar        # tc: two fp32 reductions over F*H*W pixels in different orders (both ~1e-5 from exact at F=160)
+        tag = "ok " if r < wbar else "BAD"
         print("%s wgrad %-34s rel %.3e  |ref| %.3e |got| %.3e" % (tag, oname, r, float(b.abs().mean()), float(a.abs().mean())))
-        if r >= 2e-3:
+        if r >= wbar:
             bad += 1
             d = (a - b).abs()
             print("    err by tap:", [round(float(d[:, :, t // k, t % k].mean() / (b.abs().mean() + 1e-30)), 3) for t in range(k * k)])
