@@ -69,7 +69,7 @@ template <typename T> int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 // dW_ref[co][ci][r][s] = mult[co] * sum_splits partial ; mult = bn_scale * 1/loss_scale
 int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
                           float out_scale, float* dw_ref, int accumulate, cudaStream_t s, const float* bias_partial = nullptr,
-                          float* db = nullptr);
+                          float* db = nullptr, int* flag = nullptr);    // flag: set to 1 when a summed partial is inf / NaN
 template <typename T>
 int launch_bias_grad(const void* dz, int rows, int C, int pitch, int coff, const float* mult, float out_scale,
                      float* partial, int splits, float* db, int accumulate, cudaStream_t s);
@@ -93,7 +93,7 @@ template <typename T> int launch_fill_zero(View v, int F, cudaStream_t s);
 template <typename T>
 int launch_pack_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* mean,
                      const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
-                     cudaStream_t s);
+                     cudaStream_t s, float* absmax = nullptr);   // absmax (optional, zeroed by the caller): max |folded weight|
 
 // one launch finalises the weight (and bias) gradients of many layers: split-K partial reduction in fixed order,
 // BN-fold chain rule, 1/loss-scale, reference layout [co][ci][tap]
@@ -102,7 +102,7 @@ struct FinalizeEntry {
   const float* partial; const float* mult; float* dw; const float* bias_partial; float* db;
   int splits, taps, Cout, Cin, block0, pad_;
 };
-struct FinalizeTable { int n, total_blocks; FinalizeEntry e[FIN_MAX]; };
+struct FinalizeTable { int n, total_blocks; int* flag; FinalizeEntry e[FIN_MAX]; };
 int launch_wgrad_finalize_all(const FinalizeTable& t, float out_scale, int accumulate, cudaStream_t s);
 
 // FAST-mode vectorised glue (glue_fp16.cu)
@@ -118,10 +118,18 @@ int launch_pool_mask_bias_h8(View dz, View y, View dpool, int F, int k, int stri
 //   hi = fp16(x * scale), lo = fp16(x * scale - float(hi))  =>  hi + lo carries ~22 significand bits of x * scale
 // `flag` (device int, may be null) is set to 1 when |x * scale| exceeds the fp16 range (loss-scale overflow)
 int launch_split_view(View src_f32, int F, float scale, View planes, int* flag, cudaStream_t s);
-int launch_split_flat(const float* src, long long n, __half* hi, __half* lo, cudaStream_t s);
+// weights: planes of src * 2^e with 2^e = 8192 / 2^ceil(log2(*absmax)) (so that the LO plane stays a normal fp16 number for
+// every weight within ~2^-13 of the largest); thread 0 writes 2^-e to *inv_scale (the consuming kernels' alpha_dev)
+int launch_split_flat(const float* src, long long n, __half* hi, __half* lo, const float* absmax, float* inv_scale, cudaStream_t s);
 int launch_planes_to_nchw(View planes, int F, float scale, float* dst, cudaStream_t s);
 int launch_nhwc_to_s2d_split(View src_f32, int F, __half* dst_hi, long long lo_off, int Cs, cudaStream_t s);
 int launch_nchw_to_s2d_split(const float* src, int F, int Cin, int H, int W, __half* dst_hi, long long lo_off, int Cs, cudaStream_t s);
+// SSNB_EXACT_TC vectorised fp32 glue (glue_fp32.cu); `*_planes` views (base == nullptr: none) receive the fp16 hi/lo operand planes
+int launch_maxpool_fwd_f4(View src, View dst, View dst_planes, int F, int k, int stride, int pad, uint8_t* argmax, cudaStream_t s);
+int launch_maxpool_bwd_f4(View dsrc, View ddst, int F, int k, int stride, int pad, const uint8_t* argmax, int accumulate, cudaStream_t s);
+int launch_avgpool3_f4(View src, View dst, View dst_planes, int F, int accumulate, cudaStream_t s);
+int launch_mask_bias_split_f4(View dy, View y, View planes, float scale, int write_f32, int* flag, int F, const float* mult, float out_scale,
+                              float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
 // FAST-mode layout helpers (s2d_glue.cu)
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s);

@@ -97,7 +97,7 @@ struct Op {
   int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
   int fuse_block = -1;
 };
-struct PackedConv { size_t wf, wd, bias, scale; size_t wf16 = 0, wd16 = 0, wplane = 0; };   // EXACT_TC: fp16 hi planes of wf / wd, lo = hi + wplane
+struct PackedConv { size_t wf, wd, bias, scale; size_t wf16 = 0, wd16 = 0, wplane = 0, wmax = 0; };   // EXACT_TC: fp16 hi planes of wf / wd, lo = hi + wplane
 // the 1x1 convolutions of one inception block that read the block input (1x1, 3x3_reduce, double_3x3_reduce)
 struct FusedBlock {
   int op1 = -1, op_r3 = -1, op_rd = -1;   // op indices (op1 = -1 for 3c/4e)
@@ -119,7 +119,7 @@ struct ssnb_engine {
   size_t esz = 4;
   size_t up_plane = 0, s2d_plane = 0, s2d_w_plane = 0;
   int* tc_flag = nullptr;           // device int: set when a split pass saw |x * grad_scale| beyond the fp16 range
-  size_t tc_flag_off = 0;
+  size_t tc_flag_off = 0, wmax_off = 0;
   std::vector<ConvSpec> convs;
   std::vector<Buffer> bufs;
   std::vector<Value> vals;
@@ -255,8 +255,8 @@ static void plan(ssnb_engine* e) {
       b.hoff = off; off += 2 * b.plane;
       if (e->cfg.training) { b.ghoff = off; off += 2 * b.plane; }
     }
-    e->tc_flag_off = off; off = align_up(off + 256, 1024);
   }
+  e->tc_flag_off = off; off = align_up(off + 256, 1024);      // gradient overflow flag (every mode)
   for (Op& o : e->ops)
     if (o.kind == OP_MAXPOOL) {
       const Buffer& ob = e->bufs[e->vals[o.out_val].buf];
@@ -276,6 +276,11 @@ static void plan(ssnb_engine* e) {
       e->packed[i].wf16 = off; off += 2 * e->packed[i].wplane;
       e->packed[i].wd16 = off; off += 2 * e->packed[i].wplane;
     }
+  }
+  if (e->tc) {      // per layer: [0] max |folded weight| (atomicMax target, zeroed before every pack), [1] 1 / plane scale (the kernels' alpha_dev)
+    e->wmax_off = off;
+    for (size_t i = 0; i < e->convs.size(); ++i) e->packed[i].wmax = off + i * 8;
+    off = align_up(off + e->convs.size() * 8, 1024);
   }
   // backward bookkeeping: accumulate flags + split-K sizing
   size_t pmax = 0;
@@ -409,6 +414,12 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
     return umma_conv_launch(e->umma_ctx, o.umma, s);
   }
   tag_next(0, 0.0);
+  if (e->tc && (o.kind == OP_MAXPOOL || o.kind == OP_AVGPOOL) && e->bufs[e->vals[o.out_val].buf].plane) {
+    // vectorised fp32 pooling that also emits the output's operand planes (glue_fp32.cu)
+    const View in = e->view(o.in_val, false), out = e->view(o.out_val, false), pl = e->planes(o.out_val, false);
+    if (o.kind == OP_MAXPOOL) return launch_maxpool_fwd_f4(in, out, pl, e->F, o.k, o.stride, o.pad, (uint8_t*)(e->ws + o.argmax_off), s);
+    return launch_avgpool3_f4(in, out, pl, e->F, 0, s);
+  }
   if (int rc = run_fwd_impl(e, o, input_nchw, feat, s)) return rc;
   return (e->tc && o.out_val >= 0) ? tc_split_value(e, o.out_val, false, 1.0f, s) : 0;
 }
@@ -467,12 +478,14 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if (full && e->fp16 && e->fold_pools && o.folded_into_conv) return 0;      // gathered by the producer conv's mask+bias pass
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
     const uint8_t* am = (const uint8_t*)(e->ws + o.argmax_off);
+    if (e->tc && din.C % 4 == 0) return launch_maxpool_bwd_f4(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s);
     if (e->fp16 && din.C % 8 == 0) return launch_maxpool_bwd_h8(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s);
     return DISPATCH(e, launch_maxpool_bwd<float>(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s),
                     launch_maxpool_bwd<__half>(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s));
   }
   if (o.kind == OP_AVGPOOL) {
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
+    if (e->tc && din.C % 4 == 0) return launch_avgpool3_f4(dout, din, View(), F, o.grad_accumulate, s);
     if (e->fp16 && din.C % 8 == 0) return launch_avgpool3_h8(dout, din, F, o.grad_accumulate, s);
     return DISPATCH(e, launch_avgpool3_fwd<float>(dout, din, F, o.grad_accumulate, s),
                     launch_avgpool3_fwd<__half>(dout, din, F, o.grad_accumulate, s));
@@ -489,16 +502,17 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
   if (e->tc) {
     // EXACT_TC: fp32 mask + bias gradient (as EXACT), then dz * grad_scale as hi/lo planes for the tensor-core products
     const float gst = e->cfg.grad_scale;
-    if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
-    if (dbp) {
-      int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
-      if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f, bpartial, bs, dbp, e->grad_accumulate, s))) return rc;
-    }
     const bool want_w = e->dw.size() && e->dw[o.conv];
     const bool want_x = e->vals[o.in_val].name != "data" && !skip_dgrad;
     const bool tc_w = want_w && o.umma_wgrad.enabled, tc_x = want_x && o.umma_dgrad.enabled;
-    if (tc_w || tc_x)
-      if ((rc = tc_split_value(e, o.out_val, true, gst, s))) return rc;
+    {
+      // one pass over dy: ReLU mask, bias-gradient column sums and the hi/lo planes of dz * grad_scale; the masked fp32 dz is
+      // written back only when a SIMT kernel will read it
+      const bool need_f32 = (want_w && !tc_w) || (want_x && !tc_x) || !full;
+      View pl = (tc_w || tc_x) ? e->planes(o.out_val, true) : View();
+      if ((rc = launch_mask_bias_split_f4(dy, y, pl, gst, need_f32 ? 1 : 0, e->tc_flag, F, scale, 1.0f, bpartial, (1024 * 512 - 64) / y.C, dbp,
+                                          e->grad_accumulate, s))) return rc;
+    }
     if (tc_x && c.stride == 2 && o.conv != 0) {              // dz at input resolution (zero-upsampled), both planes
       const View dzp = e->planes(o.out_val, true);
       View lo = dzp; lo.base = (char*)dzp.base + dzp.lo_off;
@@ -560,7 +574,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, bp))) return rc;
     if (full && e->fold_pools && o.conv != 0) { e->pending_finalize.push_back((int)(&o - e->ops.data())); rc = 0; }   // batched at the end of the backward
     else if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s);
-    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s, bp, dbp);
+    else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gs, e->dw[o.conv], e->grad_accumulate, s, bp, dbp, e->tc_flag);
     if (rc) return rc;
   } else if (e->dw.size() && e->dw[o.conv]) {
     WgradArgs w;
@@ -647,12 +661,12 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
   if (((uintptr_t)dev_ptr) % 1024) return h->fail(SSNB_EINVAL, "workspace must be 1024-byte aligned");
   h->ws = (char*)dev_ptr;
   h->weights_ready = false;
-  if (h->fp16 && cudaMemset(h->ws + h->bpartial_off, 0, 256) != cudaSuccess) { cudaGetLastError(); /* no device (CPU-only planning) */ }
+  if ((h->fp16 || h->tc) && cudaMemset(h->ws + h->bpartial_off, 0, 256) != cudaSuccess) { cudaGetLastError(); /* no device (CPU-only planning) */ }
+  h->tc_flag = (int*)(h->ws + h->tc_flag_off);
+  if (cudaMemset(h->tc_flag, 0, 256) != cudaSuccess) cudaGetLastError();
   if (h->tc) {
     // SSNB_EXACT_TC: split-operand plans over the hi/lo planes.  SSNB_DISABLE_UMMA=1 leaves every convolution on the fp32
     // SIMT kernels (= SSNB_EXACT_FP32 arithmetic; what the tensor-core launches are diffed against).
-    h->tc_flag = (int*)(h->ws + h->tc_flag_off);
-    if (cudaMemset(h->tc_flag, 0, 256) != cudaSuccess) cudaGetLastError();
     const char* dis_tc = getenv("SSNB_DISABLE_UMMA");
     const bool use_tc = !(dis_tc && dis_tc[0] == '1');
     const char* disw_tc = getenv("SSNB_DISABLE_UMMA_WGRAD");
@@ -672,7 +686,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
         View xs; xs.base = h->ws + h->s2d_off; xs.H = 112; xs.W = 112; xs.C = Ck; xs.pitch = Ck; xs.coff = 0; xs.lo_off = (long long)h->s2d_plane;
         int dy[4], dx[4];
         for (int t = 0; t < 4; ++t) { dy[t] = t - 2; dx[t] = 0; }
-        UmmaTcOpts t; t.w_lo_off = (long long)h->s2d_w_plane; t.out32 = (float*)out32.base; t.alpha = 1.0f;
+        UmmaTcOpts t; t.w_lo_off = (long long)h->s2d_w_plane; t.out32 = (float*)out32.base; t.alpha = 1.0f; t.alpha_dev = (const float*)(h->ws + pk.wmax) + 1;
         rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, h->planes(o.out_val, false), h->F, Ck, c.cout, 4, dy, dx,
                                  (const __half*)(h->ws + h->s2d_w_off), (const float*)(h->ws + pk.bias), 1, &t);
         if (rc) return h->fail(rc, "tc conv1 bind: " + ssnb::thread_error());
@@ -685,7 +699,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
         continue;
       }
       if (c.cin % 8 != 0 || c.k * c.k > UMMA_MAX_TAPS) continue;
-      UmmaTcOpts t; t.w_lo_off = (long long)pk.wplane; t.out32 = (float*)out32.base; t.alpha = 1.0f;
+      UmmaTcOpts t; t.w_lo_off = (long long)pk.wplane; t.out32 = (float*)out32.base; t.alpha = 1.0f; t.alpha_dev = (const float*)(h->ws + pk.wmax) + 1;
       rc = umma_conv_bind_fwd(h->umma_ctx, o.umma, h->planes(o.in_val, false), h->planes(o.out_val, false), h->F, c.cin, c.cout, c.k, c.pad,
                               c.stride, (const __half*)(h->ws + pk.wd16), (const float*)(h->ws + pk.bias), &t);
       if (rc) return h->fail(rc, "tc bind_fwd(" + c.id + "): " + ssnb::thread_error());
@@ -694,7 +708,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       const View in = h->view(o.in_val, false);
       if (c.stride == 2) { dz.base = h->ws + h->up_off; dz.H = in.H; dz.W = in.W; dz.C = c.cout; dz.pitch = c.cout; dz.coff = 0; dz.lo_off = (long long)h->up_plane; }
       View dxp = h->planes(o.in_val, true); dxp.base = nullptr; dxp.lo_off = 0;          // data gradients: fp32 only (masked and split by their consumer)
-      UmmaTcOpts tg; tg.w_lo_off = (long long)pk.wplane; tg.out32 = (float*)h->view(o.in_val, true).base; tg.alpha = 1.0f / gs;
+      UmmaTcOpts tg; tg.w_lo_off = (long long)pk.wplane; tg.out32 = (float*)h->view(o.in_val, true).base; tg.alpha = 1.0f / gs; tg.alpha_dev = (const float*)(h->ws + pk.wmax) + 1;
       rc = umma_conv_bind_dgrad(h->umma_ctx, o.umma_dgrad, dz, dxp, h->F, c.cin, c.cout, c.k, c.pad, (const __half*)(h->ws + pk.wf16),
                                 o.grad_accumulate, &tg);
       if (rc) return h->fail(rc, "tc bind_dgrad(" + c.id + "): " + ssnb::thread_error());
@@ -824,6 +838,7 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                       const float* const* beta, const float* const* mean, const float* const* var, void* stream) {
   if (!h || !h->ws) return h ? h->fail(SSNB_ESTATE, "set_workspace first") : SSNB_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
+  if (h->tc && cudaMemsetAsync(h->ws + h->wmax_off, 0, h->convs.size() * 8, s) != cudaSuccess) return h->fail(SSNB_ECUDA, "pack_weights: memset");
   for (size_t i = 0; i < h->convs.size(); ++i) {
     const ConvSpec& c = h->convs[i];
     const PackedConv& p = h->packed[i];
@@ -832,12 +847,14 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                                                 (float*)(h->ws + p.scale), s)
                      : launch_pack_conv<float>(w[i], b[i], gamma[i], beta[i], mean[i], var[i], c.cout, c.cin, c.k,
                                                (float*)(h->ws + p.wf), (float*)(h->ws + p.wd), (float*)(h->ws + p.bias),
-                                               (float*)(h->ws + p.scale), s);
+                                               (float*)(h->ws + p.scale), s, h->tc ? (float*)(h->ws + p.wmax) : nullptr);
     if (rc) return h->fail(rc, "pack_weights(" + c.id + "): " + ssnb::thread_error());
     if (h->tc) {     // hi/lo fp16 planes of the folded fp32 weights, both kernel layouts
       const long long n = (long long)c.cout * c.cin * c.k * c.k;
-      if ((rc = launch_split_flat((const float*)(h->ws + p.wf), n, (__half*)(h->ws + p.wf16), (__half*)(h->ws + p.wf16 + p.wplane), s)) ||
-          (rc = launch_split_flat((const float*)(h->ws + p.wd), n, (__half*)(h->ws + p.wd16), (__half*)(h->ws + p.wd16 + p.wplane), s)))
+      const float* wmax = (const float*)(h->ws + p.wmax);
+      float* winv = (float*)(h->ws + p.wmax) + 1;
+      if ((rc = launch_split_flat((const float*)(h->ws + p.wf), n, (__half*)(h->ws + p.wf16), (__half*)(h->ws + p.wf16 + p.wplane), wmax, winv, s)) ||
+          (rc = launch_split_flat((const float*)(h->ws + p.wd), n, (__half*)(h->ws + p.wd16), (__half*)(h->ws + p.wd16 + p.wplane), wmax, winv, s)))
         return h->fail(rc, "pack_weights split(" + c.id + "): " + ssnb::thread_error());
     }
   }
@@ -944,7 +961,7 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
   };
   auto finalize = [&]() -> int {
     const float gs = h->fp16 ? h->cfg.grad_scale : 1.0f;
-    FinalizeTable t; t.n = 0; t.total_blocks = 0;
+    FinalizeTable t; t.n = 0; t.total_blocks = 0; t.flag = h->tc_flag;
     auto flush = [&]() -> int { int rc = launch_wgrad_finalize_all(t, 1.0f / gs, h->grad_accumulate, s); t.n = 0; t.total_blocks = 0; return rc; };
     for (int oi : h->pending_finalize) {
       const Op& o = h->ops[oi];
@@ -1029,6 +1046,18 @@ int ssnb_run_op(ssnb_handle h, int op, int backward, void* stream) {
   if (o.kind == OP_GPOOL) return h->fail(SSNB_ENOSUPPORT, "run_op: global_pool runs through backbone_fwd/bwd");
   int rc = backward ? run_bwd(h, o, nullptr, (cudaStream_t)stream) : run_fwd(h, o, nullptr, nullptr, (cudaStream_t)stream);
   return rc ? h->fail(rc, o.id + ": " + ssnb::thread_error()) : SSNB_OK;
+}
+
+int ssnb_grad_overflow(ssnb_handle h, int clear) {
+  // did a gradient leave the fp16 range under the loss scale since the last clear?  EXACT_TC: an operand plane saw
+  // |dz * grad_scale| > 65504 or NaN; FAST: a weight-gradient sum came out inf / NaN (fp16 gradient storage overflowed).
+  // Synchronises the device (one 4-byte read).
+  if (!h) return -1;
+  if (!h->tc_flag) return 0;
+  int v = 0;
+  if (cudaMemcpy(&v, h->tc_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (v && clear) cudaMemset(h->tc_flag, 0, sizeof(int));
+  return v ? 1 : 0;
 }
 
 int ssnb_timing_begin(void* stream) {

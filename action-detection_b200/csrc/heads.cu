@@ -86,6 +86,160 @@ __global__ void gpool_stpp_kernel(const T* __restrict__ src, int HW, int C, int 
   course[p * C + c] = s / (float)(pt.chi - pt.clo);
 }
 
+
+// ---- vectorised STPP (S <= SMAX segments per proposal, D % 4 == 0) --------------------------------------------------
+// One thread owns 4 features of one proposal: the S segment vectors are loaded ONCE (S independent 16-byte loads in
+// flight) and every pyramid part + the course feature is formed from registers in the reference's order (sequential sum
+// over the part's segments, / len, / norm, * scaling: ops/ssn_ops.py:49-64), then stored as 16-byte vectors.  Algorithmic
+// traffic only: 61,448 B per proposal for (1,(1,2),1) at D = 1024; the scalar kernel above re-read
+// every segment once per part that contains it.
+template <int SMAX>
+__global__ void stpp_fwd_v4_kernel(const float* __restrict__ ft, const float* __restrict__ scaling, int n, int S, int D,
+                                   PartTable pt, float* __restrict__ course, float* __restrict__ stpp) {
+  const int D4 = D / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * D4) return;
+  const int d = (int)(i % D4) * 4;
+  const long long p = i / D4;
+  const float* row = ft + (p * S) * D + d;
+  float4 v[SMAX];
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t)
+    if (t < S) v[t] = __ldg(reinterpret_cast<const float4*>(row + (long long)t * D));
+  const float s0 = scaling[p * 2], s1 = scaling[p * 2 + 1];
+  auto part = [&](int lo, int hi) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t)
+      if (t < S && t >= lo && t < hi) { s.x += v[t].x; s.y += v[t].y; s.z += v[t].z; s.w += v[t].w; }
+    const float len = (float)(hi - lo);             // 0/0 = NaN for an empty part, like torch
+    return make_float4(s.x / len, s.y / len, s.z / len, s.w / len);
+  };
+  for (int q = 0; q < pt.n; ++q) {
+    float4 m = part(pt.lo[q], pt.hi[q]);
+    const float nm = (float)pt.norm[q];
+    m.x /= nm; m.y /= nm; m.z /= nm; m.w /= nm;
+    if (pt.col[q] >= 0) { const float sc = pt.col[q] == 0 ? s0 : s1; m.x *= sc; m.y *= sc; m.z *= sc; m.w *= sc; }
+    *reinterpret_cast<float4*>(stpp + (p * pt.n + q) * D + d) = m;
+  }
+  *reinterpret_cast<float4*>(course + p * D + d) = part(pt.clo, pt.chi);
+}
+
+// backward: every part gradient is loaded once, each of the S segment gradients is formed in the scalar kernel's order
+template <int SMAX, int PMAX>
+__global__ void stpp_bwd_v4_kernel(const float* __restrict__ dcourse, const float* __restrict__ dstpp, const float* __restrict__ scaling,
+                                   int n, int S, int D, PartTable pt, float* __restrict__ dft) {
+  const int D4 = D / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * D4) return;
+  const int d = (int)(i % D4) * 4;
+  const long long p = i / D4;
+  const float s0 = scaling[p * 2], s1 = scaling[p * 2 + 1];
+  float4 g[PMAX];
+#pragma unroll
+  for (int q = 0; q < PMAX; ++q)
+    if (q < pt.n) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(dstpp + (p * pt.n + q) * D + d));
+      if (pt.col[q] >= 0) { const float sc = pt.col[q] == 0 ? s0 : s1; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+      const float nm = (float)pt.norm[q], len = (float)(pt.hi[q] - pt.lo[q]);
+      g[q] = make_float4(v.x / nm / len, v.y / nm / len, v.z / nm / len, v.w / nm / len);
+    }
+  float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dcourse) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dcourse + p * D + d));
+    const float len = (float)(pt.chi - pt.clo);
+    gc = make_float4(v.x / len, v.y / len, v.z / len, v.w / len);
+  }
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+    if (t >= S) break;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < PMAX; ++q)
+      if (q < pt.n && t >= pt.lo[q] && t < pt.hi[q]) { a.x += g[q].x; a.y += g[q].y; a.z += g[q].z; a.w += g[q].w; }
+    if (dcourse && t >= pt.clo && t < pt.chi) { a.x += gc.x; a.y += gc.y; a.z += gc.z; a.w += gc.w; }
+    *reinterpret_cast<float4*>(dft + (p * S + t) * D + d) = a;
+  }
+}
+
+// ---- fused 7x7 global average pool (+ dropout mask) + STPP, second generation ------------------------------------------
+// CTA = (proposal, 256-channel slab), 256 threads = (16-byte channel groups of the slab) x (pixel lanes): every thread
+// accumulates its pixel subset of all S frames in registers (S x HW/lanes independent 16-byte loads, consecutive threads on
+// consecutive 16-byte chunks of a pixel row), the pixel lanes are reduced through shared memory, then thread c forms the
+// parts of channel c from the S pooled values.  Reads the 5b output exactly once with 128 x (C/256) x n CTAs in flight;
+// the first-generation kernel gave every thread a serial chain of S x HW 2-byte loads.
+template <typename T, int SMAX>
+__global__ void __launch_bounds__(256) gpool_stpp_v2_kernel(const T* __restrict__ src, int HW, int C, int pitch, int coff, int n, int S,
+                                                            const float* __restrict__ mask, const float* __restrict__ scaling, PartTable pt,
+                                                            float* __restrict__ feat, float* __restrict__ course, float* __restrict__ stpp) {
+  constexpr int VEC = 16 / sizeof(T);              // channels per 16-byte load: 8 (fp16) or 4 (fp32)
+  constexpr int G = 256 / VEC;                     // channel groups per slab: 32 / 64
+  constexpr int L = 256 / G;                       // pixel lanes: 8 / 4
+  extern __shared__ float red[];                   // [L][SMAX][256]
+  const long long p = blockIdx.x;
+  const int c0 = blockIdx.y * 256;
+  const int g = threadIdx.x % G, l = threadIdx.x / G;
+  float acc[SMAX][VEC];
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[t][j] = 0.f;
+  const bool live = c0 + g * VEC < C;
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) {
+      if (t >= S) break;
+      const T* base = src + ((p * S + t) * HW) * pitch + coff + c0 + g * VEC;
+      for (int q = l; q < HW; q += L) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(base + (long long)q * pitch));
+        if (sizeof(T) == 2) {
+          const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h[j]); acc[t][(2 * j) % VEC] += f2.x; acc[t][(2 * j + 1) % VEC] += f2.y; }
+        } else {
+          acc[t][0] += __uint_as_float(r.x); acc[t][1 % VEC] += __uint_as_float(r.y); acc[t][2 % VEC] += __uint_as_float(r.z); acc[t][3 % VEC] += __uint_as_float(r.w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) red[(l * SMAX + t) * 256 + g * VEC + j] = acc[t][j];
+  __syncthreads();
+  const int c = c0 + threadIdx.x;
+  if (c >= C) return;
+  float pooled[SMAX];
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t) {
+    float s = 0.f;
+#pragma unroll
+    for (int ll = 0; ll < L; ++ll) s += red[(ll * SMAX + t) * 256 + threadIdx.x];
+    float v = s / (float)HW;
+    if (t < S) {
+      const long long f = p * S + t;
+      if (mask) v = v * mask[f * C + c];
+      feat[f * C + c] = v;
+    }
+    pooled[t] = v;
+  }
+  for (int q = 0; q < pt.n; ++q) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t)
+      if (t < S && t >= pt.lo[q] && t < pt.hi[q]) s += pooled[t];
+    float m = s / (float)(pt.hi[q] - pt.lo[q]);
+    m = m / (float)pt.norm[q];
+    if (pt.col[q] >= 0) m = m * scaling[p * 2 + pt.col[q]];
+    stpp[(p * pt.n + q) * C + c] = m;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < SMAX; ++t)
+    if (t < S && t >= pt.clo && t < pt.chi) s += pooled[t];
+  course[p * C + c] = s / (float)(pt.chi - pt.clo);
+}
+
 // ---- STPPReorgainzed ------------------------------------------------------------------------------
 struct ReorgCfg { int nstage; int nlev[3]; int lev[3][8]; int cnt[3]; };
 
@@ -162,6 +316,30 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) y[warp] = s + (b ? b[j] : 0.f);
+}
+// test-time scores with the crop mean folded in (ssn_test.py:80-86: rst.view(num_crop, -1, D).mean(0) after test_fc):
+//   y[t, j] = b[j] + w[j, :] . (1/crops * sum_c x[c*nt + t, :])      (the mean commutes with the linear layer)
+// one CTA per tick t: phase 1 averages the crops' features into shared memory, phase 2 = one warp per output row
+__global__ void linear_cropmean_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                       int crops, int nt, int in_dim, int out_dim, float* __restrict__ y) {
+  extern __shared__ float xm[];
+  const int t = blockIdx.x;
+  const float inv = 1.0f / (float)crops;
+  for (int d = threadIdx.x; d < in_dim; d += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < crops; ++c) s += x[((long long)c * nt + t) * in_dim + d];
+    xm[d] = s * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  for (int j = warp; j < out_dim; j += nw) {
+    const float* wr = w + (long long)j * in_dim;
+    float s = 0.f;
+    for (int d = lane; d < in_dim; d += 32) s = fmaf(xm[d], __ldg(wr + d), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[(long long)t * out_dim + j] = s + (b ? b[j] : 0.f);
+  }
 }
 __global__ void linear_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, int n, int in_dim,
                                     int out_dim, float* __restrict__ dw, float* __restrict__ db) {
@@ -522,6 +700,28 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
   p[i] -= lr * b;
 }
 
+// one launch for the whole model: the flat buffer is cut into segments (one per parameter tensor) carrying their group's
+// learning rate and weight decay (ssn_train.py:391-398 lr_mult / decay_mult); the segment of an element is found by
+// binary search over the cumulative ends staged in shared memory
+constexpr int SGD_MAX_SEG = 512;
+__global__ void sgd_groups_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                                  const long long* __restrict__ seg_end, const float* __restrict__ seg_lr, const float* __restrict__ seg_wd,
+                                  int nseg, float mom, float gm) {
+  __shared__ long long s_end[SGD_MAX_SEG];
+  __shared__ float s_lr[SGD_MAX_SEG], s_wd[SGD_MAX_SEG];
+  for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_end[i] = seg_end[i]; s_lr[i] = seg_lr[i]; s_wd[i] = seg_wd[i]; }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = nseg - 1;                 // first segment whose end is > i
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_end[mid] > i) hi = mid; else lo = mid + 1; }
+  const float w = p[i];
+  const float gr = g[i] * gm + s_wd[lo] * w;
+  const float b = mom * buf[i] + gr;
+  buf[i] = b;
+  p[i] = w - s_lr[lo] * b;
+}
+
 int fill_parts(PartTable& pt, int n_parts, const int* lo, const int* hi, const int* norm, const int* col, int clo, int chi, int S) {
   if (n_parts < 1 || n_parts > MAX_PARTS) { set_thread_error("stpp: 1..32 parts supported"); return SSNB_EINVAL; }
   pt.n = n_parts;
@@ -551,8 +751,17 @@ int ssnb_stpp_fwd(const float* ft, const float* scaling, int n, int n_seg, int D
   if (int rc = fill_parts(pt, n_parts, part_lo, part_hi, part_norm, part_scale_col, course_lo, course_hi, n_seg)) return rc;
   if (n == 0) return SSNB_OK;
   const long long tot = (long long)n * D;
-  stpp_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ft, scaling, n, n_seg, D, pt, course_ft, stpp_ft);
-  SSNB_LAUNCH_CHECK("stpp_fwd_kernel");
+  const bool vec = D % 4 == 0 && ((uintptr_t)ft | (uintptr_t)course_ft | (uintptr_t)stpp_ft) % 16 == 0;
+  if (vec && n_seg <= 9) {
+    stpp_fwd_v4_kernel<9><<<(unsigned)((tot / 4 + 255) / 256), 256, 0, s>>>(ft, scaling, n, n_seg, D, pt, course_ft, stpp_ft);
+    SSNB_LAUNCH_CHECK("stpp_fwd_v4_kernel");
+  } else if (vec && n_seg <= 16) {
+    stpp_fwd_v4_kernel<16><<<(unsigned)((tot / 4 + 255) / 256), 256, 0, s>>>(ft, scaling, n, n_seg, D, pt, course_ft, stpp_ft);
+    SSNB_LAUNCH_CHECK("stpp_fwd_v4_kernel");
+  } else {
+    stpp_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(ft, scaling, n, n_seg, D, pt, course_ft, stpp_ft);
+    SSNB_LAUNCH_CHECK("stpp_fwd_kernel");
+  }
   return SSNB_OK;
 }
 
@@ -565,8 +774,17 @@ int ssnb_stpp_bwd(const float* d_course, const float* d_stpp, const float* scali
   if (int rc = fill_parts(pt, n_parts, part_lo, part_hi, part_norm, part_scale_col, course_lo, course_hi, n_seg)) return rc;
   if (n == 0) return SSNB_OK;
   const long long tot = (long long)n * n_seg * D;
-  stpp_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_course, d_stpp, scaling, n, n_seg, D, pt, d_ft);
-  SSNB_LAUNCH_CHECK("stpp_bwd_kernel");
+  const bool vec = D % 4 == 0 && ((uintptr_t)d_course | (uintptr_t)d_stpp | (uintptr_t)d_ft) % 16 == 0;
+  if (vec && n_seg <= 9 && pt.n <= 8) {
+    stpp_bwd_v4_kernel<9, 8><<<(unsigned)(((long long)n * D / 4 + 255) / 256), 256, 0, s>>>(d_course, d_stpp, scaling, n, n_seg, D, pt, d_ft);
+    SSNB_LAUNCH_CHECK("stpp_bwd_v4_kernel");
+  } else if (vec && n_seg <= 16 && pt.n <= 16) {
+    stpp_bwd_v4_kernel<16, 16><<<(unsigned)(((long long)n * D / 4 + 255) / 256), 256, 0, s>>>(d_course, d_stpp, scaling, n, n_seg, D, pt, d_ft);
+    SSNB_LAUNCH_CHECK("stpp_bwd_v4_kernel");
+  } else {
+    stpp_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_course, d_stpp, scaling, n, n_seg, D, pt, d_ft);
+    SSNB_LAUNCH_CHECK("stpp_bwd_kernel");
+  }
   return SSNB_OK;
 }
 
@@ -583,6 +801,24 @@ int ssnb_gpool_stpp_fwd(ssnb_handle h, const float* drop_mask, const float* scal
   if (int rc = fill_parts(pt, n_parts, part_lo, part_hi, part_norm, part_scale_col, course_lo, course_hi, n_seg)) return rc;
   const int n = F / n_seg;
   const long long tot = (long long)n * v.C;
+  if (n_seg <= 9 && v.C % 8 == 0 && v.pitch % 8 == 0 && v.coff % 8 == 0) {
+    // second-generation kernel: CTA = (proposal, 256-channel slab)
+    static bool attr_set[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = (size_t)(fp16 ? 8 : 4) * 9 * 256 * 4;
+    if (dev >= 0 && dev < 64 && !attr_set[dev][fp16 ? 1 : 0]) {
+      cudaError_t e = fp16 ? cudaFuncSetAttribute(gpool_stpp_v2_kernel<__half, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(gpool_stpp_v2_kernel<float, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { cudaGetLastError(); set_thread_error("gpool_stpp: cannot raise the dynamic shared memory limit"); return SSNB_ECUDA; }
+      attr_set[dev][fp16 ? 1 : 0] = true;
+    }
+    dim3 grid((unsigned)n, (unsigned)((v.C + 255) / 256));
+    if (fp16) gpool_stpp_v2_kernel<__half, 9><<<grid, 256, smem, s>>>((const __half*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
+    else gpool_stpp_v2_kernel<float, 9><<<grid, 256, smem, s>>>((const float*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
+    SSNB_LAUNCH_CHECK("gpool_stpp_v2_kernel");
+    return SSNB_OK;
+  }
   if (fp16) gpool_stpp_kernel<__half><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>((const __half*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
   else gpool_stpp_kernel<float><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>((const float*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
   SSNB_LAUNCH_CHECK("gpool_stpp_kernel");
@@ -617,6 +853,16 @@ int ssnb_linear_fwd(const float* x, const float* w, const float* b, int n, int i
   const long long warps = (long long)n * out_dim;
   linear_fwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(x, w, b, n, in_dim, out_dim, y);
   SSNB_LAUNCH_CHECK("linear_fwd_kernel");
+  return SSNB_OK;
+}
+
+int ssnb_test_fc_cropmean(const float* feat, const float* w, const float* b, int crops, int nt, int in_dim, int out_dim,
+                          float* y, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!feat || !w || !y || crops <= 0 || nt < 0 || in_dim <= 0 || in_dim > 12000 || out_dim <= 0) { set_thread_error("test_fc_cropmean: bad argument"); return SSNB_EINVAL; }
+  if (nt == 0) return SSNB_OK;
+  linear_cropmean_kernel<<<(unsigned)nt, 256, (size_t)in_dim * 4, s>>>(feat, w, b, crops, nt, in_dim, out_dim, y);
+  SSNB_LAUNCH_CHECK("linear_cropmean_kernel");
   return SSNB_OK;
 }
 
@@ -723,6 +969,17 @@ int ssnb_sgd_step(float* param, const float* grad, float* momentum_buf, size_t n
   if (n == 0) return SSNB_OK;
   sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_mult);
   SSNB_LAUNCH_CHECK("sgd_kernel");
+  return SSNB_OK;
+}
+
+int ssnb_sgd_step_groups(float* param, const float* grad, float* momentum_buf, size_t n, const int64_t* seg_end, const float* seg_lr,
+                         const float* seg_wd, int n_seg, float momentum, float grad_mult, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!param || !grad || !momentum_buf || !seg_end || !seg_lr || !seg_wd || n_seg < 1 || n_seg > SGD_MAX_SEG) { set_thread_error("sgd_groups: bad argument"); return SSNB_EINVAL; }
+  if (n == 0) return SSNB_OK;
+  sgd_groups_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(param, grad, momentum_buf, (long long)n, (const long long*)seg_end, seg_lr, seg_wd, n_seg,
+                                                              momentum, grad_mult);
+  SSNB_LAUNCH_CHECK("sgd_groups_kernel");
   return SSNB_OK;
 }
 

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
 // layout [co][ci][tap]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin,
                                       const float* __restrict__ mult, float out_scale, float* __restrict__ dw, int accumulate,
-                                      const float* __restrict__ bias_partial, float* __restrict__ db) {
+                                      const float* __restrict__ bias_partial, float* __restrict__ db, int* __restrict__ flag) {
   const long long total = (long long)taps * Cout * Cin;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (bias_partial && db && i < Cout) {          // bias gradient from the weight-gradient kernel's ones-operand accumulator
@@ -280,6 +280,7 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
   const int tap = (int)(i / ((long long)Cin * Cout));
   float s = 0.f;
   for (int sp = 0; sp < splits; ++sp) s += partial[(long long)sp * total + i];
+  if (flag && !(fabsf(s) <= 3.0e38f)) *flag = 1;         // inf / NaN: a gradient left the fp16 range under this loss scale
   float* o = dw + ((long long)co * Cin + ci) * taps + tap;
   *o = (accumulate ? *o : 0.f) + s * mult[co] * out_scale;
 }
@@ -301,6 +302,7 @@ __global__ void wgrad_finalize_all_kernel(const __grid_constant__ FinalizeTable 
   const int tap = (int)(i / ((long long)q.Cin * q.Cout));
   float s = 0.f;
   for (int sp = 0; sp < q.splits; ++sp) s += q.partial[(long long)sp * total + i];
+  if (t.flag && !(fabsf(s) <= 3.0e38f)) *t.flag = 1;
   float* o = q.dw + ((long long)co * q.Cin + ci) * q.taps + tap;
   *o = (accumulate ? *o : 0.f) + s * q.mult[co] * out_scale;
 }
@@ -366,10 +368,10 @@ template int launch_wgrad<float>(const WgradArgs&, cudaStream_t);
 template int launch_wgrad<__half>(const WgradArgs&, cudaStream_t);
 
 int launch_wgrad_finalize(const float* partial, int splits, int taps, int Cout, int Cin, const float* mult,
-                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s, const float* bias_partial, float* db) {
+                          float out_scale, float* dw_ref, int accumulate, cudaStream_t s, const float* bias_partial, float* db, int* flag) {
   const long long total = (long long)taps * Cout * Cin;
   wgrad_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(partial, splits, taps, Cout, Cin, mult,
-                                                                       out_scale, dw_ref, accumulate, bias_partial, db);
+                                                                       out_scale, dw_ref, accumulate, bias_partial, db, flag);
   SSNB_LAUNCH_CHECK("wgrad_finalize_kernel");
   return 0;
 }

@@ -170,7 +170,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ var, int Cout, int Cin, int k,
                                  T* __restrict__ wf, T* __restrict__ wd, float* __restrict__ bias_f,
-                                 float* __restrict__ scale) {
+                                 float* __restrict__ scale, float* __restrict__ absmax) {
   const int taps = k * k;
   const long long total = (long long)Cout * Cin * taps;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,14 +179,23 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
     scale[i] = s;
     bias_f[i] = (b[i] - mean[i]) * s + beta[i];
   }
-  if (i >= total) return;
-  const int tap = (int)(i % taps);
-  const int ci = (int)((i / taps) % Cin);
-  const int co = (int)(i / ((long long)taps * Cin));
-  const float s = gamma[co] / sqrtf(var[co] + 1e-5f);
-  const T v = from_f<T>(w[i] * s);
-  wf[((long long)tap * Cin + ci) * Cout + co] = v;
-  wd[((long long)tap * Cout + co) * Cin + ci] = v;
+  float av = 0.f;
+  if (i < total) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((long long)taps * Cin));
+    const float s = gamma[co] / sqrtf(var[co] + 1e-5f);
+    const float fv = w[i] * s;
+    const T v = from_f<T>(fv);
+    wf[((long long)tap * Cin + ci) * Cout + co] = v;
+    wd[((long long)tap * Cout + co) * Cin + ci] = v;
+    av = fabsf(fv);
+  }
+  if (absmax) {          // SSNB_EXACT_TC: largest folded weight of the layer (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) av = fmaxf(av, __shfl_xor_sync(0xffffffffu, av, o));
+    if (threadIdx.x % 32 == 0 && av > 0.f) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(av));
+  }
 }
 
 }  // namespace
@@ -257,9 +266,9 @@ template <typename T> int launch_fill_zero(View v, int F, cudaStream_t s) {
 template <typename T>
 int launch_pack_conv(const float* w, const float* b, const float* gamma, const float* beta, const float* mean,
                      const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
-                     cudaStream_t s) {
+                     cudaStream_t s, float* absmax) {
   const long long n = (long long)Cout * Cin * k * k;
-  pack_conv_kernel<T><<<blocks_for(n > Cout ? n : Cout), TPB, 0, s>>>(w, b, gamma, beta, mean, var, Cout, Cin, k, wf, wd, bias_f, scale);
+  pack_conv_kernel<T><<<blocks_for(n > Cout ? n : Cout), TPB, 0, s>>>(w, b, gamma, beta, mean, var, Cout, Cin, k, wf, wd, bias_f, scale, absmax);
   SSNB_LAUNCH_CHECK("pack_conv_kernel");
   return 0;
 }
@@ -275,7 +284,7 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
   template int launch_relu_mask<T>(View, View, int, cudaStream_t);                                           \
   template int launch_fill_zero<T>(View, int, cudaStream_t);                                                 \
   template int launch_pack_conv<T>(const float*, const float*, const float*, const float*, const float*,     \
-                                   const float*, int, int, int, T*, T*, float*, float*, cudaStream_t);
+                                   const float*, int, int, int, T*, T*, float*, float*, cudaStream_t, float*);
 INST(float)
 INST(__half)
 

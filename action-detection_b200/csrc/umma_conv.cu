@@ -116,6 +116,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
       // SSNB_EXACT_TC: fp32 epilogue + the result's fp16 hi / lo operand planes (umma_epi32.cuh)
       float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
       __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
+      const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
       for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
         const bool two = c0 + 16 < p.block_n;
         const int cola = t.n0 + c0, colb = cola + 16;
@@ -123,8 +124,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
         tmem_ld16(taddr + c0, ra);
         if (two) tmem_ld16(taddr + c0 + 16, rb);
         tmem_ld_wait();
-        if (valid && cola < p.Cout) store_chunk32(p, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr);
-        if (two && valid && colb < p.Cout) store_chunk32(p, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr);
+        if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr);
+        if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -391,7 +392,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   }
   plan.tmap_a2 = plan.tmap_a; plan.tmap_a2_lo = plan.tmap_a_lo;
   // SSNB_EXACT_TC: three operand segments per K chunk, fp32 epilogue (+ fp16 operand planes of the result)
-  p.nseg = tc ? 3 : 1; p.out_f32 = tc ? 1 : 0; p.alpha = tc ? tc->alpha : 1.0f;
+  p.nseg = tc ? 3 : 1; p.out_f32 = tc ? 1 : 0; p.alpha = tc ? tc->alpha : 1.0f; p.alpha_dev = tc ? tc->alpha_dev : nullptr;
   p.out32 = tc ? tc->out32 : nullptr; p.out_hi = tc ? reinterpret_cast<__half*>(o.base) : nullptr; p.out_lo_off = tc ? o.lo_off : 0;
   if (tc && (!tc->out32 || !a.lo_off || !tc->w_lo_off)) { set_thread_error("umma conv: split-operand bind needs operand planes and an fp32 output"); return 1; }
   plan.enabled = true;

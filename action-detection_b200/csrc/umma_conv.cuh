@@ -63,6 +63,7 @@ struct UmmaConvParams {
   // also writes the result's fp16 hi / lo operand planes (same pitch / channel offset, lo plane out_lo_off bytes later).
   int nseg, out_f32;
   float alpha;
+  const float* alpha_dev;         // optional device scalar multiplied into alpha (1 / the power-of-two scale of the weight planes)
   float* out32; __half* out_hi; long long out_lo_off;
 };
 
@@ -83,7 +84,7 @@ struct UmmaConvPlan {
 // SSNB_EXACT_TC binding options: split weights (LO plane `w_lo_off` bytes after the HI plane), fp32 output view `out32`
 // (the bind call's own out/dx view then names the fp16 HI plane of the result, lo_off its LO plane; base == nullptr: no
 // planes are written), accumulator scale alpha
-struct UmmaTcOpts { long long w_lo_off = 0; float* out32 = nullptr; float alpha = 1.0f; };
+struct UmmaTcOpts { long long w_lo_off = 0; float* out32 = nullptr; float alpha = 1.0f; const float* alpha_dev = nullptr; };
 void umma_context_init(UmmaContext& ctx, bool fp16);
 void umma_context_destroy(UmmaContext& ctx);
 // forward convolution plan (stride 1): in/out views, weights wd = [tap][cout][cin] fp16

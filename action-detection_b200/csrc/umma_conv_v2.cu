@@ -338,6 +338,7 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ---- SSNB_EXACT_TC: fp32 epilogue (no software pipelining of the old-gradient reads yet) ----
         float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
         __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
+        const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -362,8 +363,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
             }
           }
-          if (valid && cola < p.Cout) store_chunk32(p, ra, bias_s + c0 + it.nt * p.block_n, orow32 + cola, hrow ? hrow + cola : nullptr);
-          if (two && valid && colb < p.Cout) store_chunk32(p, rb, bias_s + c0 + 16 + it.nt * p.block_n, orow32 + colb, hrow ? hrow + colb : nullptr);
+          if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, bias_s + cola, orow32 + cola, hrow ? hrow + cola : nullptr);
+          if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, bias_s + colb, orow32 + colb, hrow ? hrow + colb : nullptr);
         }
       } else if (TMAE) {
         // ---- TMA-fed: the operands of 64-column chunk i of this tile are in ring stage `es` (old gradient at +0, activation

@@ -31,10 +31,10 @@ __device__ __forceinline__ void stg256(void* p, const U8& a) {
 
 // SSNB_EXACT_TC epilogue: one 16-column chunk of an accumulator row in fp32 -- alpha * acc (+ bias, ReLU | + old) ->
 // 64 bytes of fp32, plus the value's fp16 hi / lo operand planes (2 x 32 bytes) for the convolutions that consume it
-__device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, const uint32_t* r, const float* bias, float* dst, __half* hdst) {
+__device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, float alpha, const uint32_t* r, const float* bias, float* dst, __half* hdst) {
   float v[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * alpha;
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -33,6 +33,9 @@ class BNInception(nn.Module):
     def set_precision(self, precision, grad_scale=None):
         """precision: ssn_b200.EXACT_FP32 (fp32 SIMT), ssn_b200.FAST_FP16 (tcgen05, fp16 operands) or
         ssn_b200.EXACT_TC (tcgen05, error-compensated split fp16 operands: fp32-grade results)."""
+        if precision == _lib.FAST_FP16 and grad_scale is None and self.grad_scale == 1.0:
+            raise ValueError("FAST_FP16 stores gradients in fp16: pass an explicit power-of-two grad_scale (e.g. 4096) so small "
+                             "gradients do not underflow, and poll engine.grad_overflow() to catch overflow")
         self.precision = precision
         if grad_scale is not None:
             self.grad_scale = float(grad_scale)
@@ -47,12 +50,23 @@ class BNInception(nn.Module):
     def in_channels(self):
         return getattr(self, self._conv_names[0]).in_channels
 
+    def grad_overflow(self, clear=True):
+        """True when a gradient left the fp16 range under grad_scale in any engine since the last call (device sync)."""
+        return any([e.grad_overflow(clear) for e in self._engines.values()])
+
     def _weights_version(self):
         v = 0
         for c, b in zip(self._convs(), self._bns()):
             v += c.weight._version + c.bias._version + b.weight._version + b.bias._version \
                 + b.running_mean._version + b.running_var._version
         return (v, id(self._convs()[0].weight), self._convs()[0].weight.data_ptr())
+
+    def invalidate_packed(self):
+        """The kernels read BN-folded, re-laid-out copies of the weights.  They are refreshed automatically when a parameter's
+        Tensor._version moves (optimizer.step(), in-place ops); writes that bypass the version counter -- `p.data.copy_()`,
+        the fused SGD kernel, a raw pointer -- need this call."""
+        for eng in self._engines.values():
+            eng.packed_version = None
 
     def engine_for(self, frames, training, device):
         key = (frames, bool(training), self.precision, self.in_channels(), str(device))

@@ -64,6 +64,7 @@ SIGNATURES = {
     "ssnb_gpool_stpp_fwd": (_i, [_vp, _vp, _vp, _i, _i, _ip, _ip, _ip, _ip, _i, _i, _vp, _vp, _vp, _vp]),
     "ssnb_stpp_reorg": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp]),
     "ssnb_linear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ssnb_test_fc_cropmean": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ssnb_linear_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ssnb_ohem_hinge_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ssnb_ohem_hinge_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
@@ -71,9 +72,11 @@ SIGNATURES = {
     "ssnb_classwise_reg_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "ssnb_heads_loss_workspace_bytes": (_sz, [C.POINTER(HeadsCfg)]),
     "ssnb_heads_loss_fwd_bwd": (_i, [C.POINTER(HeadsCfg)] + [_vp] * 25),
+    "ssnb_grad_overflow": (_i, [_vp, _i]),
     "ssnb_timing_begin": (_i, [_vp]),
     "ssnb_timing_report": (C.c_char_p, []),
     "ssnb_sgd_step": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp]),
+    "ssnb_sgd_step_groups": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _i, _f, _f, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

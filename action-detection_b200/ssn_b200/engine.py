@@ -45,6 +45,7 @@ class BackboneEngine:
             check(lib.ssnb_set_workspace(self.h, C.c_void_p(self.ws_ptr), nbytes), self.h, "set_workspace")
         self.workspace_bytes = nbytes
         self.packed_version = None
+        self.generation = 0        # bumped by every forward: the saved activations belong to the latest one only
 
     def __del__(self):
         try:
@@ -67,6 +68,7 @@ class BackboneEngine:
         assert x.shape[0] == self.frames and x.shape[1] == self.in_channels and tuple(x.shape[2:]) == (224, 224), \
             "engine planned for [%d,%d,224,224], got %s" % (self.frames, self.in_channels, tuple(x.shape))
         feat = torch.empty(self.frames, 1024, dtype=torch.float32, device=x.device)
+        self.generation += 1
         with torch.cuda.device(self.device):
             check(lib.ssnb_backbone_fwd(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(feat.data_ptr()), _stream()),
                   self.h, "backbone_fwd")
@@ -116,6 +118,10 @@ class BackboneEngine:
     def bind_grads(self, dw, db):
         check(lib.ssnb_bind_grads(self.h, _lib.ptr_array(dw), _lib.ptr_array(db)), self.h, "bind_grads")
 
+    def grad_overflow(self, clear=True):
+        """EXACT_TC: True when a gradient operand plane left the fp16 range under the current grad_scale (device sync)."""
+        return lib.ssnb_grad_overflow(self.h, int(clear)) == 1
+
     def launch_count(self):
         return lib.ssnb_launch_count(self.h)
 
@@ -127,21 +133,41 @@ class BackboneFunction(torch.autograd.Function):
     With direct_grad (default) the kernels add straight into each parameter's .grad (allocating it
     when it is None), exactly what autograd's AccumulateGrad would do with returned gradients, but
     without 138 temporary tensors and 138 tiny add kernels per step; the Function then returns None
-    for the parameters.  Set BackboneFunction.direct_grad = False to get ordinary returned gradients
-    (needed for torch.autograd.grad or parameter hooks)."""
+    for the parameters.  That shortcut is only taken when it is indistinguishable from autograd: every
+    parameter is a leaf tensor without hooks (nn.DataParallel replicas are non-leaf; DDP and user code
+    register hooks) -- otherwise, or with BackboneFunction.direct_grad = False, ordinary gradients are
+    returned (also needed for torch.autograd.grad).
+
+    The engine keeps ONE set of saved activations per frame count: a second forward through the same
+    engine before this node's backward overwrites them, which is detected (generation counter) and raised."""
     direct_grad = True
 
     @staticmethod
     def forward(ctx, x, engine, n_conv, *wb):
         ctx.engine, ctx.n_conv = engine, n_conv
         ctx.params = wb
-        return engine.forward(x)
+        feat = engine.forward(x)
+        ctx.generation = engine.generation
+        return feat
+
+    @staticmethod
+    def _direct_ok(params):
+        for p in params:
+            if not p.requires_grad:
+                continue
+            if not p.is_leaf or getattr(p, "_backward_hooks", None) or getattr(p, "_post_accumulate_grad_hooks", None):
+                return False
+        return True
 
     @staticmethod
     def backward(ctx, dfeat):
         eng, n = ctx.engine, ctx.n_conv
         dev = dfeat.device
-        if BackboneFunction.direct_grad:
+        if ctx.generation != eng.generation:
+            raise RuntimeError("BNInception(B200): another forward of %d frames ran through this engine after the one being "
+                               "differentiated; its saved activations are gone.  Run backward before the next forward of the same "
+                               "shape (or use different frame counts / a second model instance)." % eng.frames)
+        if BackboneFunction.direct_grad and BackboneFunction._direct_ok(ctx.params):
             grads = []
             for p in ctx.params:
                 if not p.requires_grad:

@@ -217,6 +217,27 @@ class SSN(torch.nn.Module):
         base_out = self.base_model(self._frames(input))
         return self.test_fc(base_out), base_out
 
+    def test_scores(self, input, num_crop=10):
+        """One chunk of a test video, crop-major [num_crop * ticks, C, H, W] -> per-tick scores [ticks, D]: what the reference's
+        loop body computes as `rst, _ = net(frames, None, None, None, None); rst.view(num_crop, -1, D).mean(dim=0)`
+        (ssn_test.py:80-84), with the crop mean folded into the folded FC (one kernel, 1/num_crop of the FC work).  Unlike
+        the reference's data loader (gen_batchsize = 4 ticks -> 40-image calls, ssn_dataset.py:393) the chunk size is the
+        caller's: >= 256 frames per call keep the tensor cores busy."""
+        if self.test_fc is None:
+            raise RuntimeError("call prepare_test_fc() first (ssn_test.py:62)")
+        frames = self._frames(input)
+        F_ = frames.shape[0]
+        assert F_ % num_crop == 0, "frame count must be a multiple of the crop count"
+        nt = F_ // num_crop
+        with torch.no_grad():
+            base_out = self.base_model(frames).contiguous()          # [F, 1024]: fc is Identity / eval-mode Dropout at test time
+        out = torch.empty(nt, self.test_fc.out_features, dtype=torch.float32, device=base_out.device)
+        from ssn_b200.engine import _stream
+        with torch.cuda.device(base_out.device):
+            check(lib.ssnb_test_fc_cropmean(base_out.data_ptr(), self.test_fc.weight.data_ptr(), self.test_fc.bias.data_ptr(), num_crop, nt,
+                                            base_out.shape[1], self.test_fc.out_features, out.data_ptr(), _stream()), None, "test_fc_cropmean")
+        return out
+
     # ---- fused training step: backbone fwd -> pool+STPP -> heads+loss(+grads) -> backbone bwd ---------
     def fused_step(self, input, aug_scaling, target, reg_target, prop_type, fg_per_video=1, comp_group=7,
                    props_per_video=8, ohem_ratio=0.17, comp_w=0.1, reg_w=0.1, global_videos=None, loss_scale=1.0):
@@ -226,6 +247,11 @@ class SSN(torch.nn.Module):
         import ctypes as C
         from ssn_b200.engine import _stream
         assert self.with_regression, "fused_step implements the regression configuration"
+        if not input.is_cuda:
+            raise RuntimeError("SSN(B200).fused_step needs CUDA tensors (libssn_b200 has no CPU path)")
+        for b in self.base_model._bns():
+            if b.training:
+                raise NotImplementedError("fused_step implements bn_mode='frozen' (every BatchNorm2d in eval mode, ssn_models.py:156-174)")
         frames = self._frames(input)
         bm = self.base_model
         eng = bm.engine_for(frames.shape[0], True, frames.device)
@@ -264,9 +290,11 @@ class SSN(torch.nn.Module):
         cs = bm._convs()
         params = [c.weight for c in cs] + [c.bias for c in cs]
         for p in params:
-            if p.grad is None:
+            if p.requires_grad and p.grad is None:
                 p.grad = torch.zeros_like(p)
-        eng.backward(dft, [c.weight.grad for c in cs], [c.bias.grad for c in cs], accumulate=True)   # straight into .grad
+        # straight into .grad; parameters with requires_grad=False get no gradient (None -> the kernels skip them)
+        eng.backward(dft, [c.weight.grad if c.weight.requires_grad else None for c in cs],
+                     [c.bias.grad if c.bias.requires_grad else None for c in cs], accumulate=True)
 
         def acc(p, g):
             if p.grad is None:
@@ -274,7 +302,10 @@ class SSN(torch.nn.Module):
             else:
                 p.grad.add_(g)
         for fc, k in ((self.activity_fc, "act"), (self.completeness_fc, "comp"), (self.regressor_fc, "reg")):
-            acc(fc.weight, out["d_%s_w" % k]); acc(fc.bias, out["d_%s_b" % k])
+            if fc.weight.requires_grad:
+                acc(fc.weight, out["d_%s_w" % k])
+            if fc.bias.requires_grad:
+                acc(fc.bias, out["d_%s_b" % k])
         self.last_fused = dict(out, feat=feat, course=course, stpp=stpp)
         return out["losses"]
 

@@ -81,6 +81,11 @@ int ssnb_value_shape(ssnb_handle h, const char* name, int* c, int* hh, int* ww);
 int ssnb_value_write(ssnb_handle h, const char* name, int grad, const float* src_nchw, void* stream);
 int ssnb_value_read(ssnb_handle h, const char* name, int grad, float* dst_nchw, void* stream);
 int ssnb_run_op(ssnb_handle h, int op, int backward, void* stream);
+/* Loss-scale guard: 1 when a gradient left the fp16 range under grad_scale since the last clear (EXACT_TC: an operand plane
+ * saw |dz * grad_scale| > 65504 or NaN; FAST: a weight-gradient sum came out inf / NaN), 0 otherwise, -1 on error.
+ * Synchronises the device: poll it every N steps and skip / rescale like a dynamic loss scaler would. */
+int ssnb_grad_overflow(ssnb_handle h, int clear);
+
 /* Per-launch device timing for the roofline figures (bench.py): ssnb_timing_begin opens a session on the calling thread
  * (every library launch then records a CUDA event on its stream); ssnb_timing_report closes it, waits for the last
  * launch and returns lines "kernel\tphase\tlaunches\tms\talgorithmic_flop\n" aggregated by kernel and pass
@@ -117,6 +122,11 @@ int ssnb_stpp_reorg(const float* scores, int T, int D, const int32_t* ticks, con
 /* ---- heads: activity_fc / completeness_fc / regressor_fc (ssn_models.py:272-283) ------------- */
 int ssnb_linear_fwd(const float* x, const float* w, const float* b, int n, int in_dim, int out_dim, float* y,
                     void* stream);
+/* Test-time scores of one chunk of a video with the 10-crop mean folded into the folded FC (replaces
+ * `rst, _ = net(input); sc = rst.view(num_crop, -1, D).mean(0)`, ssn_test.py:83-84, with test_fc from
+ * SSN.prepare_test_fc, ssn_models.py:176-201): feat [crops*nt, in_dim] crop-major -> y [nt, out_dim]. */
+int ssnb_test_fc_cropmean(const float* feat, const float* w, const float* b, int crops, int nt, int in_dim, int out_dim,
+                          float* y, void* stream);
 /* dy [n,out] -> dx [n,in] (may be NULL), dw [out,in], db [out]; overwrite */
 int ssnb_linear_bwd(const float* x, const float* w, const float* dy, int n, int in_dim, int out_dim, float* dx,
                     float* dw, float* db, void* stream);
@@ -169,6 +179,13 @@ int ssnb_heads_loss_fwd_bwd(const ssnb_heads_cfg* cfg, const float* course_ft, c
  * g = grad*grad_mult + wd*p; buf = mom*buf + g; p -= lr*buf */
 int ssnb_sgd_step(float* param, const float* grad, float* momentum_buf, size_t n, float lr, float momentum,
                   float weight_decay, float grad_mult, void* stream);
+
+/* The whole model in ONE launch: the flat buffers are cut into n_seg <= 512 segments (one per parameter tensor; seg_end =
+ * cumulative element ends, device int64) with their parameter group's learning rate and weight decay (device fp32 arrays):
+ * the per-group lr_mult / decay_mult of SSN.get_optim_policies (ssn_models.py:203-251) as applied by
+ * adjust_learning_rate (ssn_train.py:391-398).  Same update rule as ssnb_sgd_step. */
+int ssnb_sgd_step_groups(float* param, const float* grad, float* momentum_buf, size_t n, const int64_t* seg_end,
+                         const float* seg_lr, const float* seg_wd, int n_seg, float momentum, float grad_mult, void* stream);
 
 #ifdef __cplusplus
 }

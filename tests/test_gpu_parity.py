@@ -201,6 +201,9 @@ def backbone_rgb():
     return synth.synth_backbone(3, seed=0)
 
 
+E2E_TOL = {"exact": 1e-4, "exact_tc": 5e-4}     # whole-network bars (north_star: 1e-3)
+
+
 def _prec(name):
     from ssn_b200 import _lib
     return {"exact": _lib.EXACT_FP32, "fast": _lib.FAST_FP16, "exact_tc": _lib.EXACT_TC}[name]
@@ -224,7 +227,9 @@ def test_backbone_exact_golden(golden_dir, backbone_rgb, precision):
         out = net(frames)
     err = rel_l2(out, torch.tensor(z["rgb_base_out18"]))
     print("backbone 18 frames (%s) rel-L2 vs reference golden: %.3e" % (precision, err))
-    assert err < 1e-4, err     # tolerance: 1e-3 relative fp32 (north_star); measured ~1e-6
+    # tolerance: 1e-3 relative fp32 (north_star).  Measured on B200: exact ~1e-6; exact_tc 2.1e-4 (per-layer 1e-6..3e-6 --
+    # 22-bit split operands, tensor-core accumulation -- amplified by the ReLU switching of 69 random layers)
+    assert err < E2E_TOL[precision], err
 
 
 @pytest.mark.parametrize("precision", ["exact", "exact_tc", "fast"])
@@ -350,7 +355,8 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb, precision):
         sd[k].copy_(v)
     model = model.to(dev)
     model.train()
-    model.set_precision(_prec(precision), 1024.0)
+    gs = float(os.environ.get("SSNB_TEST_GS", "1024"))
+    model.set_precision(_prec(precision), gs)
     x, sc, tgt, rtgt, ptype = synth.synth_batch(2, K, 3, seed=0)
     outs = model(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
     act, act_t, comp, comp_t, reg, reg_l, reg_t = outs
@@ -359,14 +365,16 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb, precision):
     lr = R.ClassWiseRegressionLoss()(reg, reg_l, reg_t)
     loss = la + 0.1 * lc + 0.1 * lr
     loss.backward()
+    for eng in model.base_model._engines.values():
+        assert not eng.grad_overflow(), "gradient operand planes overflowed fp16 under grad_scale %g" % gs
     z = _load(golden_dir, "ssn_e2e.npz")
     for name, o in zip(("act", "act_t", "comp", "comp_t", "reg", "reg_l", "reg_t"), outs):
         ref = z["rgb_" + name]
         if ref.dtype.kind == "f":
-            assert rel_l2(o.detach(), torch.tensor(ref)) < 1e-4, name
+            assert rel_l2(o.detach(), torch.tensor(ref)) < E2E_TOL[precision], name
         else:
             np.testing.assert_array_equal(o.cpu().numpy(), ref)     # index selection: bit-exact
-    np.testing.assert_allclose([la.item(), lc.item(), lr.item(), loss.item()], z["rgb_losses"], rtol=1e-4)
+    np.testing.assert_allclose([la.item(), lc.item(), lr.item(), loss.item()], z["rgb_losses"], rtol=E2E_TOL[precision])
     # gradients: against the oracle run on THIS machine with the same regenerated weights (the
     # golden gradients were produced with BN statistics calibrated on another CPU; 1e-6 weight
     # differences are amplified by the ReLU/max-pool switching of 69 random layers).  The per-layer
@@ -411,9 +419,10 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb, precision):
     ours64 = agg(lambda n_: params[n_].grad)
     ref64 = agg(lambda n_: (bbo[n_[len("base_model."):]] if n_.startswith("base_model.") else hdo[n_]).grad)
     print("e2e %s aggregate gradient rel-L2 vs float64 oracle: ours %.3e, fp32 reference %.3e" % (precision, ours64, ref64))
-    assert ours64 <= 2.0 * ref64 + 1e-4, (ours64, ref64)
+    # exact_tc: forward differs from fp32 by 2e-4 instead of 1e-6, so proportionally more ReLUs sit inside the flip band
+    assert ours64 <= (2.0 if precision == "exact" else 4.0) * ref64 + 1e-4, (ours64, ref64)
     for n_ in ("activity_fc.weight", "completeness_fc.weight", "regressor_fc.weight"):
-        assert errs[n_] < 1e-3, (n_, errs[n_])
+        assert errs[n_] < (1e-3 if precision == "exact" else 3e-3), (n_, errs[n_])
 
     # the fused step must reproduce the modular path
     model2 = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
@@ -422,6 +431,7 @@ def test_ssn_train_exact_vs_oracle(golden_dir, backbone_rgb, precision):
     model2.set_precision(_prec(precision), 1024.0)
     losses = model2.fused_step(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
     np.testing.assert_allclose(losses.cpu().numpy(), [la.item(), lc.item(), lr.item(), loss.item()], rtol=1e-5)
+    print("fused_step (%s) losses" % precision, losses.tolist())
     p2 = dict(model2.named_parameters())
     for n_, p in params.items():
         if p.grad is not None:
@@ -450,7 +460,7 @@ def test_flow_forward_exact(golden_dir, precision):
     for name, o in zip(("act", "act_t", "comp", "comp_t", "reg", "reg_l", "reg_t"), outs):
         ref = z["flow_" + name]
         if ref.dtype.kind == "f":
-            assert rel_l2(o, torch.tensor(ref)) < 1e-4, name
+            assert rel_l2(o, torch.tensor(ref)) < E2E_TOL[precision], name
         else:
             np.testing.assert_array_equal(o.cpu().numpy(), ref)
 
@@ -481,7 +491,7 @@ def test_test_forward_and_prepare_test_fc(backbone_rgb):
     assert rel_l2(scores, torch.nn.functional.linear(ref_feat, w_ref, b_ref)) < 1e-4
     # the same inference call on the tensor-core path (forward-only engine, no gradient buffers)
     from ssn_b200 import _lib
-    model.set_precision(_lib.FAST_FP16)
+    model.set_precision(_lib.FAST_FP16, 1024.0)
     with torch.no_grad():
         scores_f, base_f = model(x, None, None, None, None)
     assert rel_l2(base_f, ref_feat) < 5e-2 and rel_l2(scores_f, scores) < 5e-2
@@ -543,7 +553,7 @@ def test_fast_fused_vs_unfused_and_oracle(backbone_rgb):
     print("fast fused vs unfused: feat %.2e max dW %.2e max db %.2e | vs SIMT-fp16: feat %.2e max dW %.2e | vs fp32 oracle: feat %.2e worst dW %s"
           % (u_feat, u_w, u_b, e_feat, e_w, o_feat, o_w))
     assert u_feat < 1e-4 and u_w < 1e-2 and u_b < 1e-2
-    assert e_feat < 5e-3
+    assert e_feat < 5e-3 and e_w < 2e-2, (e_feat, e_w)          # tcgen05 vs SIMT on the same fp16 operands
     # End-to-end gradients of FAST mode on this synthetic random-weight net are dominated by ReLU / max-pool
     # decision flips (forward differs by ~1e-2 => many flips; cf. the fp32 noise floor of ~1e-2 measured in
     # test_ssn_train_exact_vs_oracle for a 1e-5 forward difference).  Reported, bounded loosely; the
@@ -591,3 +601,253 @@ def test_flow_conv1_fwd_bwd(precision):
     feat = eng.forward(x.to(dev))
     ref = O.backbone_forward(bb, x, 10)
     assert rel_l2(feat, ref) < (1e-4 if precision == "exact" else 5e-2)
+
+
+def _agg_rel(get_ours, ref_grads):
+    num = den = 0.0
+    for n_, r in ref_grads.items():
+        num += float((get_ours(n_).double().cpu() - r.double()).pow(2).sum()); den += float(r.double().pow(2).sum())
+    return (num / den) ** 0.5
+
+
+def _cos(get_ours, ref_grads):
+    dot = na = nb = 0.0
+    for n_, r in ref_grads.items():
+        a = get_ours(n_).double().cpu().flatten(); b = r.double().flatten()
+        dot += float(a @ b); na += float(a @ a); nb += float(b @ b)
+    return dot / (na * nb) ** 0.5
+
+
+@pytest.mark.parametrize("precision", ["exact_tc", "fast"])
+def test_fused_step_bench_shape(precision):
+    """What bench.py times: SSN.fused_step at the BASELINE configs[1] shape (4 videos x 8 proposals x 9 segments = 288
+    frames, K=20, STPP (1,(1,2),1)) in the benched precision modes, against the CPU oracle on the same batch: losses, the
+    fused global-pool + STPP outputs (feat / course / stpp), head logits and head gradients, and the 138 backbone
+    gradients in aggregate.  Bars: exact_tc is the parity mode (north_star 1e-3 on outputs); fast is reported with the
+    bars its fp16 operands can meet."""
+    dev = _cuda()
+    import ssn_models
+    K, V = 20, 4
+    bb = synth.synth_backbone(3, seed=0, calib_frames=2)
+    hd = synth.synth_heads(K, 5, seed=0, std=0.01, bias_std=0.05)
+    model = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+    sd = model.state_dict()
+    for k, v in bb.items():
+        sd["base_model." + k].copy_(v)
+    for k, v in hd.items():
+        sd[k].copy_(v)
+    model = model.to(dev).train()
+    model.set_precision(_prec(precision), 4096.0)
+    batch = synth.synth_batch(V, K, 3, seed=100)
+    losses = model.fused_step(*[t.to(dev) for t in batch])
+    torch.cuda.synchronize()
+    for eng in model.base_model._engines.values():
+        assert not eng.grad_overflow()
+    bbo = {k: v.clone() for k, v in bb.items()}
+    hdo = {k: v.clone() for k, v in hd.items()}
+    for d in (bbo, hdo):
+        for k in d:
+            if "_bn." not in k:
+                d[k].requires_grad_(True)
+    x, sc, tgt, rtgt, ptype = batch
+    feat_ref = O.backbone_forward(bbo, x.view(-1, 3, 224, 224), 3)
+    course_ref, stpp_ref = O.stpp_forward(feat_ref, sc.view(-1, 2), [2, 7, 9], (1, (1, 2), 1))
+    outs = O.ssn_train_forward(bbo, hdo, x, sc, tgt, rtgt, ptype)
+    oloss, (la, lc, lr) = O.total_loss(outs)
+    oloss.backward()
+    lf = model.last_fused
+    e = {"feat": rel_l2(lf["feat"], feat_ref.detach()), "course": rel_l2(lf["course"], course_ref.detach()),
+         "stpp": rel_l2(lf["stpp"], stpp_ref.detach())}
+    ref_l = np.array([la.item(), lc.item(), lr.item(), oloss.item()])
+    e["loss"] = float(np.abs(losses.cpu().numpy() - ref_l).max() / np.abs(ref_l).max())
+    params = dict(model.named_parameters())
+    head_ref = {k: v.grad for k, v in hdo.items()}
+    bb_ref = {"base_model." + k: v.grad for k, v in bbo.items() if v.grad is not None}
+    e["head_grads"] = _agg_rel(lambda n_: params[n_].grad, head_ref)
+    e["backbone_grads"] = _agg_rel(lambda n_: params[n_].grad, bb_ref)
+    e["backbone_grads_cos"] = _cos(lambda n_: params[n_].grad, bb_ref)
+    print("fused_step F=288 (%s) vs fp32 oracle: %s" % (precision, {k: "%.3e" % v for k, v in e.items()}))
+    print("fused_step F=288 (%s) losses %s oracle %s" % (precision, losses.tolist(), ref_l.tolist()))
+    bars = {"exact_tc": {"feat": 5e-4, "course": 5e-4, "stpp": 5e-4, "loss": 1e-3, "head_grads": 1e-2, "backbone_grads": 1.5e-1},
+            "fast": {"feat": 3e-2, "course": 3e-2, "stpp": 3e-2, "loss": 3e-2, "head_grads": 2e-1, "backbone_grads": 1.0}}[precision]
+    for k, b in bars.items():
+        assert e[k] < b, (k, e[k], b)
+    assert e["backbone_grads_cos"] > (0.99 if precision == "exact_tc" else 0.7), e["backbone_grads_cos"]
+
+
+@pytest.mark.parametrize("precision", ["exact", "exact_tc"])
+def test_flow_train_vs_oracle(precision):
+    """whole-net Flow (2x5-channel, conv1 with 10 input channels) forward + backward through the module surface, B=2 videos
+    (144 frames): the 7 outputs, the losses and all gradients against the CPU oracle (ssn_models.py:318-343 conv1 shape)."""
+    dev = _cuda()
+    import ssn_models
+    import ops.ssn_ops as R
+    K = 4
+    bb = synth.synth_backbone(10, seed=0)
+    hd = synth.synth_heads(K, 5, seed=0, std=0.02, bias_std=0.1)
+    model = ssn_models.SSN(K, 2, 5, 2, "Flow", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+    sd = model.state_dict()
+    for k, v in bb.items():
+        sd["base_model." + k].copy_(v)
+    for k, v in hd.items():
+        sd[k].copy_(v)
+    model = model.to(dev).train()
+    model.set_precision(_prec(precision), 1024.0)
+    x, sc, tgt, rtgt, ptype = synth.synth_batch(2, K, 10, seed=0)
+    outs = model(x.to(dev), sc.to(dev), tgt.to(dev), rtgt.to(dev), ptype.to(dev))
+    act, act_t, comp, comp_t, reg, reg_l, reg_t = outs
+    loss = torch.nn.CrossEntropyLoss()(act, act_t) + 0.1 * R.CompletenessLoss()(comp, comp_t, 1, 7) + 0.1 * R.ClassWiseRegressionLoss()(reg, reg_l, reg_t)
+    loss.backward()
+    bbo = {k: v.clone() for k, v in bb.items()}
+    hdo = {k: v.clone() for k, v in hd.items()}
+    for d in (bbo, hdo):
+        for k in d:
+            if "_bn." not in k:
+                d[k].requires_grad_(True)
+    oouts = O.ssn_train_forward(bbo, hdo, x, sc, tgt, rtgt, ptype)
+    oloss, _ = O.total_loss(oouts)
+    oloss.backward()
+    for name, o, r in zip(("act", "act_t", "comp", "comp_t", "reg", "reg_l", "reg_t"), outs, oouts):
+        if r.dtype.is_floating_point:
+            assert rel_l2(o.detach(), r.detach()) < E2E_TOL[precision], name
+        else:
+            np.testing.assert_array_equal(o.cpu().numpy(), r.numpy())
+    assert abs(loss.item() - oloss.item()) < E2E_TOL[precision] * abs(oloss.item())
+    params = dict(model.named_parameters())
+    ref = {"base_model." + k: v.grad for k, v in bbo.items() if v.grad is not None}
+    ref.update({k: v.grad for k, v in hdo.items()})
+    agg, cos = _agg_rel(lambda n_: params[n_].grad, ref), _cos(lambda n_: params[n_].grad, ref)
+    c1 = rel_l2(params["base_model.conv1_7x7_s2.weight"].grad, bbo["conv1_7x7_s2.weight"].grad)
+    print("flow e2e (%s): aggregate gradient rel-L2 vs fp32 oracle %.3e, cosine %.6f, conv1 (10-ch) dW %.3e" % (precision, agg, cos, c1))
+    # two fp32-grade evaluations of this random-weight net differ by ReLU / max-pool switching (see test_ssn_train_exact_vs_oracle)
+    assert agg < (3e-2 if precision == "exact" else 1e-1) and cos > 0.995, (agg, cos)
+
+
+def test_test_scores_cropmean(backbone_rgb):
+    """f2: SSN.test_scores (10-crop mean folded into the folded test FC, one kernel) == the reference loop body
+    `rst, _ = net(frames); rst.view(num_crop, -1, D).mean(0)` (ssn_test.py:83-84)."""
+    dev = _cuda()
+    import ssn_models
+    K, crops, nt = 4, 10, 3
+    model = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, test_mode=True, stpp_cfg=(1, (1, 2), 1))
+    hd = synth.synth_heads(K, 5, seed=1, std=0.02, bias_std=0.1)
+    sd = model.state_dict()
+    for k, v in backbone_rgb.items():
+        sd["base_model." + k].copy_(v)
+    for k, v in hd.items():
+        sd[k].copy_(v)
+    model.prepare_test_fc()
+    model = model.to(dev).eval()
+    x = synth.synth_frames(crops * nt, 3, seed=6).to(dev)
+    with torch.no_grad():
+        rst, _ = model(x, None, None, None, None)
+        ref = rst.view(crops, -1, rst.shape[1]).mean(dim=0)
+        got = model.test_scores(x, crops)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < 1e-5
+    w_ref, b_ref = O.prepare_test_fc(hd, 5)
+    feat = O.backbone_forward(backbone_rgb, x.cpu(), 3)
+    oracle = torch.nn.functional.linear(feat, w_ref, b_ref).view(crops, -1, w_ref.shape[0]).mean(dim=0)
+    assert rel_l2(got, oracle) < 1e-4
+
+
+def test_stpp_large_vs_oracle():
+    """the vectorised STPP kernels at a bandwidth-bound size (2048 proposals) and with a deep pyramid: forward and backward
+    against the oracle restatement of ops/ssn_ops.py:39-70 (part boundaries exact, values <= 1e-6)."""
+    dev = _cuda()
+    from ops.ssn_ops import StructuredTemporalPyramidPooling
+    g = torch.Generator().manual_seed(21)
+    for cfg, seg, n, D in (((1, (1, 2), 1), (2, 5, 2), 2048, 1024), (((1, 2), (1, 2, 4), 2), (4, 8, 4), 64, 256), ([1, 1, 1], (2, 5, 2), 33, 1024)):
+        S = sum(seg)
+        split = [seg[0], seg[0] + seg[1], S]
+        ft = torch.randn(n * S, D, generator=g)
+        sc = torch.rand(n, 2, generator=g)
+        fr = ft.clone().requires_grad_(True)
+        ra, rc = O.stpp_forward(fr, sc, split, cfg)
+        wa, wc = torch.randn(ra.shape, generator=g), torch.randn(rc.shape, generator=g)
+        (ra * wa).sum().add((rc * wc).sum()).backward()
+        mod = StructuredTemporalPyramidPooling(D, True, configs=cfg)
+        fd = ft.clone().to(dev).requires_grad_(True)
+        a, c = mod(fd, sc.to(dev), split)
+        ((a * wa.to(dev)).sum() + (c * wc.to(dev)).sum()).backward()
+        assert torch.allclose(a.detach().cpu(), ra.detach(), rtol=1e-6, atol=1e-6) and torch.allclose(c.detach().cpu(), rc.detach(), rtol=1e-6, atol=1e-6)
+        assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-6, atol=1e-6)
+
+
+def test_fused_sgd_matches_torch(backbone_rgb):
+    """f4: ssn_b200.optim.FusedSGD (one launch over flat buffers, per-group lr_mult / decay_mult of SSN.get_optim_policies,
+    ssn_train.py:141-144,391-398) against torch.optim.SGD on the same parameter groups, three steps with momentum."""
+    dev = _cuda()
+    import ssn_models
+    from ssn_b200.optim import FusedSGD
+    K = 4
+
+    def make():
+        m = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+        sd = m.state_dict()
+        for k, v in backbone_rgb.items():
+            sd["base_model." + k].copy_(v)
+        return m.to(dev).train()
+    torch.manual_seed(3)
+    m1 = make()
+    torch.manual_seed(3)
+    m2 = make()
+    lr, wd, mom = 0.01, 5e-4, 0.9
+    pol1 = m1.get_optim_policies()
+    groups = [{"params": g["params"], "lr": lr * g["lr_mult"], "weight_decay": wd * g["decay_mult"]} for g in pol1 if g["params"]]
+    ref = torch.optim.SGD(groups, lr=lr, momentum=mom)
+    invalidated = []
+    opt = FusedSGD(m2.get_optim_policies(), lr=lr, momentum=mom, weight_decay=wd, on_step=[lambda: invalidated.append(1), m2.base_model.invalidate_packed])
+    assert [len(g["params"]) for g in opt.param_groups] == [len(g["params"]) for g in groups]
+    g = torch.Generator().manual_seed(4)
+    p1 = [p for p in m1.parameters() if p.requires_grad]
+    p2 = [p for p in m2.parameters() if p.requires_grad]
+    assert len(p1) == len(p2) == 144
+    for step in range(3):
+        for a, b in zip(p1, p2):
+            gr = torch.randn(a.shape, generator=g).to(dev)
+            a.grad = gr.clone()
+            if step == 1:
+                b.grad = None                    # zero_grad(set_to_none=True) in the reference loop: the optimizer re-binds
+                opt.rebind_grads()
+            b.grad.copy_(gr)
+        ref.step()
+        opt.step()
+        worst = max(rel_l2(b, a) for a, b in zip(p1, p2))
+        assert worst < 1e-6, (step, worst)
+    assert len(invalidated) == 3
+    # lr schedule: adjust_learning_rate rewrites the groups' lr / weight_decay
+    for gr_, go in zip(ref.param_groups, opt.param_groups):
+        gr_["lr"] *= 0.1
+        go["lr"] *= 0.1
+    opt.refresh_groups()
+    for a, b in zip(p1, p2):
+        gr = torch.randn(a.shape, generator=g).to(dev)
+        a.grad = gr.clone(); b.grad.copy_(gr)
+    ref.step(); opt.step()
+    assert max(rel_l2(b, a) for a, b in zip(p1, p2)) < 1e-6
+
+
+def test_autograd_guards(backbone_rgb):
+    """ADVICE round 1: (a) a second forward through the same engine before backward is detected, not silently wrong;
+    (b) parameters with hooks (DDP-style) get their gradients through autograd, not the direct .grad shortcut."""
+    dev = _cuda()
+    import model_zoo
+    from ops.ssn_ops import Identity
+    net = model_zoo.BNInception()
+    net.fc = Identity()
+    _load_backbone(net, backbone_rgb, dev).eval()
+    x1, x2 = synth.synth_frames(2, 3, seed=1).to(dev), synth.synth_frames(2, 3, seed=2).to(dev)
+    o1 = net(x1)
+    o2 = net(x2)
+    with pytest.raises(RuntimeError, match="another forward"):
+        o1.sum().backward()
+    o2.sum().backward()
+    direct = net.conv1_7x7_s2.weight.grad.clone()
+    net.zero_grad()
+    seen = []
+    h = net.conv1_7x7_s2.weight.register_hook(lambda g: seen.append(float(g.abs().sum())))
+    net(x2).sum().backward()
+    h.remove()
+    assert len(seen) == 1 and seen[0] > 0
+    assert rel_l2(net.conv1_7x7_s2.weight.grad, direct) < 1e-6

@@ -19,7 +19,8 @@ sd = model.state_dict()
 for k, v in bb.items():
     sd["base_model." + k].copy_(v)
 model = model.to(dev).train()
-model.set_precision(_lib.FAST_FP16, 4096.0)
+prec = {"fast": _lib.FAST_FP16, "exact": _lib.EXACT_FP32, "exact_tc": _lib.EXACT_TC}[sys.argv[2] if len(sys.argv) > 2 else "fast"]
+model.set_precision(prec, 4096.0)
 batch = tuple(t.to(dev) for t in synth.synth_batch(4, 20, 3, seed=0))
 params = [p for p in model.parameters() if p.requires_grad]
 flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
