@@ -95,6 +95,20 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
                      const float* var, int Cout, int Cin, int k, T* wf, T* wd, float* bias_f, float* scale,
                      cudaStream_t s, float* absmax = nullptr);   // absmax (optional, zeroed by the caller): max |folded weight|
 
+// the same for many layers per launch (block0 = first CTA of the entry; 256 threads per CTA)
+constexpr int PACK_MAX = 32;
+struct PackEntry {
+  const float *w, *b, *gamma, *beta, *mean, *var;
+  void *wf, *wd; float *bias, *scale, *absmax;
+  int cout, cin, k, block0;
+};
+struct PackTable { int n, pad_; PackEntry e[PACK_MAX]; };
+template <typename T> int launch_pack_all(const PackTable& t, int total_blocks, cudaStream_t s);
+// EXACT_TC: hi/lo planes of both fp32 weight layouts of many layers per launch (scale from each layer's absmax, see launch_split_flat)
+struct SplitEntry { const float *wf, *wd; __half *wf16, *wd16; long long plane_bytes, n; const float* absmax; float* inv_scale; int block0, pad_; };
+struct SplitTable { int n, pad_; SplitEntry e[PACK_MAX]; };
+int launch_split_all(const SplitTable& t, int total_blocks, cudaStream_t s);
+
 // one launch finalises the weight (and bias) gradients of many layers: split-K partial reduction in fixed order,
 // BN-fold chain rule, 1/loss-scale, reference layout [co][ci][tap]
 constexpr int FIN_MAX = 36;
@@ -130,6 +144,8 @@ int launch_maxpool_bwd_f4(View dsrc, View ddst, int F, int k, int stride, int pa
 int launch_avgpool3_f4(View src, View dst, View dst_planes, int F, int accumulate, cudaStream_t s);
 int launch_mask_bias_split_f4(View dy, View y, View planes, float scale, int write_f32, int* flag, int F, const float* mult, float out_scale,
                               float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
+int launch_pool_mask_bias_split_f4(View dz, View y, View dpool, View planes, float scale, int write_f32, int* flag, int F, const uint8_t* argmax,
+                                   const float* mult, float out_scale, float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
 // FAST-mode layout helpers (s2d_glue.cu)
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s);

@@ -356,6 +356,16 @@ static void plan(ssnb_engine* e) {
     }
   }
   if (e->tc) {
+    for (int i = 0; i < (int)e->ops.size(); ++i) {      // convolutions whose only consumer is a k3/s2/pad0 max pool: backward gather folded in
+      Op& po = e->ops[i];
+      if (po.kind != OP_MAXPOOL || po.k != 3 || po.stride != 2 || po.pad != 0) continue;
+      int producer = -1, consumers = 0;
+      for (int j = 0; j < (int)e->ops.size(); ++j) {
+        if (e->ops[j].out_val == po.in_val && e->ops[j].kind == OP_CONV) producer = j;
+        if (e->ops[j].in_val == po.in_val) ++consumers;
+      }
+      if (producer >= 0 && consumers == 1 && e->vals[po.in_val].C % 4 == 0) { e->ops[producer].pool_consumer = i; po.folded_into_conv = true; }
+    }
     e->Cs = (4 * e->cfg.in_channels + 7) / 8 * 8;
     e->s2d_plane = align_up(F * 112 * 112 * 4 * e->Cs * 2, 1024);
     e->s2d_off = off; off += 2 * e->s2d_plane;
@@ -475,7 +485,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     return DISPATCH(e, launch_gpool_bwd<float>(dfeat, gs, din, F, ym, s), launch_gpool_bwd<__half>(dfeat, gs, din, F, ym, s));
   }
   if (o.kind == OP_MAXPOOL) {
-    if (full && e->fp16 && e->fold_pools && o.folded_into_conv) return 0;      // gathered by the producer conv's mask+bias pass
+    if (full && (e->fp16 || e->tc) && e->fold_pools && o.folded_into_conv) return 0;      // gathered by the producer conv's mask+bias pass
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
     const uint8_t* am = (const uint8_t*)(e->ws + o.argmax_off);
     if (e->tc && din.C % 4 == 0) return launch_maxpool_bwd_f4(din, dout, F, o.k, o.stride, o.pad, am, o.grad_accumulate, s);
@@ -505,7 +515,20 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     const bool want_w = e->dw.size() && e->dw[o.conv];
     const bool want_x = e->vals[o.in_val].name != "data" && !skip_dgrad;
     const bool tc_w = want_w && o.umma_wgrad.enabled, tc_x = want_x && o.umma_dgrad.enabled;
-    {
+    const bool pre = full && e->fold_pools && o.dy_premasked;      // the last writer of dy masked it and wrote its operand planes
+    const bool bias_w = pre && o.bias_in_wgrad && dbp && tc_w;     // ... and the column sums ride on the weight-gradient MMAs
+    if (pre) {
+      if (!bias_w && dbp)       // bias gradient only: column sums of the (already masked) fp32 dz, no planes, nothing written back
+        if ((rc = launch_mask_bias_split_f4(dy, y, View(), gst, 0, nullptr, F, scale, 1.0f, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
+    } else if (full && e->fold_pools && o.pool_consumer >= 0) {
+      // the consuming max pool's backward gather + ReLU mask + bias sums + planes in one pass (the fp32 dy is never materialised)
+      const Op& po = e->ops[o.pool_consumer];
+      const bool need_f32 = (want_w && !tc_w) || (want_x && !tc_x);
+      View pl = (tc_w || tc_x) ? e->planes(o.out_val, true) : View();
+      if ((rc = launch_pool_mask_bias_split_f4(dy, y, e->view(po.out_val, true), pl, gst, need_f32 ? 1 : 0, e->tc_flag, F,
+                                               (const uint8_t*)(e->ws + po.argmax_off), scale, 1.0f, bpartial, (1024 * 512 - 64) / y.C, dbp,
+                                               e->grad_accumulate, s))) return rc;
+    } else {
       // one pass over dy: ReLU mask, bias-gradient column sums and the hi/lo planes of dz * grad_scale; the masked fp32 dz is
       // written back only when a SIMT kernel will read it
       const bool need_f32 = (want_w && !tc_w) || (want_x && !tc_x) || !full;
@@ -521,8 +544,9 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     }
     if (tc_w) {
       tag_next(2, conv_flops(e, o));
-      if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, nullptr))) return rc;
-      if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gst, e->dw[o.conv], e->grad_accumulate, s);
+      if ((rc = umma_wgrad_launch(e->umma_ctx, o.umma_wgrad, s, bias_w ? (float*)(e->ws + o.bias_partial_off) : nullptr))) return rc;
+      if (full && o.conv != 0) { e->pending_finalize.push_back((int)(&o - e->ops.data())); rc = 0; }     // batched at the end of the backward
+      else if (o.conv == 0) rc = launch_wgrad_finalize_s2d(partial, o.umma_wgrad.p.splits, c.cout, c.cin, e->Cs, scale, 1.0f / gst, e->dw[o.conv], e->grad_accumulate, s);
       else rc = launch_wgrad_finalize(partial, o.umma_wgrad.p.splits, c.k * c.k, c.cout, c.cin, scale, 1.0f / gst, e->dw[o.conv], e->grad_accumulate, s);
       if (rc) return rc;
     } else if (want_w) {
@@ -536,7 +560,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
       if ((rc = launch_wgrad_finalize(partial, o.wsplits, c.k * c.k, c.cout, c.cin, scale, 1.0f, e->dw[o.conv], e->grad_accumulate, s))) return rc;
     }
     tag_next(1, conv_flops(e, o));
-    if (tc_x) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s);
+    if (tc_x) return umma_conv_launch(e->umma_ctx, o.umma_dgrad, s, full && e->fold_pools && o.dgrad_masks);
     if (want_x) {
       ConvArgs a;
       a.src = dy.base; a.SH = dy.H; a.SW = dy.W; a.Csrc = dy.C; a.src_pitch = dy.pitch; a.src_coff = dy.coff;
@@ -721,6 +745,41 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     }
     h->fold_pools = false;
     for (FusedBlock& fb : h->fused) fb.enabled = false;
+    // ReLU-mask fusion (same rule as the FAST schedule below): the consumer with the smallest forward index is the LAST writer
+    // of a value's gradient in the reverse schedule; when that is a tensor-core data gradient its fp32 epilogue applies
+    // dz = dy * (y > 0) and emits the value's gradient operand planes (dz * grad_scale), so the producing convolutions run
+    // neither a mask pass nor a split pass: their bias gradients ride on the weight-gradient MMAs (ones operand).
+    // SSNB_DISABLE_FUSION=1 keeps one mask + bias + split pass per convolution.
+    const char* disf_tc = getenv("SSNB_DISABLE_FUSION");
+    if (use_tc && h->cfg.training && !(disf_tc && disf_tc[0] == '1')) {
+      h->fold_pools = true;
+      std::vector<int> first_consumer(h->vals.size(), -1);
+      for (int i = 0; i < (int)h->ops.size(); ++i)
+        if (first_consumer[h->ops[i].in_val] < 0) first_consumer[h->ops[i].in_val] = i;
+      for (size_t v = 0; v < h->vals.size(); ++v) {
+        const int fc = first_consumer[v];
+        if (fc < 0 || h->vals[v].name == "data" || !h->bufs[h->vals[v].buf].plane) continue;
+        bool conv_made = false;                    // only buffers that hold convolution outputs have a ReLU to differentiate
+        for (const Op& q : h->ops) conv_made = conv_made || (q.kind == OP_CONV && h->vals[q.out_val].buf == h->vals[v].buf);
+        if (!conv_made) continue;
+        Op& c = h->ops[fc];
+        if (c.kind == OP_CONV && c.umma_dgrad.enabled) {
+          c.dgrad_masks = true;
+          umma_conv_set_mask_tc(c.umma_dgrad, h->view((int)v, false), h->planes((int)v, true), gs, h->tc_flag);
+        }
+      }
+      for (Op& o : h->ops) {
+        if (o.kind != OP_CONV) continue;
+        int w = o.out_val;
+        if (first_consumer[w] < 0) {               // a slice of a concat buffer: gradients are written through the whole-buffer value
+          const Value& ov = h->vals[o.out_val];
+          for (size_t v = 0; v < h->vals.size(); ++v)
+            if (h->vals[v].buf == ov.buf && h->vals[v].coff == 0 && h->vals[v].C == h->bufs[ov.buf].C && first_consumer[v] >= 0) { w = (int)v; break; }
+        }
+        if (first_consumer[w] >= 0 && h->ops[first_consumer[w]].dgrad_masks) o.dy_premasked = true;
+        o.bias_in_wgrad = o.dy_premasked && o.conv != 0 && o.umma_wgrad.enabled && o.umma_wgrad.p.taps_per_cta * o.umma_wgrad.p.mma_n + 16 <= 512;
+      }
+    }
     return SSNB_OK;
   }
   // bind tcgen05 plans (tensor maps need final addresses); SSNB_DISABLE_UMMA=1 keeps FAST mode on the SIMT kernels
@@ -839,24 +898,37 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
   if (!h || !h->ws) return h ? h->fail(SSNB_ESTATE, "set_workspace first") : SSNB_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   if (h->tc && cudaMemsetAsync(h->ws + h->wmax_off, 0, h->convs.size() * 8, s) != cudaSuccess) return h->fail(SSNB_ECUDA, "pack_weights: memset");
-  for (size_t i = 0; i < h->convs.size(); ++i) {
-    const ConvSpec& c = h->convs[i];
-    const PackedConv& p = h->packed[i];
-    int rc = h->fp16 ? launch_pack_conv<__half>(w[i], b[i], gamma[i], beta[i], mean[i], var[i], c.cout, c.cin, c.k,
-                                                (__half*)(h->ws + p.wf), (__half*)(h->ws + p.wd), (float*)(h->ws + p.bias),
-                                                (float*)(h->ws + p.scale), s)
-                     : launch_pack_conv<float>(w[i], b[i], gamma[i], beta[i], mean[i], var[i], c.cout, c.cin, c.k,
-                                               (float*)(h->ws + p.wf), (float*)(h->ws + p.wd), (float*)(h->ws + p.bias),
-                                               (float*)(h->ws + p.scale), s, h->tc ? (float*)(h->ws + p.wmax) : nullptr);
-    if (rc) return h->fail(rc, "pack_weights(" + c.id + "): " + ssnb::thread_error());
-    if (h->tc) {     // hi/lo fp16 planes of the folded fp32 weights, both kernel layouts
+  {
+    // fold + re-layout of all 69 layers in a few launches (PACK_MAX entries per launch)
+    PackTable t; t.n = 0; t.pad_ = 0;
+    SplitTable st; st.n = 0; st.pad_ = 0;
+    int blocks = 0, sblocks = 0;
+    auto flush = [&]() -> int {
+      int rc = h->fp16 ? launch_pack_all<__half>(t, blocks, s) : launch_pack_all<float>(t, blocks, s);
+      if (!rc && h->tc) rc = launch_split_all(st, sblocks, s);
+      t.n = 0; st.n = 0; blocks = 0; sblocks = 0;
+      return rc;
+    };
+    for (size_t i = 0; i < h->convs.size(); ++i) {
+      const ConvSpec& c = h->convs[i];
+      const PackedConv& p = h->packed[i];
       const long long n = (long long)c.cout * c.cin * c.k * c.k;
-      const float* wmax = (const float*)(h->ws + p.wmax);
-      float* winv = (float*)(h->ws + p.wmax) + 1;
-      if ((rc = launch_split_flat((const float*)(h->ws + p.wf), n, (__half*)(h->ws + p.wf16), (__half*)(h->ws + p.wf16 + p.wplane), wmax, winv, s)) ||
-          (rc = launch_split_flat((const float*)(h->ws + p.wd), n, (__half*)(h->ws + p.wd16), (__half*)(h->ws + p.wd16 + p.wplane), wmax, winv, s)))
-        return h->fail(rc, "pack_weights split(" + c.id + "): " + ssnb::thread_error());
+      PackEntry& q = t.e[t.n++];
+      q.w = w[i]; q.b = b[i]; q.gamma = gamma[i]; q.beta = beta[i]; q.mean = mean[i]; q.var = var[i];
+      q.wf = h->ws + p.wf; q.wd = h->ws + p.wd; q.bias = (float*)(h->ws + p.bias); q.scale = (float*)(h->ws + p.scale);
+      q.absmax = h->tc ? (float*)(h->ws + p.wmax) : nullptr;
+      q.cout = c.cout; q.cin = c.cin; q.k = c.k; q.block0 = blocks;
+      blocks += (int)((std::max<long long>(n, c.cout) + 255) / 256);
+      if (h->tc) {
+        SplitEntry& e = st.e[st.n++];
+        e.wf = (const float*)(h->ws + p.wf); e.wd = (const float*)(h->ws + p.wd);
+        e.wf16 = (__half*)(h->ws + p.wf16); e.wd16 = (__half*)(h->ws + p.wd16); e.plane_bytes = (long long)p.wplane; e.n = n;
+        e.absmax = (const float*)(h->ws + p.wmax); e.inv_scale = (float*)(h->ws + p.wmax) + 1; e.block0 = sblocks; e.pad_ = 0;
+        sblocks += (int)((n + 255) / 256);
+      }
+      if (t.n == PACK_MAX) if (int rc = flush()) return h->fail(rc, "pack_weights: " + ssnb::thread_error());
     }
+    if (int rc = flush()) return h->fail(rc, "pack_weights: " + ssnb::thread_error());
   }
   if (h->tc && h->ops.size() && h->ops[0].umma.enabled) {
     for (int pl = 0; pl < 2; ++pl) {
@@ -934,7 +1006,11 @@ int ssnb_bind_grads(ssnb_handle h, float* const* dw, float* const* db) {
 }
 
 int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float* const* db, void* stream) {
-  if (!h || !dfeat) return h ? h->fail(SSNB_EINVAL, "null argument") : SSNB_EINVAL;
+  return ssnb_backbone_bwd_range(h, dfeat, dw, db, -1, 0, stream);
+}
+
+int ssnb_backbone_bwd_range(ssnb_handle h, const float* dfeat, float* const* dw, float* const* db, int op_hi, int op_lo, void* stream) {
+  if (!h || (!dfeat && (op_hi < 0 || op_hi >= (int)h->ops.size() - 1))) return h ? h->fail(SSNB_EINVAL, "null argument") : SSNB_EINVAL;
   if (!h->cfg.training) return h->fail(SSNB_ESTATE, "engine created without training=1");
   if (!h->ws || !h->weights_ready) return h->fail(SSNB_ESTATE, "workspace/weights not set");
   ssnb_bind_grads(h, dw, db);
@@ -960,7 +1036,7 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
     return 0;
   };
   auto finalize = [&]() -> int {
-    const float gs = h->fp16 ? h->cfg.grad_scale : 1.0f;
+    const float gs = (h->fp16 || h->tc) ? h->cfg.grad_scale : 1.0f;
     FinalizeTable t; t.n = 0; t.total_blocks = 0; t.flag = h->tc_flag;
     auto flush = [&]() -> int { int rc = launch_wgrad_finalize_all(t, 1.0f / gs, h->grad_accumulate, s); t.n = 0; t.total_blocks = 0; return rc; };
     for (int oi : h->pending_finalize) {
@@ -978,7 +1054,10 @@ int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float
     if (int rc = flush()) return h->fail(rc, "finalize: " + ssnb::thread_error());
     return 0;
   };
-  if (int rc = run_range((int)h->ops.size() - 1, 0)) return rc;
+  const int last = (int)h->ops.size() - 1;
+  if (op_hi < 0 || op_hi > last) op_hi = last;
+  if (op_lo < 0 || op_lo > op_hi) return h->fail(SSNB_EINVAL, "backbone_bwd_range: bad op range");
+  if (int rc = run_range(op_hi, op_lo)) return rc;
   return finalize();
 }
 

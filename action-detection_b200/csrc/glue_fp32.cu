@@ -283,6 +283,97 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_split_f4(float* __restri
   colsum_tail(partial, counter, C, mult, out_scale, db, &is_last, accumulate);
 }
 
+// Same pass for a convolution whose only consumer is a k3/s2/pad0 max pool (conv1 -> pool1, conv2_3x3 -> pool2): the pool's
+// backward gather is folded in, so the full-resolution fp32 dy tensor is neither written by a pooling kernel nor re-read:
+//   dz[p] = (sum over covering windows whose arg-max is p of dpool) * (y[p] > 0)
+// Works on 2x2 input blocks: block (2i..2i+1, 2j..2j+1) is covered by the four windows (i-1..i, j-1..j) only, so one thread
+// loads 4 windows + 4 activations for 4 outputs with 12 independent loads in flight (see glue_fp16.cu).
+__global__ void __launch_bounds__(MB_THREADS) pool_mask_bias_split2x2_f4(float* __restrict__ dz, int dpitch, int dcoff, const float* __restrict__ y,
+                                                                         int ypitch, int ycoff, int H, int W, const float* __restrict__ dpool, int OH,
+                                                                         int OW, int ppitch, int pcoff, const uint8_t* __restrict__ argmax,
+                                                                         __half* __restrict__ hi, int hpitch, int hcoff, long long lo_off, float scale,
+                                                                         int write_f32, int* __restrict__ flag, long long blocks, int C,
+                                                                         long long blocks_per_cta, float* __restrict__ partial,
+                                                                         unsigned* __restrict__ counter, const float* __restrict__ mult,
+                                                                         float out_scale, float* __restrict__ db, int accumulate) {
+  extern __shared__ float red[];
+  __shared__ bool is_last;
+  const int G = C / 4;
+  const int lanes = MB_THREADS / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  const int BH = (H + 1) / 2, BW = (W + 1) / 2;
+  const long long b0 = (long long)blockIdx.x * blocks_per_cta;
+  const long long b1 = (b0 + blocks_per_cta < blocks) ? b0 + blocks_per_cta : blocks;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float amax = 0.f;
+  if (rl < lanes) {
+    for (long long b = b0 + rl; b < b1; b += lanes) {
+      const unsigned bu = (unsigned)b;
+      const int bj = (int)(bu % (unsigned)BW), bi = (int)((bu / (unsigned)BW) % (unsigned)BH);
+      const long long f = bu / (unsigned)(BW * BH);
+      uint32_t am[4]; float4 dv[4], yv[4]; bool wok[4], pok[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int oy = bi - 1 + (q >> 1), ox = bj - 1 + (q & 1);
+        wok[q] = oy >= 0 && oy < OH && ox >= 0 && ox < OW;
+        if (wok[q]) {
+          const long long op = (f * OH + oy) * OW + ox;
+          am[q] = __ldg(reinterpret_cast<const uint32_t*>(argmax + op * C + g * 4));
+          dv[q] = ldg4(dpool + op * ppitch + pcoff + g * 4);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int iy = 2 * bi + (q >> 1), ix = 2 * bj + (q & 1);
+        pok[q] = iy < H && ix < W;
+        if (pok[q]) yv[q] = ldg4(y + ((f * H + iy) * W + ix) * ypitch + ycoff + g * 4);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!pok[q]) continue;
+        const int a = q >> 1, c = q & 1;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) {
+          const int u = wq >> 1, v = wq & 1;
+          if (!((u == 1 || a == 0) && (v == 1 || c == 0))) continue;      // compile-time: this window never covers the pixel
+          if (!wok[wq]) continue;
+          const uint32_t tag = (uint32_t)((a + 2 - 2 * u) * 3 + (c + 2 - 2 * v));
+          const float t[4] = {dv[wq].x, dv[wq].y, dv[wq].z, dv[wq].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (((am[wq] >> (8 * j)) & 0xFFu) == tag) d[j] += t[j];
+        }
+        const float yy[4] = {yv[q].x, yv[q].y, yv[q].z, yv[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(yy[j] > 0.f)) d[j] = 0.f;
+          acc[j] += d[j];
+        }
+        const int iy = 2 * bi + a, ix = 2 * bj + c;
+        const long long px = (f * H + iy) * W + ix;
+        if (write_f32) *reinterpret_cast<float4*>(dz + px * dpitch + dcoff + g * 4) = make_float4(d[0], d[1], d[2], d[3]);
+        if (hi) {
+          const float4 sv = make_float4(d[0] * scale, d[1] * scale, d[2] * scale, d[3] * scale);
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(sv.x), fabsf(sv.y)), fmaxf(fabsf(sv.z), fabsf(sv.w))));
+          if (sv.x != sv.x || sv.y != sv.y || sv.z != sv.z || sv.w != sv.w) amax = INFINITY;
+          store_planes4(hi + px * hpitch + hcoff + g * 4, lo_off, sv);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[rl * C + g * 4 + j] = acc[j];
+  }
+  if (flag && !(amax <= HALF_MAX)) *flag = 1;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += MB_THREADS) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + c];
+    partial[(long long)blockIdx.x * C + c] = s;
+  }
+  colsum_tail(partial, counter, C, mult, out_scale, db, &is_last, accumulate);
+}
+
 }  // namespace
 
 #define FP(v) reinterpret_cast<float*>((v).base)
@@ -337,6 +428,30 @@ int launch_mask_bias_split_f4(View dy, View y, View planes, float scale, int wri
                                                                     planes.pitch, planes.coff, planes.lo_off, scale, write_f32, flag, rows, C, rpc,
                                                                     part, counter, mult, out_scale, db, accumulate);
   SSNB_LAUNCH_CHECK("mask_bias_split_f4");
+  return 0;
+}
+
+// conv output y / dz views at full resolution; dpool = fp32 gradient of the k3/s2/pad0 max pool's output, argmax from its forward
+int launch_pool_mask_bias_split_f4(View dz, View y, View dpool, View planes, float scale, int write_f32, int* flag, int F, const uint8_t* argmax,
+                                   const float* mult, float out_scale, float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s) {
+  const int C = dz.C;
+  if (C % 4 || C / 4 > MB_THREADS || dz.pitch % 4 || dz.coff % 4 || y.pitch % 4 || y.coff % 4 || dpool.pitch % 4 || dpool.coff % 4 ||
+      (planes.base && (!planes.lo_off || planes.pitch % 4 || planes.coff % 4))) { set_thread_error("pool_mask_bias_split_f4: unsupported view"); return 1; }
+  const long long blocks = (long long)F * ((dz.H + 1) / 2) * ((dz.W + 1) / 2);
+  int ctas = (int)((blocks + 63) / 64);
+  if (ctas > 888) ctas = 888;
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  const long long bpc = (blocks + ctas - 1) / ctas;
+  ctas = (int)((blocks + bpc - 1) / bpc);
+  const int lanes = MB_THREADS / (C / 4);
+  unsigned* counter = reinterpret_cast<unsigned*>(partial);
+  float* part = partial + 64;
+  pool_mask_bias_split2x2_f4<<<ctas, MB_THREADS, (size_t)lanes * C * 4, s>>>(FP(dz), dz.pitch, dz.coff, FP(y), y.pitch, y.coff, dz.H, dz.W, FP(dpool),
+                                                                            dpool.H, dpool.W, dpool.pitch, dpool.coff, argmax, (__half*)planes.base,
+                                                                            planes.pitch, planes.coff, planes.lo_off, scale, write_f32, flag, blocks, C,
+                                                                            bpc, part, counter, mult, out_scale, db, accumulate);
+  SSNB_LAUNCH_CHECK("pool_mask_bias_split2x2_f4");
   return 0;
 }
 

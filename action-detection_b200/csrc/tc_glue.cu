@@ -65,6 +65,27 @@ __global__ void split_flat_kernel(const float* __restrict__ src, long long n, __
   lo[i] = __float2half_rn(v - __half2float(h));
 }
 
+__global__ void split_all_kernel(const __grid_constant__ SplitTable t) {
+  int ei = 0;
+  while (ei + 1 < t.n && (int)blockIdx.x >= t.e[ei + 1].block0) ++ei;
+  const SplitEntry& q = t.e[ei];
+  const long long i = (long long)((int)blockIdx.x - q.block0) * blockDim.x + threadIdx.x;
+  float sc = 1.0f;
+  int e = 0;
+  const float m = *q.absmax;
+  if (m > 0.f && m < INFINITY) { frexpf(m, &e); sc = ldexpf(1.0f, 13 - e); }
+  if (i == 0) *q.inv_scale = 1.0f / sc;
+  if (i >= q.n) return;
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    const float v = (l ? q.wd : q.wf)[i] * sc;
+    __half* hi = l ? q.wd16 : q.wf16;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    *reinterpret_cast<__half*>(reinterpret_cast<char*>(hi + i) + q.plane_bytes) = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // diagnostic read-back: (hi + lo) * scale as NCHW fp32 (what the consuming tensor-core kernels see)
 __global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, long long lo_off, int F, int C, int H, int W, int pitch, int coff,
                                       float scale, float* __restrict__ dst) {
@@ -165,6 +186,12 @@ int launch_split_view(View src, int F, float scale, View planes, int* flag, cuda
 int launch_split_flat(const float* src, long long n, __half* hi, __half* lo, const float* absmax, float* inv_scale, cudaStream_t s) {
   split_flat_kernel<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, s>>>(src, n, hi, lo, absmax, inv_scale);
   SSNB_LAUNCH_CHECK("split_flat_kernel");
+  return 0;
+}
+int launch_split_all(const SplitTable& t, int total_blocks, cudaStream_t s) {
+  if (t.n <= 0) return 0;
+  split_all_kernel<<<(unsigned)total_blocks, TPB, 0, s>>>(t);
+  SSNB_LAUNCH_CHECK("split_all_kernel");
   return 0;
 }
 int launch_planes_to_nchw(View planes, int F, float scale, float* dst, cudaStream_t s) {

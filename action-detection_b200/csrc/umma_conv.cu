@@ -117,6 +117,7 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
       float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
       __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
       const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+      const float* mrow32 = p.mask32 ? p.mask32 + opix * p.mask32_pitch + p.mask32_coff : nullptr;
       for (int c0 = cpar * 32; c0 < p.block_n; c0 += 64) {
         const bool two = c0 + 16 < p.block_n;
         const int cola = t.n0 + c0, colb = cola + 16;
@@ -124,8 +125,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
         tmem_ld16(taddr + c0, ra);
         if (two) tmem_ld16(taddr + c0 + 16, rb);
         tmem_ld_wait();
-        if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr);
-        if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr);
+        if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr, mrow32 ? mrow32 + cola : nullptr);
+        if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr, mrow32 ? mrow32 + colb : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -393,6 +394,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   plan.tmap_a2 = plan.tmap_a; plan.tmap_a2_lo = plan.tmap_a_lo;
   // SSNB_EXACT_TC: three operand segments per K chunk, fp32 epilogue (+ fp16 operand planes of the result)
   p.nseg = tc ? 3 : 1; p.out_f32 = tc ? 1 : 0; p.alpha = tc ? tc->alpha : 1.0f; p.alpha_dev = tc ? tc->alpha_dev : nullptr;
+  p.mask32 = nullptr; p.mask32_pitch = 0; p.mask32_coff = 0; p.plane_scale = 1.0f; p.flag = nullptr;
   p.out32 = tc ? tc->out32 : nullptr; p.out_hi = tc ? reinterpret_cast<__half*>(o.base) : nullptr; p.out_lo_off = tc ? o.lo_off : 0;
   if (tc && (!tc->out32 || !a.lo_off || !tc->w_lo_off)) { set_thread_error("umma conv: split-operand bind needs operand planes and an fp32 output"); return 1; }
   plan.enabled = true;
@@ -624,6 +626,12 @@ void umma_conv_set_mask(UmmaContext& ctx, UmmaConvPlan& plan, View y) {
   }
 }
 
+void umma_conv_set_mask_tc(UmmaConvPlan& plan, View y32, View dplanes, float plane_scale, int* flag) {
+  plan.mask32 = reinterpret_cast<const float*>(y32.base); plan.mask32_pitch = y32.pitch; plan.mask32_coff = y32.coff;
+  plan.mask_planes = reinterpret_cast<__half*>(dplanes.base); plan.mask_planes_lo = dplanes.lo_off;
+  plan.mask_plane_scale = plane_scale; plan.mask_flag = flag;
+}
+
 int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s, bool mask) {
   if (!plan.enabled) { set_thread_error("umma conv: plan not bound"); return 3; }
   if (!ctx.attr_set) {
@@ -633,6 +641,10 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
   }
   UmmaConvParams p = plan.p;
   if (mask && plan.mask_y) { p.mask_y = plan.mask_y; p.mask_pitch = plan.mask_pitch; p.mask_coff = plan.mask_coff; }
+  if (mask && p.out_f32 && plan.mask32) {
+    p.mask32 = plan.mask32; p.mask32_pitch = plan.mask32_pitch; p.mask32_coff = plan.mask32_coff;
+    p.out_hi = plan.mask_planes; p.out_lo_off = plan.mask_planes_lo; p.plane_scale = plan.mask_plane_scale; p.flag = plan.mask_flag;
+  }
   static const int ablate = [] { const char* e = getenv("SSNB_ABLATE"); return e ? atoi(e) : 0; }();     // timing experiments only
   p.ablate = ablate;
   if (p.v2) return umma_conv_v2_launch(ctx, plan, p, s);

@@ -65,6 +65,11 @@ struct UmmaConvParams {
   float alpha;
   const float* alpha_dev;         // optional device scalar multiplied into alpha (1 / the power-of-two scale of the weight planes)
   float* out32; __half* out_hi; long long out_lo_off;
+  // out_f32 data gradient that is the LAST writer of its output value v: dz = (alpha * acc + old) * (y > 0) with y = the fp32
+  // activation of v; the planes written through out_hi then hold dz * plane_scale (the loss scale) for v's producers'
+  // weight / data gradients, and *flag is raised when that leaves the fp16 range
+  const float* mask32; int mask32_pitch, mask32_coff;
+  float plane_scale; int* flag;
 };
 
 struct UmmaConvPlan {
@@ -73,6 +78,9 @@ struct UmmaConvPlan {
   CUtensorMap tmap_a, tmap_a2, tmap_b;
   CUtensorMap tmap_a_lo, tmap_a2_lo, tmap_b_lo;   // SSNB_EXACT_TC: LO planes of the three operands (copies of the HI maps otherwise)
   long long b_lo_off = 0;                        // byte offset of the LO weight plane (0: single plane)
+  // SSNB_EXACT_TC mask fusion, applied only when launched with mask=true (see UmmaConvParams::mask32)
+  const float* mask32 = nullptr; int mask32_pitch = 0, mask32_coff = 0;
+  __half* mask_planes = nullptr; long long mask_planes_lo = 0; float mask_plane_scale = 1.0f; int* mask_flag = nullptr;
   CUtensorMap tmap_old, tmap_y;   // experimental TMA-fed epilogue: output (old gradient) and mask-activation tiles, [128 rows][64 ch] boxes
   bool epi_maps_ready = false, epi_mask_ready = false;
   int epi_box[3] = {0, 0, 0}, epi_F = 0;     // box {W, F, H} extents and frame count for encoding tmap_y when the mask is attached
@@ -107,6 +115,8 @@ int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s,
 bool umma_conv_v2_supported(int ntaps);
 int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaConvParams& p, cudaStream_t s);
 void umma_conv_set_mask(UmmaContext& ctx, UmmaConvPlan& plan, View y);
+// EXACT_TC: y32 = fp32 activation of the output value, dplanes = that value's gradient operand planes (hi base + lo_off)
+void umma_conv_set_mask_tc(UmmaConvPlan& plan, View y32, View dplanes, float plane_scale, int* flag);
 
 // host helpers shared by the tensor-core kernels
 int umma_resolve_encode(UmmaContext& ctx);

@@ -339,6 +339,7 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
         __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
         const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
+        const float* mrow32 = p.mask32 ? p.mask32 + opix * p.mask32_pitch + p.mask32_coff : nullptr;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(quad * 32) << 16);
@@ -363,8 +364,8 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
             }
           }
-          if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, bias_s + cola, orow32 + cola, hrow ? hrow + cola : nullptr);
-          if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, bias_s + colb, orow32 + colb, hrow ? hrow + colb : nullptr);
+          if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, bias_s + cola, orow32 + cola, hrow ? hrow + cola : nullptr, mrow32 ? mrow32 + cola : nullptr);
+          if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, bias_s + colb, orow32 + colb, hrow ? hrow + colb : nullptr, mrow32 ? mrow32 + colb : nullptr);
         }
       } else if (TMAE) {
         // ---- TMA-fed: the operands of 64-column chunk i of this tile are in ring stage `es` (old gradient at +0, activation

@@ -31,7 +31,8 @@ __device__ __forceinline__ void stg256(void* p, const U8& a) {
 
 // SSNB_EXACT_TC epilogue: one 16-column chunk of an accumulator row in fp32 -- alpha * acc (+ bias, ReLU | + old) ->
 // 64 bytes of fp32, plus the value's fp16 hi / lo operand planes (2 x 32 bytes) for the convolutions that consume it
-__device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, float alpha, const uint32_t* r, const float* bias, float* dst, __half* hdst) {
+__device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, float alpha, const uint32_t* r, const float* bias, float* dst, __half* hdst,
+                                              const float* ymask) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * alpha;
@@ -51,12 +52,26 @@ __device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, float alp
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
   }
+  if (ymask) {                               // ReLU gradient of the value this data gradient completes: keep where y > 0 (NaN -> 0)
+    const U8 y0 = ldg256_nc(ymask), y1 = ldg256_nc(ymask + 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!(__uint_as_float(y0.v[j]) > 0.f)) v[j] = 0.f;
+      if (!(__uint_as_float(y1.v[j]) > 0.f)) v[8 + j] = 0.f;
+    }
+  }
   U8 q0, q1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { q0.v[j] = __float_as_uint(v[j]); q1.v[j] = __float_as_uint(v[8 + j]); }
   stg256(dst, q0);
   stg256(dst + 8, q1);
   if (hdst) {
+    if (p.flag || p.plane_scale != 1.0f) {   // gradient planes: scaled by the loss scale, guarded against the fp16 range
+      float m = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v[j] *= p.plane_scale; m = fmaxf(m, fabsf(v[j])); if (v[j] != v[j]) m = INFINITY; }
+      if (p.flag && !(m <= 65504.f)) *p.flag = 1;
+    }
     U8 qh, ql;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

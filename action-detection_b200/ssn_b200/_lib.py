@@ -49,6 +49,7 @@ SIGNATURES = {
     "ssnb_pack_weights": (_i, [_vp, _pp, _pp, _pp, _pp, _pp, _pp, _vp]),
     "ssnb_backbone_fwd": (_i, [_vp, _vp, _vp, _vp]),
     "ssnb_backbone_bwd": (_i, [_vp, _vp, _pp, _pp, _vp]),
+    "ssnb_backbone_bwd_range": (_i, [_vp, _vp, _pp, _pp, _i, _i, _vp]),
     "ssnb_bind_grads": (_i, [_vp, _pp, _pp]),
     "ssnb_set_grad_accumulate": (_i, [_vp, _i]),
     "ssnb_num_ops": (_i, [_vp]),
@@ -75,6 +76,8 @@ SIGNATURES = {
     "ssnb_grad_overflow": (_i, [_vp, _i]),
     "ssnb_timing_begin": (_i, [_vp]),
     "ssnb_timing_report": (C.c_char_p, []),
+    "ssnb_detect_workspace_bytes": (_sz, [_i, _i]),
+    "ssnb_detect_postprocess": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.c_double, _i, _vp, _vp, _vp, _vp]),
     "ssnb_sgd_step": (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _f, _vp]),
     "ssnb_sgd_step_groups": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _i, _f, _f, _vp]),
 }

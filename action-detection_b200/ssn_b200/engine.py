@@ -74,12 +74,42 @@ class BackboneEngine:
                   self.h, "backbone_fwd")
         return feat
 
-    def backward(self, dfeat, dw, db, accumulate=False):
+    def backward(self, dfeat, dw, db, accumulate=False, buckets=None, on_bucket=None):
+        """buckets: list of (op_hi, op_lo) ranges from the top of the network down (see bucket_ranges); on_bucket(i) runs
+        after range i has been enqueued -- its convolutions' gradients are final then (bucketed gradient exchange)."""
         dfeat = dfeat.contiguous().float()
         check(lib.ssnb_set_grad_accumulate(self.h, int(accumulate)), self.h, "set_grad_accumulate")
         with torch.cuda.device(self.device):
-            check(lib.ssnb_backbone_bwd(self.h, C.c_void_p(dfeat.data_ptr()), _lib.ptr_array(dw), _lib.ptr_array(db),
-                                        _stream()), self.h, "backbone_bwd")
+            if not buckets:
+                check(lib.ssnb_backbone_bwd(self.h, C.c_void_p(dfeat.data_ptr()), _lib.ptr_array(dw), _lib.ptr_array(db),
+                                            _stream()), self.h, "backbone_bwd")
+                return
+            pw, pb = _lib.ptr_array(dw), _lib.ptr_array(db)
+            for i, (hi, lo) in enumerate(buckets):
+                check(lib.ssnb_backbone_bwd_range(self.h, C.c_void_p(dfeat.data_ptr()), pw, pb, hi, lo, _stream()), self.h, "backbone_bwd_range")
+                if on_bucket is not None:
+                    on_bucket(i)
+
+    def bucket_ranges(self, first_ops):
+        """first_ops: names of the convolutions that start a bucket, top of the network first (e.g. ['inception_4e_3x3_reduce',
+        'inception_3c_3x3_reduce']); returns [(op_hi, op_lo)] covering all ops and, per bucket, the index of its first conv in
+        graph order (for slicing a flat gradient buffer laid out in parameter order)."""
+        ops = self.ops()
+        conv_idx, k = {}, 0
+        first_of = {}
+        for i, (kind, _iname, oname) in enumerate(ops):
+            if kind == "conv":
+                conv_idx[oname[:-3]] = (i, k)
+                k += 1
+        cuts = sorted([conv_idx[n] for n in first_ops], reverse=True)       # (op index, conv index), top first
+        ranges, convs = [], []
+        hi = len(ops) - 1
+        for (oi, ci) in cuts:
+            ranges.append((hi, oi)); convs.append(ci)
+            hi = oi - 1
+        if hi >= 0:
+            ranges.append((hi, 0)); convs.append(0)
+        return ranges, convs
 
     # ---- introspection used by the per-layer parity tests ----
     def ops(self):

@@ -12,9 +12,11 @@ from ._lib import lib, check
 
 
 class FusedSGD:
-    def __init__(self, policies, lr, momentum=0.9, weight_decay=5e-4, on_step=None):
+    def __init__(self, policies, lr, momentum=0.9, weight_decay=5e-4, on_step=None, order=None):
         """policies: list of dicts with 'params', 'lr_mult', 'decay_mult' (SSN.get_optim_policies()).  on_step: callables run
-        after every step (e.g. BNInception.invalidate_packed: the kernels' packed weight copies are stale)."""
+        after every step (e.g. BNInception.invalidate_packed: the kernels' packed weight copies are stale).  order: the
+        parameters in the order they should occupy the flat buffers (default: group by group; model.parameters() order
+        puts each layer's weight and bias side by side, which ssn_b200.dp.GradSync's buckets need)."""
         self.param_groups = []
         for g in policies:
             ps = [p for p in g["params"] if p.requires_grad]
@@ -27,6 +29,12 @@ class FusedSGD:
         self.momentum = float(momentum)
         self.on_step = list(on_step or [])
         params = [p for g in self.param_groups for p in g["params"]]
+        self._group_of = {id(p): g for g in self.param_groups for p in g["params"]}
+        if order is not None:
+            order = [p for p in order if id(p) in self._group_of]
+            assert len(order) == len(params), "order must list exactly the parameters of the groups"
+            params = order
+        self.params = params
         assert params and all(p.is_cuda and p.dtype == torch.float32 for p in params), "FusedSGD: fp32 CUDA parameters"
         dev = params[0].device
         self.device = dev
@@ -51,10 +59,8 @@ class FusedSGD:
 
     def refresh_groups(self):
         """re-read lr / weight_decay of every group (call after adjust_learning_rate changed them)"""
-        lr, wd = [], []
-        for g in self.param_groups:
-            lr += [float(g["lr"])] * len(g["params"])
-            wd += [float(g["weight_decay"])] * len(g["params"])
+        lr = [float(self._group_of[id(p)]["lr"]) for p in self.params]
+        wd = [float(self._group_of[id(p)]["weight_decay"]) for p in self.params]
         self._seg_lr.copy_(torch.tensor(lr)); self._seg_wd.copy_(torch.tensor(wd))
 
     def rebind_grads(self):

@@ -240,10 +240,11 @@ class SSN(torch.nn.Module):
 
     # ---- fused training step: backbone fwd -> pool+STPP -> heads+loss(+grads) -> backbone bwd ---------
     def fused_step(self, input, aug_scaling, target, reg_target, prop_type, fg_per_video=1, comp_group=7,
-                   props_per_video=8, ohem_ratio=0.17, comp_w=0.1, reg_w=0.1, global_videos=None, loss_scale=1.0):
+                   props_per_video=8, ohem_ratio=0.17, comp_w=0.1, reg_w=0.1, global_videos=None, loss_scale=1.0, grad_sync=None):
         """Same arithmetic as train_forward + the three criteria + loss.backward() of
         ssn_train.py:207-236, issued as ~4 library calls.  Accumulates into .grad like autograd and
-        returns losses[4] = (act, comp, reg, total) as a device tensor."""
+        returns losses[4] = (act, comp, reg, total) as a device tensor.  grad_sync (ssn_b200.dp.GradSync): exchange the
+        gradients bucket by bucket while the backward of the lower layers is still running."""
         import ctypes as C
         from ssn_b200.engine import _stream
         assert self.with_regression, "fused_step implements the regression configuration"
@@ -287,15 +288,6 @@ class SSN(torch.nn.Module):
                                     self.starting_segment + self.course_segment, dft.data_ptr(), _stream()), None, "stpp_bwd")
         if mask is not None:
             dft = dft * mask
-        cs = bm._convs()
-        params = [c.weight for c in cs] + [c.bias for c in cs]
-        for p in params:
-            if p.requires_grad and p.grad is None:
-                p.grad = torch.zeros_like(p)
-        # straight into .grad; parameters with requires_grad=False get no gradient (None -> the kernels skip them)
-        eng.backward(dft, [c.weight.grad if c.weight.requires_grad else None for c in cs],
-                     [c.bias.grad if c.bias.requires_grad else None for c in cs], accumulate=True)
-
         def acc(p, g):
             if p.grad is None:
                 p.grad = g
@@ -306,6 +298,19 @@ class SSN(torch.nn.Module):
                 acc(fc.weight, out["d_%s_w" % k])
             if fc.bias.requires_grad:
                 acc(fc.bias, out["d_%s_b" % k])
+        if grad_sync is not None:
+            grad_sync.begin()
+            grad_sync.heads_done()
+        cs = bm._convs()
+        params = [c.weight for c in cs] + [c.bias for c in cs]
+        for p in params:
+            if p.requires_grad and p.grad is None:
+                p.grad = torch.zeros_like(p)
+        # straight into .grad; parameters with requires_grad=False get no gradient (None -> the kernels skip them)
+        buckets = grad_sync.engine_buckets(eng)[0] if grad_sync is not None else None
+        eng.backward(dft, [c.weight.grad if c.weight.requires_grad else None for c in cs],
+                     [c.bias.grad if c.bias.requires_grad else None for c in cs], accumulate=True, buckets=buckets,
+                     on_bucket=(lambda i: grad_sync.bucket_done(eng, i)) if grad_sync is not None else None)
         self.last_fused = dict(out, feat=feat, course=course, stpp=stpp)
         return out["losses"]
 

@@ -193,7 +193,7 @@ def run_reference(args):
                         d[k].requires_grad_(True)
 
             def one():
-                loss, _ = O.total_loss(O.ssn_train_forward(bb, hd, *batch, stpp_cfg=STPP_CFG))
+                loss, _ = O.total_loss(O.ssn_train_forward(bb, hd, *batch, stpp_cfg=STPP_CFG, in_channels=in_ch))
                 loss.backward()
                 for d in (bb, hd):
                     for v in d.values():
@@ -370,21 +370,20 @@ def main():
             sd["base_model." + k].copy_(v)
         model = model.to(dev).train()
         model.set_precision(PREC[precision], args.grad_scale)
-        params = [p for p in model.parameters() if p.requires_grad]
-        flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
-        off = 0
-        for p in params:
-            p.grad = flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        policies = model.get_optim_policies()
-        groups = [{"params": g["params"], "lr": 1e-5 * g["lr_mult"], "weight_decay": 5e-4 * g["decay_mult"]} for g in policies if g["params"]]
-        opt = torch.optim.SGD(groups, lr=1e-5, momentum=0.9)
+        # fused SGD over flat buffers in model.parameters() order (ssn_train.py:141-144 semantics, per-group lr_mult / decay_mult);
+        # gradients are exchanged bucket by bucket on a communication stream while the backward is still running
+        from ssn_b200.optim import FusedSGD
+        from ssn_b200.dp import GradSync
+        order = [p for p in model.parameters() if p.requires_grad]
+        opt = FusedSGD(model.get_optim_policies(), lr=1e-5, momentum=0.9, weight_decay=5e-4, order=order,
+                       on_step=[model.base_model.invalidate_packed])
+        flat_grad = opt.flat_grad
+        sync = GradSync(flat_grad, order, model)
 
         def eager_step(batch):
             flat_grad.zero_()
-            losses = model.fused_step(*batch, global_videos=args.videos_per_gpu * world, loss_scale=1.0 / world)
-            if world > 1:
-                dist.all_reduce(flat_grad)
+            losses = model.fused_step(*batch, global_videos=args.videos_per_gpu * world, loss_scale=1.0 / world, grad_sync=sync)
+            sync.finish()
             opt.step()
             return losses
         return model, flat_grad, opt, eager_step

@@ -67,6 +67,12 @@ int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void*
 /* dfeat [F,1024] fp32 -> dw[i] [cout,cin,k,k], db[i] [cout] fp32 in reference layout (what autograd
  * leaves in Conv2d.weight.grad / .bias.grad; BN params are frozen and get none).  Overwrites. */
 int ssnb_backbone_bwd(ssnb_handle h, const float* dfeat, float* const* dw, float* const* db, void* stream);
+/* The same backward in pieces, for overlapping the gradient exchange with it: runs the reverse schedule for ops
+ * op_hi .. op_lo (indices of ssnb_op_info; op_hi < 0 = the last op, the global pool, which reads dfeat) and finalises the
+ * weight / bias gradients of exactly those ops, so after the call dw[i] / db[i] of their convolutions are complete and a
+ * bucket all-reduce can be issued on another stream while the next range runs.  Ranges must be issued from the top down. */
+int ssnb_backbone_bwd_range(ssnb_handle h, const float* dfeat, float* const* dw, float* const* db, int op_hi, int op_lo,
+                            void* stream);
 /* 0 (default): ssnb_backbone_bwd overwrites dw/db; 1: it adds to them (what autograd's AccumulateGrad does
  * with Conv2d.weight.grad), so the caller can hand in the live .grad tensors */
 int ssnb_set_grad_accumulate(ssnb_handle h, int accumulate);
@@ -174,6 +180,18 @@ int ssnb_heads_loss_fwd_bwd(const ssnb_heads_cfg* cfg, const float* course_ft, c
                             const float* reg_target, float* raw_act, float* raw_comp, float* raw_reg, float* losses,
                             float* d_course_ft, float* d_stpp_ft, float* d_act_w, float* d_act_b, float* d_comp_w,
                             float* d_comp_b, float* d_reg_w, float* d_reg_b, void* workspace, void* stream);
+
+/* ---- detection post-processing of one video (eval_detection_results.py:91-183, ops/utils.py:38-40,56-82) --------------
+ * rel_props [N,2] (start, end in [0,1]), act_scores [N,K+1], comp_scores [N,K], reg_scores [N,K,2] (already de-normalised,
+ * ssn_test.py:89-92) ->  per class c: combined score softmax(act)[:,c+1] * exp(comp[:,c]), greedy temporal NMS at
+ * nms_thresh in descending score order, then (regress != 0) the location regression of the survivors.
+ * detections [K, N, 5] rows (t0, t1, score, loc, dur) in kept order, counts [K] int32; combined_ws: N*K floats of scratch
+ * (ssnb_detect_workspace_bytes).  N <= 8192.  act_scores == NULL: combined_ws already holds the [N,K] scores to rank by
+ * (plain class-wise temporal_nms, ops/utils.py:56-82). */
+size_t ssnb_detect_workspace_bytes(int n_props, int num_class);
+int ssnb_detect_postprocess(const float* rel_props, const float* act_scores, const float* comp_scores, const float* reg_scores,
+                            int n_props, int num_class, double nms_thresh, int regress, float* detections, int* counts,
+                            float* combined_ws, void* stream);
 
 /* fused SGD-momentum step over flat fp32 buffers (ssn_train.py:141-144 torch.optim.SGD semantics):
  * g = grad*grad_mult + wd*p; buf = mom*buf + g; p -= lr*buf */

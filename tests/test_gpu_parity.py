@@ -668,11 +668,14 @@ def test_fused_step_bench_shape(precision):
     e["backbone_grads_cos"] = _cos(lambda n_: params[n_].grad, bb_ref)
     print("fused_step F=288 (%s) vs fp32 oracle: %s" % (precision, {k: "%.3e" % v for k, v in e.items()}))
     print("fused_step F=288 (%s) losses %s oracle %s" % (precision, losses.tolist(), ref_l.tolist()))
-    bars = {"exact_tc": {"feat": 5e-4, "course": 5e-4, "stpp": 5e-4, "loss": 1e-3, "head_grads": 1e-2, "backbone_grads": 1.5e-1},
-            "fast": {"feat": 3e-2, "course": 3e-2, "stpp": 3e-2, "loss": 3e-2, "head_grads": 2e-1, "backbone_grads": 1.0}}[precision]
+    # measured on B200 (round 2): exact_tc feat 3.4e-5, loss 6e-7, head grads 2.7e-5, backbone grads 1.0e-2 (cosine 0.9999; the
+    # fp32 reference itself is 7.6e-3 from the float64 gradient on this random-weight net, test_ssn_train_exact_vs_oracle);
+    # fast feat 9.2e-3, loss 3e-4, head grads 3.1e-3, backbone grads 0.27 (cosine 0.964): outside the 1e-3 tolerance, reported
+    bars = {"exact_tc": {"feat": 2e-4, "course": 2e-4, "stpp": 2e-4, "loss": 1e-4, "head_grads": 5e-4, "backbone_grads": 5e-2},
+            "fast": {"feat": 3e-2, "course": 3e-2, "stpp": 3e-2, "loss": 3e-3, "head_grads": 2e-2, "backbone_grads": 0.6}}[precision]
     for k, b in bars.items():
         assert e[k] < b, (k, e[k], b)
-    assert e["backbone_grads_cos"] > (0.99 if precision == "exact_tc" else 0.7), e["backbone_grads_cos"]
+    assert e["backbone_grads_cos"] > (0.999 if precision == "exact_tc" else 0.9), e["backbone_grads_cos"]
 
 
 @pytest.mark.parametrize("precision", ["exact", "exact_tc"])
@@ -704,7 +707,7 @@ def test_flow_train_vs_oracle(precision):
         for k in d:
             if "_bn." not in k:
                 d[k].requires_grad_(True)
-    oouts = O.ssn_train_forward(bbo, hdo, x, sc, tgt, rtgt, ptype)
+    oouts = O.ssn_train_forward(bbo, hdo, x, sc, tgt, rtgt, ptype, in_channels=10)
     oloss, _ = O.total_loss(oouts)
     oloss.backward()
     for name, o, r in zip(("act", "act_t", "comp", "comp_t", "reg", "reg_l", "reg_t"), outs, oouts):
@@ -851,3 +854,30 @@ def test_autograd_guards(backbone_rgb):
     h.remove()
     assert len(seen) == 1 and seen[0] > 0
     assert rel_l2(net.conv1_7x7_s2.weight.grad, direct) < 1e-6
+
+
+def test_detect_postprocess_vs_reference(golden_dir):
+    """f3: GPU detection post-processing (combined scores, class-wise temporal NMS, location regression) against the
+    reference's own outputs (tests/golden/detect.npz): the survivor sets and their order are exact, values to fp32 rounding."""
+    dev = _cuda()
+    from ops.detection import video_detections, temporal_nms
+    z = _load(golden_dir, "detect.npz")
+    for tag in "abcd":
+        props, act, comp, reg = (torch.tensor(z[tag + k]).to(dev) for k in ("_props", "_act", "_comp", "_reg"))
+        thr = float(z[tag + "_thr"])
+        K = comp.shape[1]
+        det, cnt = video_detections(props, act, comp, reg, thr)
+        raw, cnt2 = video_detections(props, act, comp, reg, thr, regress=False)
+        assert torch.equal(cnt, cnt2)
+        for c in range(K):
+            ref_nms, ref_det = z["%s_nms_%d" % (tag, c)], z["%s_det_%d" % (tag, c)]
+            n = int(cnt[c])
+            assert n == ref_nms.shape[0], (tag, c, n, ref_nms.shape)
+            got_raw, got = raw[c, :n].cpu().numpy(), det[c, :n].cpu().numpy()
+            np.testing.assert_array_equal(got_raw[:, [0, 1, 3, 4]], ref_nms[:, [0, 1, 3, 4]])     # same boxes, same order
+            np.testing.assert_allclose(got_raw[:, 2], ref_nms[:, 2], rtol=2e-6)
+            np.testing.assert_allclose(got, ref_det, rtol=2e-6, atol=1e-6)
+        # plain temporal_nms on given scores (ops/utils.py:56-82)
+        boxes = torch.tensor(z["%s_nms_0" % tag] if False else np.concatenate((z[tag + "_props"], z[tag + "_combined"][:, :1]), axis=1)).to(dev)
+        kept = temporal_nms(boxes, thr).cpu().numpy()
+        np.testing.assert_array_equal(kept, z["%s_nms_0" % tag][:, :3])

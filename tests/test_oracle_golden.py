@@ -152,3 +152,20 @@ def test_ssn_e2e_rgb(golden_dir):
 
 def test_ssn_e2e_flow_forward(golden_dir):
     _e2e(golden_dir, "Flow", 10, False)
+
+
+def test_detect_oracle_matches_reference(golden_dir):
+    """oracle/detect_oracle.py against tests/golden/detect.npz (real reference: ops.utils.softmax / temporal_nms and
+    eval_detection_results.perform_regression): combined scores, NMS survivors and regressed detections, bit for bit."""
+    from oracle import detect_oracle as D
+    z = np.load(os.path.join(golden_dir, "detect.npz"))
+    for tag in "abcd":
+        props, act, comp, reg = z[tag + "_props"], z[tag + "_act"], z[tag + "_comp"], z[tag + "_reg"]
+        thr = float(z[tag + "_thr"])
+        K = comp.shape[1]
+        np.testing.assert_array_equal(D.softmax(act)[:, 1:] * np.exp(comp), z[tag + "_combined"])
+        dets = D.video_detections(props, act, comp, reg, thr)
+        raw = D.video_detections(props, act, comp, reg, thr, regress=False)
+        for c in range(K):
+            np.testing.assert_array_equal(raw[c], z["%s_nms_%d" % (tag, c)])
+            np.testing.assert_array_equal(dets[c], z["%s_det_%d" % (tag, c)])
