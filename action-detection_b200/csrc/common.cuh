@@ -101,6 +101,7 @@ struct PackEntry {
   const float *w, *b, *gamma, *beta, *mean, *var;
   void *wf, *wd; float *bias, *scale, *absmax;
   int cout, cin, k, block0;
+  int nofold, pad_[3];          // nofold: scale = 1, bias' = b (the layer's BatchNorm runs in training mode, unfused)
 };
 struct PackTable { int n, pad_; PackEntry e[PACK_MAX]; };
 template <typename T> int launch_pack_all(const PackTable& t, int total_blocks, cudaStream_t s);
@@ -146,6 +147,11 @@ int launch_mask_bias_split_f4(View dy, View y, View planes, float scale, int wri
                               float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
 int launch_pool_mask_bias_split_f4(View dz, View y, View dpool, View planes, float scale, int write_f32, int* flag, int F, const uint8_t* argmax,
                                    const float* mult, float out_scale, float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s);
+// training-mode BatchNorm + ReLU of the first layer (bn_train.cu); stat: 4*C floats, partial: max_ctas * 2 * C floats
+int launch_bn_train_fwd(View z, View y, View y_planes, int F, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                        float* running_var, float* stat, float* partial, int max_ctas, cudaStream_t s);
+int launch_bn_train_bwd(View z, View dy, View y, View dz, View dz_planes, float plane_scale, int* flag, int F, const float* gamma, float* stat,
+                        float* partial, int max_ctas, float* dgamma, float* dbeta, int accumulate, cudaStream_t s);
 // FAST-mode layout helpers (s2d_glue.cu)
 int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s);
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s);

@@ -78,7 +78,7 @@ static std::vector<ConvSpec> conv_table(int in_ch) {
 // ---- planned objects -----------------------------------------------------------------------------
 struct Buffer { std::string name; int H, W, C; size_t off = 0, goff = 0; size_t hoff = 0, ghoff = 0, plane = 0; };   // EXACT_TC: fp16 hi/lo operand planes (lo = hi + plane)
 struct Value { std::string name; int buf, coff, C; };
-enum OpKind { OP_CONV = 0, OP_MAXPOOL = 1, OP_AVGPOOL = 2, OP_GPOOL = 3 };
+enum OpKind { OP_CONV = 0, OP_MAXPOOL = 1, OP_AVGPOOL = 2, OP_GPOOL = 3, OP_BN1 = 4 };   // OP_BN1: training-mode BatchNorm + ReLU behind conv1 (bn_mode='partial')
 struct Op {
   OpKind kind; std::string id; int in_val, out_val;
   int conv = -1, k = 0, stride = 1, pad = 0;
@@ -94,6 +94,7 @@ struct Op {
   bool dgrad_masks = false; // this op's data gradient is the LAST writer of d(in_val): it applies the ReLU mask of in_val
   bool bias_in_wgrad = false;// conv: bias gradient comes out of the tcgen05 weight-gradient kernel (ones operand)
   bool dy_premasked = false;// conv: d(out) arrives already masked, the backward pass only needs the bias column sums
+  bool raw = false;         // conv whose BatchNorm runs unfused in training mode: no fold, no ReLU in the epilogue, no ReLU mask in backward
   int fuse_role = 0;        // sibling 1x1 fusion: 1 = leader (launches the fused kernels), 2 = follower
   int fuse_block = -1;
 };
@@ -120,6 +121,10 @@ struct ssnb_engine {
   size_t up_plane = 0, s2d_plane = 0, s2d_w_plane = 0;
   int* tc_flag = nullptr;           // device int: set when a split pass saw |x * grad_scale| beyond the fp16 range
   size_t tc_flag_off = 0, wmax_off = 0;
+  bool bn1_train = false;           // bn_mode='partial': the first BatchNorm2d in training mode (bn_train.cu)
+  const float *bn1_gamma = nullptr, *bn1_beta = nullptr; float *bn1_rmean = nullptr, *bn1_rvar = nullptr, *bn1_dgamma = nullptr, *bn1_dbeta = nullptr;
+  float bn1_momentum = 0.1f, bn1_eps = 1e-5f;
+  size_t bn_stat_off = 0, bn_partial_off = 0;
   std::vector<ConvSpec> convs;
   std::vector<Buffer> bufs;
   std::vector<Value> vals;
@@ -207,7 +212,14 @@ static void build_graph(ssnb_engine* e) {
     return add_value(e, name, add_buffer(e, name, H, W, C), 0, C);
   };
   int x = whole("data", 224, 224, cin);
-  int v = whole("conv1_7x7_s2_bn", 112, 112, 64); conv_op(x, v); x = v;
+  int v;
+  if (e->bn1_train) {
+    const int raw = whole("conv1_7x7_s2_raw", 112, 112, 64); conv_op(x, raw); e->ops.back().raw = true;
+    v = whole("conv1_7x7_s2_bn", 112, 112, 64);
+    pool_op(OP_BN1, "conv1_7x7_s2_bn", raw, v, 0, 1, 0); x = v;
+  } else {
+    v = whole("conv1_7x7_s2_bn", 112, 112, 64); conv_op(x, v); x = v;
+  }
   v = whole("pool1_3x3_s2", 56, 56, 64); pool_op(OP_MAXPOOL, "pool1_3x3_s2", x, v, 3, 2, 0); x = v;
   v = whole("conv2_3x3_reduce_bn", 56, 56, 64); conv_op(x, v); x = v;
   v = whole("conv2_3x3_bn", 56, 56, 192); conv_op(x, v); x = v;
@@ -257,6 +269,7 @@ static void plan(ssnb_engine* e) {
     }
   }
   e->tc_flag_off = off; off = align_up(off + 256, 1024);      // gradient overflow flag (every mode)
+  if (e->bn1_train) { e->bn_stat_off = off; off = align_up(off + 4 * 64 * 4, 1024); e->bn_partial_off = off; off = align_up(off + (size_t)1200 * 2 * 64 * 4, 1024); }
   for (Op& o : e->ops)
     if (o.kind == OP_MAXPOOL) {
       const Buffer& ob = e->bufs[e->vals[o.out_val].buf];
@@ -424,6 +437,12 @@ static int run_fwd(ssnb_engine* e, const Op& o, const float* input_nchw, float* 
     return umma_conv_launch(e->umma_ctx, o.umma, s);
   }
   tag_next(0, 0.0);
+  if (o.kind == OP_BN1) {
+    if (!e->bn1_gamma || !e->bn1_beta) { set_thread_error("bn1_train engine: call ssnb_set_bn1 first"); return SSNB_ESTATE; }
+    return launch_bn_train_fwd(e->view(o.in_val, false), e->view(o.out_val, false), e->tc ? e->planes(o.out_val, false) : View(), e->F, e->bn1_gamma,
+                               e->bn1_beta, e->bn1_eps, e->bn1_momentum, e->bn1_rmean, e->bn1_rvar, (float*)(e->ws + e->bn_stat_off),
+                               (float*)(e->ws + e->bn_partial_off), 1200, s);
+  }
   if (e->tc && (o.kind == OP_MAXPOOL || o.kind == OP_AVGPOOL) && e->bufs[e->vals[o.out_val].buf].plane) {
     // vectorised fp32 pooling that also emits the output's operand planes (glue_fp32.cu)
     const View in = e->view(o.in_val, false), out = e->view(o.out_val, false), pl = e->planes(o.out_val, false);
@@ -449,7 +468,7 @@ static int run_fwd_impl(ssnb_engine* e, const Op& o, const float* input_nchw, fl
     a.src = in.base; a.SH = in.H; a.SW = in.W; a.Csrc = in.C; a.src_pitch = in.pitch; a.src_coff = in.coff;
     a.dst = out.base; a.DH = out.H; a.DW = out.W; a.Cdst = out.C; a.dst_pitch = out.pitch; a.dst_coff = out.coff;
     a.wgt = e->ws + e->packed[o.conv].wf; a.bias = (const float*)(e->ws + e->packed[o.conv].bias);
-    a.F = F; a.k = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = 1; a.accumulate = 0; a.dgrad = 0;
+    a.F = F; a.k = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = o.raw ? 0 : 1; a.accumulate = 0; a.dgrad = 0;
     tag_next(0, conv_flops(e, o));
     return DISPATCH(e, launch_conv<float>(a, s), launch_conv<__half>(a, s));
   }
@@ -484,6 +503,11 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     const void* ym = (full && e->fold_pools && o.dgrad_masks) ? e->view(o.in_val, false).base : nullptr;
     return DISPATCH(e, launch_gpool_bwd<float>(dfeat, gs, din, F, ym, s), launch_gpool_bwd<__half>(dfeat, gs, din, F, ym, s));
   }
+  if (o.kind == OP_BN1) {
+    return launch_bn_train_bwd(e->view(o.in_val, false), e->view(o.out_val, true), e->view(o.out_val, false), e->view(o.in_val, true),
+                               e->tc ? e->planes(o.in_val, true) : View(), e->cfg.grad_scale, e->tc_flag, F, e->bn1_gamma, (float*)(e->ws + e->bn_stat_off),
+                               (float*)(e->ws + e->bn_partial_off), 1200, e->bn1_dgamma, e->bn1_dbeta, e->grad_accumulate, s);
+  }
   if (o.kind == OP_MAXPOOL) {
     if (full && (e->fp16 || e->tc) && e->fold_pools && o.folded_into_conv) return 0;      // gathered by the producer conv's mask+bias pass
     const View din = e->view(o.in_val, true), dout = e->view(o.out_val, true);
@@ -517,7 +541,11 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     const bool tc_w = want_w && o.umma_wgrad.enabled, tc_x = want_x && o.umma_dgrad.enabled;
     const bool pre = full && e->fold_pools && o.dy_premasked;      // the last writer of dy masked it and wrote its operand planes
     const bool bias_w = pre && o.bias_in_wgrad && dbp && tc_w;     // ... and the column sums ride on the weight-gradient MMAs
-    if (pre) {
+    if (o.raw) {
+      // the training-mode BatchNorm behind this convolution produced dz and its planes: only the bias-gradient column sums are left
+      if (dbp)
+        if ((rc = launch_mask_bias_split_f4(dy, View(), View(), gst, 0, nullptr, F, scale, 1.0f, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
+    } else if (pre) {
       if (!bias_w && dbp)       // bias gradient only: column sums of the (already masked) fp32 dz, no planes, nothing written back
         if ((rc = launch_mask_bias_split_f4(dy, y, View(), gst, 0, nullptr, F, scale, 1.0f, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
     } else if (full && e->fold_pools && o.pool_consumer >= 0) {
@@ -583,7 +611,7 @@ static int run_bwd(ssnb_engine* e, const Op& o, const float* dfeat, cudaStream_t
     if (bias_w) { /* no pass at all: dy is already masked and the column sums ride on the weight-gradient MMAs */ }
     else if ((rc = launch_mask_bias_h8(dy, pre ? View() : y, F, scale, 1.0f / gs, bpartial, (1024 * 512 - 64) / y.C, dbp, e->grad_accumulate, s))) return rc;
   } else {
-    if ((rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
+    if (!o.raw && (rc = launch_relu_mask<float>(dy, y, F, s))) return rc;
     if (dbp) {
       int bs = (int)((M + 4095) / 4096); if (bs > 64) bs = 64; if (bs < 1) bs = 1;
       if ((rc = launch_bias_grad<float>(dy.base, (int)M, y.C, dy.pitch, dy.coff, scale, 1.0f / gs, bpartial, bs, dbp, e->grad_accumulate, s))) return rc;
@@ -660,6 +688,8 @@ int ssnb_create(const ssnb_config* cfg, ssnb_handle* out) {
   e->F = cfg->frames;
   e->fp16 = cfg->precision == SSNB_FAST_FP16;
   e->tc = cfg->precision == SSNB_EXACT_TC;
+  e->bn1_train = cfg->bn1_train != 0;
+  if (e->bn1_train && e->fp16) { delete e; set_thread_error("ssnb_create: bn1_train (bn_mode='partial') needs EXACT_FP32 or EXACT_TC"); return SSNB_ENOSUPPORT; }
   e->esz = e->fp16 ? 2 : 4;
   build_graph(e);
   if ((int)e->convs.size() != 69) { delete e; set_thread_error("internal: conv table size"); return SSNB_ESTATE; }
@@ -712,7 +742,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
         for (int t = 0; t < 4; ++t) { dy[t] = t - 2; dx[t] = 0; }
         UmmaTcOpts t; t.w_lo_off = (long long)h->s2d_w_plane; t.out32 = (float*)out32.base; t.alpha = 1.0f; t.alpha_dev = (const float*)(h->ws + pk.wmax) + 1;
         rc = umma_conv_bind_taps(h->umma_ctx, o.umma, xs, h->planes(o.out_val, false), h->F, Ck, c.cout, 4, dy, dx,
-                                 (const __half*)(h->ws + h->s2d_w_off), (const float*)(h->ws + pk.bias), 1, &t);
+                                 (const __half*)(h->ws + h->s2d_w_off), (const float*)(h->ws + pk.bias), o.raw ? 0 : 1, &t);
         if (rc) return h->fail(rc, "tc conv1 bind: " + ssnb::thread_error());
         if (!o.umma.p.v2) o.umma.enabled = false;
         if (use_wgrad_tc) {
@@ -918,6 +948,7 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
       q.wf = h->ws + p.wf; q.wd = h->ws + p.wd; q.bias = (float*)(h->ws + p.bias); q.scale = (float*)(h->ws + p.scale);
       q.absmax = h->tc ? (float*)(h->ws + p.wmax) : nullptr;
       q.cout = c.cout; q.cin = c.cin; q.k = c.k; q.block0 = blocks;
+      q.nofold = (h->bn1_train && i == 0) ? 1 : 0; q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
       blocks += (int)((std::max<long long>(n, c.cout) + 255) / 256);
       if (h->tc) {
         SplitEntry& e = st.e[st.n++];
@@ -963,6 +994,16 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
     }
   }
   h->weights_ready = true;
+  return SSNB_OK;
+}
+
+int ssnb_set_bn1(ssnb_handle h, const float* gamma, const float* beta, float* running_mean, float* running_var, float* dgamma, float* dbeta,
+                 float momentum, float eps) {
+  if (!h) return SSNB_EINVAL;
+  if (!h->bn1_train) return h->fail(SSNB_ESTATE, "engine created without bn1_train");
+  if (!gamma || !beta) return h->fail(SSNB_EINVAL, "set_bn1: gamma / beta are required");
+  h->bn1_gamma = gamma; h->bn1_beta = beta; h->bn1_rmean = running_mean; h->bn1_rvar = running_var; h->bn1_dgamma = dgamma; h->bn1_dbeta = dbeta;
+  h->bn1_momentum = momentum; h->bn1_eps = eps;
   return SSNB_OK;
 }
 
@@ -1071,7 +1112,7 @@ int ssnb_num_ops(ssnb_handle h) { return h ? (int)h->ops.size() : 0; }
 
 int ssnb_op_info(ssnb_handle h, int op, char* kind, int kind_cap, char* in_name, int in_cap, char* out_name, int out_cap) {
   if (!h || op < 0 || op >= (int)h->ops.size()) return SSNB_EINVAL;
-  static const char* kn[] = {"conv", "maxpool", "avgpool", "gpool"};
+  static const char* kn[] = {"conv", "maxpool", "avgpool", "gpool", "bn"};
   const Op& o = h->ops[op];
   if (kind) snprintf(kind, kind_cap, "%s", kn[o.kind]);
   if (in_name) snprintf(in_name, in_cap, "%s", h->vals[o.in_val].name.c_str());

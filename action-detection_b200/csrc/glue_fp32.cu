@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_split_f4(float* __restri
         const long long r = rb + (long long)u * lanes;
         if (r < r1) {
           dv[u] = *reinterpret_cast<const float4*>(dy + r * dpitch + dcoff + g * 4);
-          yv[u] = ldg4(y + r * ypitch + ycoff + g * 4);
+          if (y) yv[u] = ldg4(y + r * ypitch + ycoff + g * 4);
         }
       }
 #pragma unroll
@@ -254,11 +254,13 @@ __global__ void __launch_bounds__(MB_THREADS) mask_bias_split_f4(float* __restri
         const long long r = rb + (long long)u * lanes;
         if (r >= r1) continue;
         float d[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
-        const float a[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
         bool changed = false;
+        if (y) {                                  // y == nullptr: no ReLU behind this convolution (column sums / planes only)
+          const float a[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
+          for (int j = 0; j < 4; ++j)
+            if (!(a[j] > 0.f)) { changed = changed || (d[j] != 0.f); d[j] = 0.f; }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] += d[j];
         if (write_f32 && changed) *reinterpret_cast<float4*>(dy + r * dpitch + dcoff + g * 4) = make_float4(d[0], d[1], d[2], d[3]);
@@ -413,7 +415,7 @@ int launch_mask_bias_split_f4(View dy, View y, View planes, float scale, int wri
                               float* partial, int max_ctas, float* db, int accumulate, cudaStream_t s) {
   const long long rows = (long long)F * dy.H * dy.W;
   const int C = dy.C;
-  if (C % 4 || C / 4 > MB_THREADS || dy.pitch % 4 || dy.coff % 4 || y.pitch % 4 || y.coff % 4 || (planes.base && (!planes.lo_off || planes.pitch % 4 || planes.coff % 4))) {
+  if (C % 4 || C / 4 > MB_THREADS || dy.pitch % 4 || dy.coff % 4 || (y.base && (y.pitch % 4 || y.coff % 4)) || (planes.base && (!planes.lo_off || planes.pitch % 4 || planes.coff % 4))) {
     set_thread_error("mask_bias_split_f4: unsupported view"); return 1; }
   int ctas = (int)((rows + 255) / 256);
   if (ctas > 592) ctas = 592;                      // four CTAs per SM

@@ -282,6 +282,69 @@ __device__ void pspool_dev(const float* __restrict__ scores, int T, int D, int c
   }
 }
 
+// ---- STPPReorgainzed through column prefix sums ---------------------------------------------------------------------------
+// Every pooled part is a mean over a contiguous row range of the [T, D] score table, and the 1000 proposals of a video overlap
+// heavily: one exclusive scan down the rows (fp64, so that P[b] - P[a] is exact to fp32 rounding of the part's own sum), then
+// each part costs two loads instead of (b - a).  P has T + 1 rows.
+__global__ void colscan_f64_kernel(const float* __restrict__ scores, int T, int D, double* __restrict__ P) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double s = 0.0;
+  P[d] = 0.0;
+  for (int r = 0; r < T; ++r) {
+    s += (double)scores[(long long)r * D + d];
+    P[(long long)(r + 1) * D + d] = s;
+  }
+}
+
+__device__ void pspool_prefix_dev(const double* __restrict__ P, int T, int D, int col0, int score_len, const int* tk, float s0, float s1,
+                                  const ReorgCfg& cfg, float* __restrict__ out) {
+  for (int j = threadIdx.x; j < score_len; j += blockDim.x) {
+    float acc = 0.f;
+    int offset = 0;
+    for (int si = 0; si < 3; ++si) {
+      const float s = si == 0 ? s0 : (si == 2 ? s1 : 1.0f);
+      const int left = tk[si];
+      const int right = max(tk[si] + 1, tk[si + 1]);
+      if (right <= 0 || left >= T) { offset += cfg.cnt[si]; continue; }
+      for (int l = 0; l < cfg.nlev[si]; ++l) {
+        const int np_ = cfg.lev[si][l];
+        const double step = (double)(right - left) / (double)np_;
+        for (int q = 0; q < np_; ++q) {
+          const int pl = (int)((double)left + (double)q * step);
+          const int pr = (int)((double)left + (double)(q + 1) * step);
+          if (pr - pl >= 1) {
+            int a, b;
+            py_slice(pl, pr, T, a, b);
+            const int col = col0 + offset * score_len + j;
+            const float sum = (float)(P[(long long)b * D + col] - P[(long long)a * D + col]);
+            acc += (sum / (float)(b - a)) * s;
+          }
+          ++offset;
+        }
+      }
+    }
+    out[j] = acc;
+  }
+}
+
+__global__ void stpp_reorg_prefix_kernel(const double* __restrict__ P, int T, int D, const int32_t* __restrict__ ticks,
+                                         const float* __restrict__ scaling, int N, int act_len, int comp_len, int reg_len, ReorgCfg cfg, int mult,
+                                         float* __restrict__ out_act, float* __restrict__ out_comp, float* __restrict__ out_reg) {
+  const int i = blockIdx.x;
+  if (i >= N) return;
+  int tk[4] = {ticks[i * 4], ticks[i * 4 + 1], ticks[i * 4 + 2], ticks[i * 4 + 3]};
+  const float s0 = scaling[i * 2], s1 = scaling[i * 2 + 1];
+  {
+    int a, b;
+    py_slice(tk[1], max(tk[1] + 1, tk[2]), T, a, b);
+    for (int j = threadIdx.x; j < act_len; j += blockDim.x)
+      out_act[(long long)i * act_len + j] = (float)(P[(long long)b * D + j] - P[(long long)a * D + j]) / (float)(b - a);
+  }
+  pspool_prefix_dev(P, T, D, act_len, comp_len, tk, s0, s1, cfg, out_comp + (long long)i * comp_len);
+  pspool_prefix_dev(P, T, D, act_len + comp_len * mult, reg_len, tk, s0, s1, cfg, out_reg + (long long)i * reg_len);
+}
+
 __global__ void stpp_reorg_kernel(const float* __restrict__ scores, int T, int D, const int32_t* __restrict__ ticks,
                                   const float* __restrict__ scaling, int N, int act_len, int comp_len, int reg_len,
                                   ReorgCfg cfg, int mult, float* __restrict__ out_act, float* __restrict__ out_comp,
@@ -608,7 +671,9 @@ __global__ void __launch_bounds__(HL_THREADS) heads_loss_kernel(HeadsArgs a) {
     __syncthreads();
     if (threadIdx.x == 0) {
       const float la = cnt[0] ? lsum[0] / (float)cnt[0] : 0.f;
-      const float lc = lsum[1] / denom;
+      // the completeness rows must come in whole groups of comp_group per video (the reference's pred.view(-1, group, K) raises
+      // otherwise, ops/ssn_ops.py:225): signalled as a NaN completeness / total loss instead of silently dropping the tail rows
+      const float lc = (cnt[1] % G) ? __int_as_float(0x7fc00000) : lsum[1] / denom;
       const float lr = cnt[2] ? lsum[2] / (float)(2 * cnt[2]) * 2.f : 0.f;
       a.losses[0] = la; a.losses[1] = lc; a.losses[2] = lr; a.losses[3] = la + lc * c.comp_w + lr * c.reg_w;
     }
@@ -846,6 +911,32 @@ int ssnb_stpp_reorg(const float* scores, int T, int D, const int32_t* ticks, con
   return SSNB_OK;
 }
 
+size_t ssnb_stpp_reorg_workspace_bytes(int T, int D) { return (size_t)(T > 0 ? T + 1 : 0) * (size_t)(D > 0 ? D : 0) * sizeof(double); }
+
+int ssnb_stpp_reorg_prefix(const float* scores, int T, int D, const int32_t* ticks, const float* scaling, int N, int act_len,
+                           int comp_len, int reg_len, const int* level_counts, const int* levels, float* out_act,
+                           float* out_comp, float* out_reg, void* workspace, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!scores || !ticks || !scaling || !out_act || !out_comp || !out_reg || !workspace || T <= 0) { set_thread_error("stpp_reorg_prefix: bad argument"); return SSNB_EINVAL; }
+  ReorgCfg cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.nstage = 3;
+  int q = 0, mult = 0;
+  for (int st = 0; st < 3; ++st) {
+    if (level_counts[st] < 1 || level_counts[st] > 8) { set_thread_error("stpp_reorg: 1..8 pyramid levels per stage"); return SSNB_EINVAL; }
+    cfg.nlev[st] = level_counts[st];
+    for (int l = 0; l < level_counts[st]; ++l) { cfg.lev[st][l] = levels[q++]; cfg.cnt[st] += cfg.lev[st][l]; }
+    mult += cfg.cnt[st];
+  }
+  if (D != act_len + mult * (comp_len + reg_len)) { set_thread_error("stpp_reorg: D does not match act+M*(comp+reg)"); return SSNB_EINVAL; }
+  if (N == 0) return SSNB_OK;
+  double* P = reinterpret_cast<double*>(workspace);
+  colscan_f64_kernel<<<(D + 127) / 128, 128, 0, s>>>(scores, T, D, P);
+  SSNB_LAUNCH_CHECK("colscan_f64_kernel");
+  stpp_reorg_prefix_kernel<<<N, 128, 0, s>>>(P, T, D, ticks, scaling, N, act_len, comp_len, reg_len, cfg, mult, out_act, out_comp, out_reg);
+  SSNB_LAUNCH_CHECK("stpp_reorg_prefix_kernel");
+  return SSNB_OK;
+}
+
 int ssnb_linear_fwd(const float* x, const float* w, const float* b, int n, int in_dim, int out_dim, float* y, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!x || !w || !y) { set_thread_error("linear_fwd: null"); return SSNB_EINVAL; }
@@ -941,7 +1032,13 @@ int ssnb_heads_loss_fwd_bwd(const ssnb_heads_cfg* cfg, const float* course_ft, c
   if (cfg->feat_dim % HL_SLICE || cfg->n <= 0 || cfg->comp_group <= cfg->fg_per_video || cfg->comp_group - cfg->fg_per_video > 64 || !(cfg->comp_denom > 0.f)) {
     set_thread_error("heads_loss: feat_dim must be a multiple of 128; 1..64 negatives per group"); return SSNB_EINVAL; }
   const int slices = (cfg->feat_dim + cfg->feat_dim * cfg->feat_mult) / HL_SLICE;
-  if (slices > 148) { set_thread_error("heads_loss: more feature slices than SMs (grid barrier needs co-residency)"); return SSNB_ENOSUPPORT; }
+  // the three phases are separated by grid barriers: the launch is COOPERATIVE, so the runtime guarantees that all CTAs are
+  // co-resident (or fails the launch) whatever else occupies the device; validate the grid against the occupancy first
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heads_loss_kernel, HL_THREADS, 0) != cudaSuccess) {
+    cudaGetLastError(); set_thread_error("heads_loss: cannot query the device occupancy"); return SSNB_ECUDA; }
+  if (slices > per_sm * sms) { set_thread_error("heads_loss: more feature slices than co-resident CTAs (grid barrier)"); return SSNB_ENOSUPPORT; }
   const int ncols = (cfg->num_class + 1) + 3 * cfg->num_class;
   char* w = (char*)workspace;
   HeadsArgs a;
@@ -957,7 +1054,9 @@ int ssnb_heads_loss_fwd_bwd(const ssnb_heads_cfg* cfg, const float* course_ft, c
   a.drw = d_reg_w; a.drb = d_reg_b;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(a.barrier, 0, 256, s) != cudaSuccess) { set_thread_error("heads_loss: memset failed"); return SSNB_ECUDA; }
-  heads_loss_kernel<<<slices, HL_THREADS, 0, s>>>(a);
+  void* kargs[] = {(void*)&a};
+  if (cudaLaunchCooperativeKernel((const void*)heads_loss_kernel, dim3(slices), dim3(HL_THREADS), kargs, 0, s) != cudaSuccess) {
+    set_thread_error(std::string("heads_loss_kernel cooperative launch: ") + cudaGetErrorString(cudaGetLastError())); return SSNB_ECUDA; }
   SSNB_LAUNCH_CHECK("heads_loss_kernel");
   return SSNB_OK;
 }

@@ -209,16 +209,16 @@ __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
   const long long total = (long long)q.cout * q.cin * taps;
   const long long i = (long long)((int)blockIdx.x - q.block0) * blockDim.x + threadIdx.x;
   if (i < q.cout) {
-    const float s = q.gamma[i] / sqrtf(q.var[i] + 1e-5f);
+    const float s = q.nofold ? 1.0f : q.gamma[i] / sqrtf(q.var[i] + 1e-5f);
     q.scale[i] = s;
-    q.bias[i] = (q.b[i] - q.mean[i]) * s + q.beta[i];
+    q.bias[i] = q.nofold ? q.b[i] : (q.b[i] - q.mean[i]) * s + q.beta[i];
   }
   float av = 0.f;
   if (i < total) {
     const int tap = (int)(i % taps);
     const int ci = (int)((i / taps) % q.cin);
     const int co = (int)(i / ((long long)taps * q.cin));
-    const float s = q.gamma[co] / sqrtf(q.var[co] + 1e-5f);
+    const float s = q.nofold ? 1.0f : q.gamma[co] / sqrtf(q.var[co] + 1e-5f);
     const float fv = q.w[i] * s;
     const T v = from_f<T>(fv);
     reinterpret_cast<T*>(q.wf)[((long long)tap * q.cin + ci) * q.cout + co] = v;

@@ -68,11 +68,22 @@ class BNInception(nn.Module):
         for eng in self._engines.values():
             eng.packed_version = None
 
-    def engine_for(self, frames, training, device):
-        key = (frames, bool(training), self.precision, self.in_channels(), str(device))
+    def bn1_training(self):
+        """bn_mode='partial' (ssn_models.py:95-105): the first BatchNorm2d stays in training mode, every other one is frozen.
+        Returns True for that pattern, False when all are frozen, raises for anything else ('full')."""
+        bns = self._bns()
+        if any(b.training for b in bns[1:]):
+            raise NotImplementedError("only bn_mode='frozen' and 'partial' are accelerated: BatchNorm2d layers after the first must be in "
+                                      "eval mode ('full' is listed as a next step in DESIGN.md)")
+        return bool(bns[0].training)
+
+    def engine_for(self, frames, training, device, bn1_train=False):
+        if bn1_train and self.precision == _lib.FAST_FP16:
+            raise NotImplementedError("bn_mode='partial' runs in EXACT_FP32 / EXACT_TC precision (fp32 activations), not FAST_FP16")
+        key = (frames, bool(training), self.precision, self.in_channels(), str(device), bool(bn1_train))
         eng = self._engines.get(key)
         if eng is None:
-            eng = BackboneEngine(self.in_channels(), frames, self.precision, training, self.grad_scale, device)
+            eng = BackboneEngine(self.in_channels(), frames, self.precision, training, self.grad_scale, device, bn1_train=bn1_train)
             self._engines[key] = eng
         ver = self._weights_version()
         if eng.packed_version != ver:
@@ -86,16 +97,20 @@ class BNInception(nn.Module):
         if not input.is_cuda:
             raise RuntimeError("BNInception(B200) runs on CUDA only: move the model and input to the GPU "
                                "(libssn_b200 has no CPU path)")
-        for b in self._bns():
-            if b.training:
-                raise NotImplementedError("only bn_mode='frozen' (all BatchNorm2d in eval mode) is accelerated; "
-                                          "'partial'/'full' are listed as next steps in DESIGN.md")
+        bn1_train = self.bn1_training()
         cs = self._convs()
         params = [c.weight for c in cs] + [c.bias for c in cs]
+        bn1 = self._bns()[0]
+        if bn1_train:
+            params += [bn1.weight, bn1.bias]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        eng = self.engine_for(input.shape[0], need_grad, input.device)
+        eng = self.engine_for(input.shape[0], need_grad, input.device, bn1_train)
+        if bn1_train:
+            eng.set_bn1(bn1)                         # batch statistics + running-stat update happen inside the forward
+            if bn1.num_batches_tracked is not None:
+                bn1.num_batches_tracked.add_(1)
         if need_grad:
-            feat = BackboneFunction.apply(input, eng, len(cs), *params)
+            feat = BackboneFunction.apply(input, eng, len(cs), bn1 if bn1_train else None, *params)
         else:
             feat = eng.forward(input)
         return self.fc(feat)

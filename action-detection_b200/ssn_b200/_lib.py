@@ -47,6 +47,7 @@ SIGNATURES = {
     "ssnb_workspace_bytes": (_sz, [_vp]),
     "ssnb_set_workspace": (_i, [_vp, _vp, _sz]),
     "ssnb_pack_weights": (_i, [_vp, _pp, _pp, _pp, _pp, _pp, _pp, _vp]),
+    "ssnb_set_bn1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f]),
     "ssnb_backbone_fwd": (_i, [_vp, _vp, _vp, _vp]),
     "ssnb_backbone_bwd": (_i, [_vp, _vp, _pp, _pp, _vp]),
     "ssnb_backbone_bwd_range": (_i, [_vp, _vp, _pp, _pp, _i, _i, _vp]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "ssnb_stpp_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ip, _ip, _ip, _ip, _i, _i, _vp, _vp]),
     "ssnb_gpool_stpp_fwd": (_i, [_vp, _vp, _vp, _i, _i, _ip, _ip, _ip, _ip, _i, _i, _vp, _vp, _vp, _vp]),
     "ssnb_stpp_reorg": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp]),
+    "ssnb_stpp_reorg_workspace_bytes": (_sz, [_i, _i]),
+    "ssnb_stpp_reorg_prefix": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp]),
     "ssnb_linear_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "ssnb_test_fc_cropmean": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ssnb_linear_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

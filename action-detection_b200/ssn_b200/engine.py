@@ -31,10 +31,11 @@ def conv_table(in_channels):
 class BackboneEngine:
     """One planned BNInception instance for a fixed frame count (ssnb_create .. ssnb_destroy)."""
 
-    def __init__(self, in_channels, frames, precision, training, grad_scale, device):
+    def __init__(self, in_channels, frames, precision, training, grad_scale, device, bn1_train=False):
         self.device = torch.device(device)
         self.frames, self.in_channels, self.precision, self.training = frames, in_channels, precision, training
-        cfg = _lib.Config(in_channels, frames, precision, 1 if training else 0, float(grad_scale), (C.c_int32 * 3)())
+        self.bn1_train = bool(bn1_train)
+        cfg = _lib.Config(in_channels, frames, precision, 1 if training else 0, float(grad_scale), (C.c_int32 * 3)(1 if bn1_train else 0, 0, 0))
         self.h = C.c_void_p()
         check(lib.ssnb_create(C.byref(cfg), C.byref(self.h)), None, "ssnb_create")
         nbytes = lib.ssnb_workspace_bytes(self.h)
@@ -54,6 +55,12 @@ class BackboneEngine:
                 self.h = None
         except Exception:
             pass
+
+    def set_bn1(self, bn, dgamma=None, dbeta=None):
+        """bn1_train engines: the first BatchNorm2d module's tensors (training-mode statistics, running-stat update, gradients)"""
+        check(lib.ssnb_set_bn1(self.h, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                               None if dgamma is None else dgamma.data_ptr(), None if dbeta is None else dbeta.data_ptr(),
+                               float(bn.momentum if bn.momentum is not None else 0.1), float(bn.eps)), self.h, "set_bn1")
 
     # weights: lists of 69 tensors each, reference shapes
     def pack(self, w, b, gamma, beta, mean, var):
@@ -173,8 +180,9 @@ class BackboneFunction(torch.autograd.Function):
     direct_grad = True
 
     @staticmethod
-    def forward(ctx, x, engine, n_conv, *wb):
-        ctx.engine, ctx.n_conv = engine, n_conv
+    def forward(ctx, x, engine, n_conv, bn1, *wb):
+        # wb = 69 conv weights, 69 conv biases (+ the weight and bias of bn1, the first BatchNorm2d module, for a bn1_train engine)
+        ctx.engine, ctx.n_conv, ctx.bn1 = engine, n_conv, bn1
         ctx.params = wb
         feat = engine.forward(x)
         ctx.generation = engine.generation
@@ -197,6 +205,7 @@ class BackboneFunction(torch.autograd.Function):
             raise RuntimeError("BNInception(B200): another forward of %d frames ran through this engine after the one being "
                                "differentiated; its saved activations are gone.  Run backward before the next forward of the same "
                                "shape (or use different frame counts / a second model instance)." % eng.frames)
+        bn1 = getattr(ctx, "bn1", None)
         if BackboneFunction.direct_grad and BackboneFunction._direct_ok(ctx.params):
             grads = []
             for p in ctx.params:
@@ -206,11 +215,15 @@ class BackboneFunction(torch.autograd.Function):
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
                 grads.append(p.grad)
-            eng.backward(dfeat, grads[:n], grads[n:], accumulate=True)
-            return (None, None, None) + (None,) * len(ctx.params)
+            if bn1 is not None:
+                eng.set_bn1(bn1, grads[2 * n], grads[2 * n + 1])
+            eng.backward(dfeat, grads[:n], grads[n:2 * n], accumulate=True)
+            return (None, None, None, None) + (None,) * len(ctx.params)
         grads = [torch.empty(p.shape, dtype=torch.float32, device=dev) if p.requires_grad else None for p in ctx.params]
-        eng.backward(dfeat, grads[:n], grads[n:])
-        return (None, None, None) + tuple(grads)
+        if bn1 is not None:
+            eng.set_bn1(bn1, grads[2 * n], grads[2 * n + 1])
+        eng.backward(dfeat, grads[:n], grads[n:2 * n])
+        return (None, None, None, None) + tuple(grads)
 
 
 # ---- STPP ---------------------------------------------------------------------------------------------

@@ -63,15 +63,37 @@ class SSN(torch.nn.Module):
         else:
             raise ValueError('modality {} is outside the accelerated path (RGB, Flow)'.format(self.modality))
         import model_zoo
-        # the reference builds a 3-channel net and swaps conv1 for a mean-expanded kernel
-        # (_construct_flow_model :318-343); with random init only the shape matters.
-        self.base_model = model_zoo.BNInception(in_channels=in_ch)
+        if self.modality == 'Flow':
+            # like the reference: build the 3-channel network (this is where pretrained RGB weights would be loaded) and swap
+            # conv1 for the mean-expanded 2*new_length-channel kernel (_construct_flow_model, ssn_models.py:318-343)
+            self.base_model = self._construct_flow_model(model_zoo.BNInception(in_channels=3))
+            assert self.base_model.in_channels() == in_ch
+        else:
+            self.base_model = model_zoo.BNInception(in_channels=in_ch)
         self.base_model.last_layer_name = 'fc'
         self.input_size = 224
         self.input_mean = [104, 117, 128]
         self.input_std = [1]
         if self.modality == 'Flow':
             self.input_mean = [128]
+
+    def _construct_flow_model(self, base_model):
+        """replace the first convolution by one with 2*new_length input channels whose kernels are the mean of the RGB kernels
+        over the input-channel axis, bias kept (ssn_models.py:318-343)"""
+        name = base_model._conv_names[0]
+        conv_layer = getattr(base_model, name)
+        params = [x.clone() for x in conv_layer.parameters()]
+        kernel_size = params[0].size()
+        new_kernel_size = kernel_size[:1] + (2 * self.new_length,) + kernel_size[2:]
+        new_kernels = params[0].data.mean(dim=1, keepdim=True).expand(new_kernel_size).contiguous()
+        new_conv = nn.Conv2d(2 * self.new_length, conv_layer.out_channels, conv_layer.kernel_size, conv_layer.stride, conv_layer.padding,
+                             bias=True if len(params) == 2 else False)
+        new_conv.weight.data = new_kernels
+        if len(params) == 2:
+            new_conv.bias.data = params[1].data
+        setattr(base_model, name, new_conv)
+        base_model._engines = {}               # engines are planned per input-channel count
+        return base_model
 
     def _prepare_ssn(self, num_class, stpp_cfg):
         feature_dim = getattr(self.base_model, self.base_model.last_layer_name).in_features
@@ -250,9 +272,9 @@ class SSN(torch.nn.Module):
         assert self.with_regression, "fused_step implements the regression configuration"
         if not input.is_cuda:
             raise RuntimeError("SSN(B200).fused_step needs CUDA tensors (libssn_b200 has no CPU path)")
-        for b in self.base_model._bns():
-            if b.training:
-                raise NotImplementedError("fused_step implements bn_mode='frozen' (every BatchNorm2d in eval mode, ssn_models.py:156-174)")
+        if self.base_model.bn1_training():
+            raise NotImplementedError("fused_step implements bn_mode='frozen'; with bn_mode='partial' use the module path "
+                                      "(model(...), criteria, loss.backward()), which runs the first BatchNorm2d in training mode")
         frames = self._frames(input)
         bm = self.base_model
         eng = bm.engine_for(frames.shape[0], True, frames.device)

@@ -316,7 +316,8 @@ def main():
     if world > 1:
         # keep stdout to the one JSON line: whatever NCCL_DEBUG level the environment asks for goes to a file
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ssnb_nccl.%h.%p.log")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime       # a rank that falls out of step fails within minutes instead of NCCL's 10-minute default
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("SSNB_NCCL_TIMEOUT_S", "240"))))
 
     PREC = {"fast": _lib.FAST_FP16, "exact": _lib.EXACT_FP32, "exact_tc": _lib.EXACT_TC}
     DTYPE = {"fast": "f16 operands / f32 accumulate (tcgen05 kind::f16); parity partial",
@@ -497,16 +498,21 @@ def main():
         # ---- roofline: every launch of two eager steps timed with CUDA events on the launching stream (ssnb_timing_*),
         #      aggregated per kernel and pass; algorithmic FLOPs tagged by the engine.  Eager, not graph-replayed: the
         #      per-launch figures include the (small) launch gaps of an eager run, so they are a lower bound.
+        # EVERY rank runs the profiled steps (they contain the gradient all-reduce); rank 0 alone records and reports.
+        import ctypes as C
         roof = None
+        eager_step(batches[0]); torch.cuda.synchronize()
+        n_prof = 2
         if rank == 0:
-            import ctypes as C
-            eager_step(batches[0]); torch.cuda.synchronize()
             _lib.lib.ssnb_timing_begin(C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            n_prof = 2
-            for i in range(n_prof):
-                eager_step(batches[i % nb])
+        for i in range(n_prof):
+            eager_step(batches[i % nb])
+        if rank == 0:
             rows = parse_timing(_lib.lib.ssnb_timing_report())
             roof = roofline_from_rows(rows, n_prof, args.precision, peaks, peak_src, frames_gpu, args.modality)
+        barrier()
+
+        fused_bw = fused_gpool_stpp_bw(torch, _lib, model, frames_gpu, args.precision, l2_flush, peaks) if rank == 0 else None
 
         # ---- the other tensor-core mode, measured in the same run (half the steps) ----
         modes = None
@@ -524,6 +530,8 @@ def main():
             torch.cuda.empty_cache()
 
         stpp_info = stpp_bandwidth(torch, _lib, dev, l2_flush, peaks) if rank == 0 else None
+        if stpp_info is not None:
+            stpp_info["fused_gpool_stpp"] = fused_bw
         cpu = cpu_baseline_subprocess(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
         if rank == 0:
@@ -596,38 +604,81 @@ def roofline_from_rows(rows, n_steps, precision, peaks, peak_src, frames, modali
 
 
 def stpp_bandwidth(torch, _lib, dev, l2_flush, peaks):
-    """STPP HBM GB/s (the second half of BASELINE.json's metric): the standalone StructuredTemporalPyramidPooling kernels at the
-    bench shape (32 proposals: launch-latency bound) and at 16384 proposals where bandwidth is the bound.
+    """STPP HBM GB/s (the second half of BASELINE.json's metric): the standalone StructuredTemporalPyramidPooling kernels
+    (ssnb_stpp_fwd / ssnb_stpp_bwd through the C ABI, L2 flushed before every launch, best of 5) at the bench shape (32
+    proposals, 2 MB: launch-latency bound) and at 16384 proposals (1 GB) where HBM bandwidth is the bound.
+    Algorithmic bytes: 61,448 B per proposal each way (9 x 1024 x 4 in, 6 x 1024 x 4 out, 8 B scaling).
     A failure here never costs the bench line."""
     try:
+        import ctypes as C
         import ssn_models
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        model = ssn_models.SSN(20, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=STPP_CFG)
+        stpp = ssn_models.SSN(20, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=STPP_CFG).stpp
+        lo, hi, nm, col = stpp.part_table([2, 7, 9])
+        tab = [_lib.int_array(v) for v in (lo, hi, nm, col)]
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         out = {"hbm_peak_GB/s": hbm}
         for tag, n_prop in (("bench_shape", 32), ("large", 16384)):
-            ft = torch.randn(n_prop * SEG, 1024, device=dev, requires_grad=True)
+            ft = torch.randn(n_prop * SEG, 1024, device=dev)
             sc = torch.rand(n_prop, 2, device=dev)
+            course = torch.empty(n_prop, 1024, device=dev)
+            pooled = torch.empty(n_prop, len(lo) * 1024, device=dev)
+            dft = torch.empty_like(ft)
             best_f, best_b = 1e9, 1e9
-            for _ in range(4):
+            for _ in range(5):
                 l2_flush.zero_()
                 a.record()
-                ca, cc = model.stpp(ft, sc, [2, 7, 9])
+                rc = _lib.lib.ssnb_stpp_fwd(ft.data_ptr(), sc.data_ptr(), n_prop, SEG, 1024, len(lo), *tab, 2, 7, course.data_ptr(), pooled.data_ptr(), stream)
                 b.record(); b.synchronize()
                 best_f = min(best_f, a.elapsed_time(b))
-                g1, g2 = torch.ones_like(ca), torch.ones_like(cc)
                 l2_flush.zero_()
                 a.record()
-                torch.autograd.backward([ca, cc], [g1, g2])
+                rc |= _lib.lib.ssnb_stpp_bwd(course.data_ptr(), pooled.data_ptr(), sc.data_ptr(), n_prop, SEG, 1024, len(lo), *tab, 2, 7, dft.data_ptr(), stream)
                 b.record(); b.synchronize()
                 best_b = min(best_b, a.elapsed_time(b))
-                ft.grad = None
-            nbytes = ft.numel() * 4 + sc.numel() * 4 + ca.numel() * 4 + cc.numel() * 4       # 61,448 B/proposal (SURVEY 8d)
+                if rc:
+                    raise RuntimeError("ssnb_stpp rc=%d" % rc)
+            nbytes = ft.numel() * 4 + sc.numel() * 4 + course.numel() * 4 + pooled.numel() * 4
             out[tag] = {"proposals": n_prop, "bytes": int(nbytes),
                         "fwd": {"us": best_f * 1e3, "GB/s": nbytes / (best_f / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (best_f / 1e3) / 1e9 / hbm},
                         "bwd": {"us": best_b * 1e3, "GB/s": nbytes / (best_b / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (best_b / 1e3) / 1e9 / hbm}}
-            del ft, sc, ca, cc
+            del ft, sc, course, pooled, dft
         return out
+    except Exception as ex:
+        return {"error": repr(ex)[:300]}
+
+
+def fused_gpool_stpp_bw(torch, _lib, model, frames, precision, l2_flush, peaks):
+    """the fused 7x7 global-pool + STPP kernel at the bench shape: reads the 5b output once (F x 49 x 1024 elements, fp32 in
+    exact / exact_tc, fp16 in fast), writes feat + course + stpp"""
+    try:
+        import ctypes as C
+        dev = l2_flush.device
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        eng = model.base_model.engine_for(frames, True, dev)
+        n_prop = frames // SEG
+        lo, hi, nm, col = model.stpp.part_table([2, 7, 9])
+        feat = torch.empty(frames, 1024, device=dev)
+        course = torch.empty(n_prop, 1024, device=dev)
+        pooled = torch.empty(n_prop, len(lo) * 1024, device=dev)
+        sc = torch.rand(n_prop, 2, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(5):
+            l2_flush.zero_()
+            a.record()
+            rc = _lib.lib.ssnb_gpool_stpp_fwd(eng.h, None, C.c_void_p(sc.data_ptr()), SEG, len(lo), _lib.int_array(lo), _lib.int_array(hi),
+                                              _lib.int_array(nm), _lib.int_array(col), 2, 7, C.c_void_p(feat.data_ptr()),
+                                              C.c_void_p(course.data_ptr()), C.c_void_p(pooled.data_ptr()), stream)
+            b.record(); b.synchronize()
+            if rc != 0:
+                raise RuntimeError("ssnb_gpool_stpp_fwd rc=%d" % rc)
+            best = min(best, a.elapsed_time(b))
+        nbytes = frames * 49 * 1024 * (2 if precision == "fast" else 4) + feat.numel() * 4 + course.numel() * 4 + pooled.numel() * 4
+        return {"proposals": n_prop, "bytes": int(nbytes), "us": best * 1e3, "GB/s": nbytes / (best / 1e3) / 1e9,
+                "frac_of_hbm_peak": nbytes / (best / 1e3) / 1e9 / hbm}
     except Exception as ex:
         return {"error": repr(ex)[:300]}
 

@@ -37,7 +37,9 @@ typedef struct {
   int32_t training;    /* 1: keep activations + allocate gradient buffers */
   float grad_scale;    /* power-of-two loss scale: FAST scales dfeat (fp16 gradient storage); EXACT_TC scales the
                           fp16 operand planes of the output gradients (fp32 gradients themselves are unscaled) */
-  int32_t reserved[3];
+  int32_t bn1_train;   /* 1: the FIRST BatchNorm2d (conv1's) runs in training mode -- batch statistics, running-stat update, gradients for
+                          its weight / bias: bn_mode='partial' (ssn_models.py:95-105,156-174).  EXACT_FP32 / EXACT_TC only. */
+  int32_t reserved[2];
 } ssnb_config;
 
 /* ---- engine lifetime ---------------------------------------------------------------------- */
@@ -61,6 +63,11 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes);
  * b/gamma/beta/mean/var [cout].  Call after every optimizer step. */
 int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* b, const float* const* gamma,
                       const float* const* beta, const float* const* mean, const float* const* var, void* stream);
+/* bn1_train engines: the first BatchNorm2d's tensors (device pointers, 64 floats each).  gamma / beta / running stats are read
+ * (running stats also updated) by ssnb_backbone_fwd; dgamma / dbeta (may be NULL) are written by ssnb_backbone_bwd
+ * (added to when grad accumulation is on).  conv1's weights are then packed WITHOUT a BatchNorm fold. */
+int ssnb_set_bn1(ssnb_handle h, const float* gamma, const float* beta, float* running_mean, float* running_var, float* dgamma,
+                 float* dbeta, float momentum, float eps);
 /* input [F, C, 224, 224] fp32 NCHW (the reference's frame tensor after input.view(-1, C, H, W),
  * ssn_models.py:266) -> feat [F, 1024] fp32 (global_pool output, fc replaced by Identity/Dropout) */
 int ssnb_backbone_fwd(ssnb_handle h, const float* input_nchw, float* feat, void* stream);
@@ -124,6 +131,13 @@ int ssnb_gpool_stpp_fwd(ssnb_handle h, const float* drop_mask, const float* scal
 int ssnb_stpp_reorg(const float* scores, int T, int D, const int32_t* ticks, const float* scaling, int N,
                     int act_len, int comp_len, int reg_len, const int* level_counts, const int* levels,
                     float* out_act, float* out_comp, float* out_reg, void* stream);
+
+/* Same result through one fp64 exclusive column scan of scores (workspace: (T+1)*D doubles, ssnb_stpp_reorg_workspace_bytes)
+ * + one gather per proposal: every part costs two loads instead of its row count (1000 heavily overlapping proposals/video). */
+size_t ssnb_stpp_reorg_workspace_bytes(int T, int D);
+int ssnb_stpp_reorg_prefix(const float* scores, int T, int D, const int32_t* ticks, const float* scaling, int N, int act_len,
+                           int comp_len, int reg_len, const int* level_counts, const int* levels, float* out_act,
+                           float* out_comp, float* out_reg, void* workspace, void* stream);
 
 /* ---- heads: activity_fc / completeness_fc / regressor_fc (ssn_models.py:272-283) ------------- */
 int ssnb_linear_fwd(const float* x, const float* w, const float* b, int n, int in_dim, int out_dim, float* y,

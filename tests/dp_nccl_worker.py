@@ -27,7 +27,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     import ssn_models
     from ssn_b200 import _lib
     from ssn_b200.engine import heads_loss_fused
@@ -61,9 +62,9 @@ def main():
         errs[k] = rel(t, full[k])
     for k in keys[6:]:                       # per-row gradients: this rank's rows of the global result
         errs[k] = rel(part[k], full[k][rows])
-    losses = part["losses"].clone()
+    losses = part["losses"].clone()           # reported losses are per-rank means (only the gradients carry loss_scale): average them
     dist.all_reduce(losses)
-    errs["losses"] = rel(losses, full["losses"])
+    errs["losses"] = rel(losses / world, full["losses"])
     out["heads_64_videos"] = errs
     # ---- (2) whole step, 4 global videos, EXACT_TC ----
     K2 = 4
@@ -86,7 +87,7 @@ def main():
     m_part = model()
     vs = slice(rank * 2, rank * 2 + 2)
     l_part = m_part.fused_step(*[t[vs].to(dev) for t in batch], global_videos=4, loss_scale=1.0 / world)
-    l_sum = l_part.clone(); dist.all_reduce(l_sum)
+    l_sum = l_part.clone(); dist.all_reduce(l_sum); l_sum /= world
     worst, worst_name = 0.0, ""
     num = den = 0.0
     for (n_, p), (_n2, q) in zip(m_part.named_parameters(), m_full.named_parameters()):

@@ -112,3 +112,23 @@ def test_clock_sampler_survives_a_box_without_gpu():
     s = cs.summary()
     assert set(s) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"} and isinstance(s["reasons"], list)
     assert bench.usable_cores() >= 1
+
+
+def test_flow_model_conv1_is_mean_expanded():
+    """a4: SSN(modality='Flow') builds the 3-channel net and swaps conv1 for the 10-channel kernel that repeats the mean of
+    the RGB kernels over the input channels, bias kept (_construct_flow_model, ssn_models.py:318-343).  No GPU needed."""
+    import ssn_models
+    import model_zoo
+    torch.manual_seed(5)
+    rgb = model_zoo.BNInception(in_channels=3)
+    w3, b3 = rgb.conv1_7x7_s2.weight.data.clone(), rgb.conv1_7x7_s2.bias.data.clone()
+    torch.manual_seed(5)
+    m = ssn_models.SSN(4, 2, 5, 2, "Flow", base_model="BNInception", dropout=0)
+    c1 = m.base_model.conv1_7x7_s2
+    assert tuple(c1.weight.shape) == (64, 10, 7, 7) and c1.in_channels == 10 and m.base_model.in_channels() == 10
+    assert torch.equal(c1.bias.data, b3)
+    mean = w3.mean(dim=1, keepdim=True)
+    for ch in range(10):
+        assert torch.equal(c1.weight.data[:, ch:ch + 1], mean)
+    assert m.input_mean == [128] and m.new_length == 5
+    assert "base_model.conv1_7x7_s2.weight" in m.state_dict() and m.state_dict()["base_model.conv1_7x7_s2.weight"].shape[1] == 10
