@@ -102,11 +102,17 @@ struct PackEntry {
   void *wf, *wd; float *bias, *scale, *absmax;
   int cout, cin, k, block0;
   int nofold, pad_[3];          // nofold: scale = 1, bias' = b (the layer's BatchNorm runs in training mode, unfused)
+  float* bias_b;                // optional second copy of the folded bias (stacked bias of a fused sibling block)
 };
 struct PackTable { int n, pad_; PackEntry e[PACK_MAX]; };
 template <typename T> int launch_pack_all(const PackTable& t, int total_blocks, cudaStream_t s);
 // EXACT_TC: hi/lo planes of both fp32 weight layouts of many layers per launch (scale from each layer's absmax, see launch_split_flat)
-struct SplitEntry { const float *wf, *wd; __half *wf16, *wd16; long long plane_bytes, n; const float* absmax; float* inv_scale; int block0, pad_; };
+struct SplitEntry {
+  const float *wf, *wd; __half *wf16, *wd16; long long plane_bytes, n; const float* absmax; float* inv_scale; int block0, pad_;
+  // optional second copies inside a fused sibling block's operands (1x1 layers): wd rows stacked (contiguous), wf columns inside the
+  // K-concatenated matrix [cin][b_pitch]; b_plane_bytes = distance to the LO plane of those buffers
+  __half *wd16_b, *wf16_b; long long b_plane_bytes; int b_pitch, cout;
+};
 struct SplitTable { int n, pad_; SplitEntry e[PACK_MAX]; };
 int launch_split_all(const SplitTable& t, int total_blocks, cudaStream_t s);
 

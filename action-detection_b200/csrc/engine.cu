@@ -104,6 +104,7 @@ struct FusedBlock {
   int op1 = -1, op_r3 = -1, op_rd = -1;   // op indices (op1 = -1 for 3c/4e)
   int c1 = 0, c3r = 0, cdr = 0, cx = 0;
   size_t w_fwd = 0, bias = 0, w_dg = 0;   // stacked forward weights/bias, K-concatenated data-gradient weights
+  size_t w_fwd_plane = 0, w_dg_plane = 0, wmax = 0;   // EXACT_TC: LO plane distance of both; shared (absmax, 1/scale) slot of the three layers
   UmmaConvPlan fwd, dgrad;
   bool enabled = false;
 };
@@ -293,7 +294,7 @@ static void plan(ssnb_engine* e) {
   if (e->tc) {      // per layer: [0] max |folded weight| (atomicMax target, zeroed before every pack), [1] 1 / plane scale (the kernels' alpha_dev)
     e->wmax_off = off;
     for (size_t i = 0; i < e->convs.size(); ++i) e->packed[i].wmax = off + i * 8;
-    off = align_up(off + e->convs.size() * 8, 1024);
+    off = align_up(off + (e->convs.size() + 16) * 8, 1024);     // + one shared slot per fused sibling block
   }
   // backward bookkeeping: accumulate flags + split-K sizing
   size_t pmax = 0;
@@ -322,7 +323,7 @@ static void plan(ssnb_engine* e) {
       }
     }
   }
-  if (e->fp16) {
+  if (e->fp16 || e->tc) {
     for (int i = 0; i < (int)e->ops.size(); ++i) {
       const Op& o = e->ops[i];
       if (o.kind != OP_CONV || o.k != 1) continue;
@@ -339,11 +340,20 @@ static void plan(ssnb_engine* e) {
       fb.cx = e->convs[o.conv].cin; fb.c3r = e->convs[o.conv].cout; fb.cdr = e->convs[e->ops[fb.op_rd].conv].cout;
       fb.c1 = fb.op1 >= 0 ? e->convs[e->ops[fb.op1].conv].cout : 0;
       const int n = fb.c1 + fb.c3r + fb.cdr, kf = (fb.c1 + 63) / 64 * 64 + fb.c3r + fb.cdr;
-      fb.w_fwd = off; off = align_up(off + (size_t)n * fb.cx * 2, 1024);
+      fb.w_fwd_plane = align_up((size_t)n * fb.cx * 2, 1024); fb.w_dg_plane = align_up((size_t)fb.cx * kf * 2, 1024);
+      if (e->tc) fb.w_fwd_plane = fb.w_dg_plane = std::max(fb.w_fwd_plane, fb.w_dg_plane);     // one LO-plane distance for both (split_all_kernel)
+      fb.w_fwd = off; off += (e->tc ? 2 : 1) * fb.w_fwd_plane;
       fb.bias = off; off = align_up(off + (size_t)n * 4, 256);
-      fb.w_dg = off; off = align_up(off + (size_t)fb.cx * kf * 2, 1024);
+      fb.w_dg = off; off += (e->tc ? 2 : 1) * fb.w_dg_plane;
+      if (e->tc) {       // the three layers share ONE power-of-two plane scale (their operands are stacked / K-concatenated in one launch)
+        if (e->fused.size() >= 16) continue;
+        fb.wmax = e->wmax_off + (e->convs.size() + e->fused.size()) * 8;
+        for (int j : {fb.op1, fb.op_r3, fb.op_rd}) if (j >= 0) e->packed[e->ops[j].conv].wmax = fb.wmax;
+      }
       e->fused.push_back(fb);
     }
+  }
+  if (e->fp16) {
     for (int i = 0; i < (int)e->ops.size(); ++i) {
       Op& po = e->ops[i];
       if (po.kind != OP_MAXPOOL || po.k != 3 || po.stride != 2) continue;
@@ -775,6 +785,50 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     }
     h->fold_pools = false;
     for (FusedBlock& fb : h->fused) fb.enabled = false;
+    const char* disf_sib = getenv("SSNB_DISABLE_FUSION");
+    if (use_tc && !(disf_sib && disf_sib[0] == '1')) {
+      // horizontal fusion of the sibling 1x1 convolutions of each inception block: ONE forward launch (stacked weights; the first
+      // c1 columns land in the concat buffer, the rest in the shared reduce buffer) and ONE data-gradient launch (K-concatenated
+      // dz planes from two sources) instead of three read-modify-write passes over the block input's gradient
+      for (size_t bi = 0; bi < h->fused.size(); ++bi) {
+        FusedBlock& fb = h->fused[bi];
+        Op& o3 = h->ops[fb.op_r3]; Op& od = h->ops[fb.op_rd];
+        if (!o3.umma.enabled || !od.umma.enabled) continue;
+        const View xp = h->planes(o3.in_val, false);
+        View redp = h->planes(o3.out_val, false); redp.C = fb.c3r + fb.cdr;
+        const View red32 = h->view(o3.out_val, false);
+        const float* alpha_dev = (const float*)(h->ws + fb.wmax) + 1;
+        int rc;
+        UmmaTcOpts t; t.w_lo_off = (long long)fb.w_fwd_plane; t.alpha = 1.0f; t.alpha_dev = alpha_dev;
+        if (fb.op1 >= 0) {
+          t.out32 = (float*)h->view(h->ops[fb.op1].out_val, false).base; t.out32_2 = (float*)red32.base;
+          rc = umma_conv_bind_fused_fwd(h->umma_ctx, fb.fwd, xp, h->planes(h->ops[fb.op1].out_val, false), redp, h->F, fb.cx, fb.c1, fb.c3r + fb.cdr,
+                                        (const __half*)(h->ws + fb.w_fwd), (const float*)(h->ws + fb.bias), &t);
+        } else {
+          t.out32 = (float*)red32.base;
+          rc = umma_conv_bind_fwd(h->umma_ctx, fb.fwd, xp, redp, h->F, fb.cx, fb.c3r + fb.cdr, 1, 0, 1, (const __half*)(h->ws + fb.w_fwd),
+                                  (const float*)(h->ws + fb.bias), &t);
+        }
+        if (rc) return h->fail(rc, "tc fused fwd bind(" + o3.id + "): " + ssnb::thread_error());
+        if (!fb.fwd.p.v2) continue;
+        if (h->cfg.training) {
+          View dredp = h->planes(o3.out_val, true); dredp.C = fb.c3r + fb.cdr;
+          View d1p = fb.op1 >= 0 ? h->planes(h->ops[fb.op1].out_val, true) : dredp;
+          View dxp = h->planes(o3.in_val, true); dxp.base = nullptr; dxp.lo_off = 0;
+          UmmaTcOpts tg; tg.w_lo_off = (long long)fb.w_dg_plane; tg.out32 = (float*)h->view(o3.in_val, true).base; tg.alpha = 1.0f / gs; tg.alpha_dev = alpha_dev;
+          rc = umma_conv_bind_fused_dgrad(h->umma_ctx, fb.dgrad, d1p, dredp, dxp, h->F, fb.cx, fb.c1, fb.c3r + fb.cdr, (const __half*)(h->ws + fb.w_dg),
+                                          od.grad_accumulate, &tg);
+          if (rc) return h->fail(rc, "tc fused dgrad bind(" + o3.id + "): " + ssnb::thread_error());
+          if (!fb.dgrad.p.v2) continue;
+          // zero the K padding of the concatenated data-gradient weights once (both planes); split_all_kernel never writes it
+          if (cudaMemset(h->ws + fb.w_dg, 0, 2 * fb.w_dg_plane) != cudaSuccess) cudaGetLastError();
+        }
+        fb.enabled = true;
+        const int leader = fb.op1 >= 0 ? fb.op1 : fb.op_r3;
+        for (int j : {fb.op1, fb.op_r3, fb.op_rd})
+          if (j >= 0) { h->ops[j].fuse_block = (int)bi; h->ops[j].fuse_role = (j == leader) ? 1 : 2; }
+      }
+    }
     // ReLU-mask fusion (same rule as the FAST schedule below): the consumer with the smallest forward index is the LAST writer
     // of a value's gradient in the reverse schedule; when that is a tensor-core data gradient its fp32 epilogue applies
     // dz = dy * (y > 0) and emits the value's gradient operand planes (dz * grad_scale), so the producing convolutions run
@@ -793,7 +847,10 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
         for (const Op& q : h->ops) conv_made = conv_made || (q.kind == OP_CONV && h->vals[q.out_val].buf == h->vals[v].buf);
         if (!conv_made) continue;
         Op& c = h->ops[fc];
-        if (c.kind == OP_CONV && c.umma_dgrad.enabled) {
+        if (c.kind == OP_CONV && c.fuse_role == 1 && h->fused[c.fuse_block].enabled) {
+          c.dgrad_masks = true;
+          umma_conv_set_mask_tc(h->fused[c.fuse_block].dgrad, h->view((int)v, false), h->planes((int)v, true), gs, h->tc_flag);
+        } else if (c.kind == OP_CONV && c.fuse_role == 0 && c.umma_dgrad.enabled) {
           c.dgrad_masks = true;
           umma_conv_set_mask_tc(c.umma_dgrad, h->view((int)v, false), h->planes((int)v, true), gs, h->tc_flag);
         }
@@ -927,39 +984,69 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
                       const float* const* beta, const float* const* mean, const float* const* var, void* stream) {
   if (!h || !h->ws) return h ? h->fail(SSNB_ESTATE, "set_workspace first") : SSNB_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->tc && cudaMemsetAsync(h->ws + h->wmax_off, 0, h->convs.size() * 8, s) != cudaSuccess) return h->fail(SSNB_ECUDA, "pack_weights: memset");
+  if (h->tc && cudaMemsetAsync(h->ws + h->wmax_off, 0, (h->convs.size() + 16) * 8, s) != cudaSuccess) return h->fail(SSNB_ECUDA, "pack_weights: memset");
   {
-    // fold + re-layout of all 69 layers in a few launches (PACK_MAX entries per launch)
-    PackTable t; t.n = 0; t.pad_ = 0;
-    SplitTable st; st.n = 0; st.pad_ = 0;
-    int blocks = 0, sblocks = 0;
-    auto flush = [&]() -> int {
-      int rc = h->fp16 ? launch_pack_all<__half>(t, blocks, s) : launch_pack_all<float>(t, blocks, s);
-      if (!rc && h->tc) rc = launch_split_all(st, sblocks, s);
-      t.n = 0; st.n = 0; blocks = 0; sblocks = 0;
-      return rc;
-    };
+    // fold + re-layout of all 69 layers in a few launches (PACK_MAX entries per launch); EXACT_TC: every fold launch first (the
+    // layers of a fused sibling block share one absmax slot), then the hi/lo splits
+    struct Member { int block = -1, row = 0, col = 0; };
+    std::vector<Member> member(h->convs.size());
+    for (size_t bi = 0; bi < h->fused.size(); ++bi) {
+      const FusedBlock& fb = h->fused[bi];
+      if (!fb.enabled) continue;
+      const int k1p = (fb.c1 + 63) / 64 * 64;
+      int row = 0, col = 0;
+      for (int j : {fb.op1, fb.op_r3, fb.op_rd}) {
+        if (j < 0) continue;
+        const int ci = h->ops[j].conv;
+        member[ci].block = (int)bi; member[ci].row = row; member[ci].col = col;
+        row += h->convs[ci].cout;
+        col += (j == fb.op1) ? k1p : h->convs[ci].cout;
+      }
+    }
+    std::vector<PackTable> pt(1);
+    std::vector<SplitTable> stt(1);
+    std::vector<int> pblocks(1, 0), sblocks(1, 0);
+    pt[0].n = 0; pt[0].pad_ = 0; stt[0].n = 0; stt[0].pad_ = 0;
     for (size_t i = 0; i < h->convs.size(); ++i) {
       const ConvSpec& c = h->convs[i];
       const PackedConv& p = h->packed[i];
       const long long n = (long long)c.cout * c.cin * c.k * c.k;
-      PackEntry& q = t.e[t.n++];
+      if (pt.back().n == PACK_MAX) { pt.emplace_back(); pt.back().n = 0; pt.back().pad_ = 0; pblocks.push_back(0); stt.emplace_back(); stt.back().n = 0; stt.back().pad_ = 0; sblocks.push_back(0); }
+      const Member& mb = member[i];
+      const FusedBlock* fb = mb.block >= 0 ? &h->fused[mb.block] : nullptr;
+      PackEntry& q = pt.back().e[pt.back().n++];
       q.w = w[i]; q.b = b[i]; q.gamma = gamma[i]; q.beta = beta[i]; q.mean = mean[i]; q.var = var[i];
       q.wf = h->ws + p.wf; q.wd = h->ws + p.wd; q.bias = (float*)(h->ws + p.bias); q.scale = (float*)(h->ws + p.scale);
       q.absmax = h->tc ? (float*)(h->ws + p.wmax) : nullptr;
-      q.cout = c.cout; q.cin = c.cin; q.k = c.k; q.block0 = blocks;
+      q.cout = c.cout; q.cin = c.cin; q.k = c.k; q.block0 = pblocks.back();
       q.nofold = (h->bn1_train && i == 0) ? 1 : 0; q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
-      blocks += (int)((std::max<long long>(n, c.cout) + 255) / 256);
+      q.bias_b = (h->tc && fb) ? (float*)(h->ws + fb->bias) + mb.row : nullptr;
+      pblocks.back() += (int)((std::max<long long>(n, c.cout) + 255) / 256);
       if (h->tc) {
-        SplitEntry& e = st.e[st.n++];
+        SplitEntry& e = stt.back().e[stt.back().n++];
         e.wf = (const float*)(h->ws + p.wf); e.wd = (const float*)(h->ws + p.wd);
         e.wf16 = (__half*)(h->ws + p.wf16); e.wd16 = (__half*)(h->ws + p.wd16); e.plane_bytes = (long long)p.wplane; e.n = n;
-        e.absmax = (const float*)(h->ws + p.wmax); e.inv_scale = (float*)(h->ws + p.wmax) + 1; e.block0 = sblocks; e.pad_ = 0;
-        sblocks += (int)((n + 255) / 256);
+        e.absmax = (const float*)(h->ws + p.wmax); e.inv_scale = (float*)(h->ws + p.wmax) + 1; e.block0 = sblocks.back(); e.pad_ = 0;
+        e.wd16_b = nullptr; e.wf16_b = nullptr; e.b_plane_bytes = 0; e.b_pitch = 0; e.cout = c.cout;
+        if (fb) {
+          const int kf = (fb->c1 + 63) / 64 * 64 + fb->c3r + fb->cdr;
+          e.wd16_b = (__half*)(h->ws + fb->w_fwd) + (size_t)mb.row * fb->cx;      // stacked forward rows [n][cx]
+          e.wf16_b = (__half*)(h->ws + fb->w_dg) + mb.col;                         // column block of [cx][kf]
+          e.b_pitch = kf;
+          // both fused buffers are written through ONE plane distance per entry: the kernel applies it to wd16_b and wf16_b alike,
+          // so the two buffers are planned with equal plane sizes (max of the two)
+          e.b_plane_bytes = (long long)std::max(fb->w_fwd_plane, fb->w_dg_plane);
+        }
+        sblocks.back() += (int)((n + 255) / 256);
       }
-      if (t.n == PACK_MAX) if (int rc = flush()) return h->fail(rc, "pack_weights: " + ssnb::thread_error());
     }
-    if (int rc = flush()) return h->fail(rc, "pack_weights: " + ssnb::thread_error());
+    for (size_t k = 0; k < pt.size(); ++k) {
+      int rc = h->fp16 ? launch_pack_all<__half>(pt[k], pblocks[k], s) : launch_pack_all<float>(pt[k], pblocks[k], s);
+      if (rc) return h->fail(rc, "pack_weights: " + ssnb::thread_error());
+    }
+    if (h->tc)
+      for (size_t k = 0; k < stt.size(); ++k)
+        if (int rc = launch_split_all(stt[k], sblocks[k], s)) return h->fail(rc, "pack_weights split: " + ssnb::thread_error());
   }
   if (h->tc && h->ops.size() && h->ops[0].umma.enabled) {
     for (int pl = 0; pl < 2; ++pl) {
@@ -974,7 +1061,7 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
     if (rc) return h->fail(rc, "pack conv1 s2d: " + ssnb::thread_error());
   }
   for (FusedBlock& fb : h->fused) {
-    if (!fb.enabled) continue;
+    if (!fb.enabled || !h->fp16) continue;          // EXACT_TC: split_all_kernel wrote the fused operands directly
     // forward: rows of wd ([co][ci]) stacked; bias stacked.  data gradient: wf ([ci][co]) concatenated along K,
     // the 1x1 part padded to a multiple of 64 so each K chunk has a single activation source.
     const int k1p = (fb.c1 + 63) / 64 * 64, kf = k1p + fb.c3r + fb.cdr;

@@ -163,21 +163,21 @@ __global__ void stpp_bwd_v4_kernel(const float* __restrict__ dcourse, const floa
 }
 
 // ---- fused 7x7 global average pool (+ dropout mask) + STPP, second generation ------------------------------------------
-// CTA = (proposal, 256-channel slab), 256 threads = (16-byte channel groups of the slab) x (pixel lanes): every thread
-// accumulates its pixel subset of all S frames in registers (S x HW/lanes independent 16-byte loads, consecutive threads on
-// consecutive 16-byte chunks of a pixel row), the pixel lanes are reduced through shared memory, then thread c forms the
-// parts of channel c from the S pooled values.  Reads the 5b output exactly once with 128 x (C/256) x n CTAs in flight;
-// the first-generation kernel gave every thread a serial chain of S x HW 2-byte loads.
-template <typename T, int SMAX>
+// CTA = (proposal, SLAB-channel slab), 256 threads = (16-byte channel groups of the slab) x (pixel lanes): every thread
+// accumulates its pixel subset of all S frames in registers (S independent 16-byte loads in flight per pixel step, consecutive
+// threads on consecutive 16-byte chunks of a pixel row), the pixel lanes are reduced through shared memory, then thread c forms
+// the parts of channel c from the S pooled values.  Reads the 5b output exactly once with n x C/SLAB CTAs in flight (256 at the
+// bench shape); the first-generation kernel gave every thread a serial chain of S x HW 2-byte loads.
+template <typename T, int SMAX, int SLAB>
 __global__ void __launch_bounds__(256) gpool_stpp_v2_kernel(const T* __restrict__ src, int HW, int C, int pitch, int coff, int n, int S,
                                                             const float* __restrict__ mask, const float* __restrict__ scaling, PartTable pt,
                                                             float* __restrict__ feat, float* __restrict__ course, float* __restrict__ stpp) {
   constexpr int VEC = 16 / sizeof(T);              // channels per 16-byte load: 8 (fp16) or 4 (fp32)
-  constexpr int G = 256 / VEC;                     // channel groups per slab: 32 / 64
-  constexpr int L = 256 / G;                       // pixel lanes: 8 / 4
-  extern __shared__ float red[];                   // [L][SMAX][256]
+  constexpr int G = SLAB / VEC;                    // channel groups per slab
+  constexpr int L = 256 / G;                       // pixel lanes
+  extern __shared__ float red[];                   // [L][SMAX][SLAB]
   const long long p = blockIdx.x;
-  const int c0 = blockIdx.y * 256;
+  const int c0 = blockIdx.y * SLAB;
   const int g = threadIdx.x % G, l = threadIdx.x / G;
   float acc[SMAX][VEC];
 #pragma unroll
@@ -186,18 +186,22 @@ __global__ void __launch_bounds__(256) gpool_stpp_v2_kernel(const T* __restrict_
     for (int j = 0; j < VEC; ++j) acc[t][j] = 0.f;
   const bool live = c0 + g * VEC < C;
   if (live) {
+    const T* base = src + (p * S * HW) * pitch + coff + c0 + g * VEC;
+    // pixel loop outside, frame loop unrolled inside: S independent 16-byte loads in flight per iteration
+    for (int q = l; q < HW; q += L) {
+      uint4 r[SMAX];
 #pragma unroll
-    for (int t = 0; t < SMAX; ++t) {
-      if (t >= S) break;
-      const T* base = src + ((p * S + t) * HW) * pitch + coff + c0 + g * VEC;
-      for (int q = l; q < HW; q += L) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(base + (long long)q * pitch));
+      for (int t = 0; t < SMAX; ++t)
+        if (t < S) r[t] = __ldg(reinterpret_cast<const uint4*>(base + ((long long)t * HW + q) * pitch));
+#pragma unroll
+      for (int t = 0; t < SMAX; ++t) {
+        if (t >= S) continue;
         if (sizeof(T) == 2) {
-          const __half2* h = reinterpret_cast<const __half2*>(&r);
+          const __half2* h = reinterpret_cast<const __half2*>(&r[t]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h[j]); acc[t][(2 * j) % VEC] += f2.x; acc[t][(2 * j + 1) % VEC] += f2.y; }
         } else {
-          acc[t][0] += __uint_as_float(r.x); acc[t][1 % VEC] += __uint_as_float(r.y); acc[t][2 % VEC] += __uint_as_float(r.z); acc[t][3 % VEC] += __uint_as_float(r.w);
+          acc[t][0] += __uint_as_float(r[t].x); acc[t][1 % VEC] += __uint_as_float(r[t].y); acc[t][2 % VEC] += __uint_as_float(r[t].z); acc[t][3 % VEC] += __uint_as_float(r[t].w);
         }
       }
     }
@@ -205,8 +209,9 @@ __global__ void __launch_bounds__(256) gpool_stpp_v2_kernel(const T* __restrict_
 #pragma unroll
   for (int t = 0; t < SMAX; ++t)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) red[(l * SMAX + t) * 256 + g * VEC + j] = acc[t][j];
+    for (int j = 0; j < VEC; ++j) red[(l * SMAX + t) * SLAB + g * VEC + j] = acc[t][j];
   __syncthreads();
+  if (threadIdx.x >= SLAB) return;
   const int c = c0 + threadIdx.x;
   if (c >= C) return;
   float pooled[SMAX];
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(256) gpool_stpp_v2_kernel(const T* __restrict_
   for (int t = 0; t < SMAX; ++t) {
     float s = 0.f;
 #pragma unroll
-    for (int ll = 0; ll < L; ++ll) s += red[(ll * SMAX + t) * 256 + threadIdx.x];
+    for (int ll = 0; ll < L; ++ll) s += red[(ll * SMAX + t) * SLAB + threadIdx.x];
     float v = s / (float)HW;
     if (t < S) {
       const long long f = p * S + t;
@@ -867,20 +872,21 @@ int ssnb_gpool_stpp_fwd(ssnb_handle h, const float* drop_mask, const float* scal
   const int n = F / n_seg;
   const long long tot = (long long)n * v.C;
   if (n_seg <= 9 && v.C % 8 == 0 && v.pitch % 8 == 0 && v.coff % 8 == 0) {
-    // second-generation kernel: CTA = (proposal, 256-channel slab)
+    // second-generation kernel: CTA = (proposal, 128-channel slab)
+    constexpr int SLAB = 128;
     static bool attr_set[64][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = (size_t)(fp16 ? 8 : 4) * 9 * 256 * 4;
+    const size_t smem = (size_t)(fp16 ? 256 / (SLAB / 8) : 256 / (SLAB / 4)) * 9 * SLAB * 4;
     if (dev >= 0 && dev < 64 && !attr_set[dev][fp16 ? 1 : 0]) {
-      cudaError_t e = fp16 ? cudaFuncSetAttribute(gpool_stpp_v2_kernel<__half, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(gpool_stpp_v2_kernel<float, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = fp16 ? cudaFuncSetAttribute(gpool_stpp_v2_kernel<__half, 9, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(gpool_stpp_v2_kernel<float, 9, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { cudaGetLastError(); set_thread_error("gpool_stpp: cannot raise the dynamic shared memory limit"); return SSNB_ECUDA; }
       attr_set[dev][fp16 ? 1 : 0] = true;
     }
-    dim3 grid((unsigned)n, (unsigned)((v.C + 255) / 256));
-    if (fp16) gpool_stpp_v2_kernel<__half, 9><<<grid, 256, smem, s>>>((const __half*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
-    else gpool_stpp_v2_kernel<float, 9><<<grid, 256, smem, s>>>((const float*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
+    dim3 grid((unsigned)n, (unsigned)((v.C + SLAB - 1) / SLAB));
+    if (fp16) gpool_stpp_v2_kernel<__half, 9, SLAB><<<grid, 256, smem, s>>>((const __half*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
+    else gpool_stpp_v2_kernel<float, 9, SLAB><<<grid, 256, smem, s>>>((const float*)v.base, v.H * v.W, v.C, v.pitch, v.coff, n, n_seg, drop_mask, scaling, pt, feat, course_ft, stpp_ft);
     SSNB_LAUNCH_CHECK("gpool_stpp_v2_kernel");
     return SSNB_OK;
   }

@@ -212,6 +212,7 @@ __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
     const float s = q.nofold ? 1.0f : q.gamma[i] / sqrtf(q.var[i] + 1e-5f);
     q.scale[i] = s;
     q.bias[i] = q.nofold ? q.b[i] : (q.b[i] - q.mean[i]) * s + q.beta[i];
+    if (q.bias_b) q.bias_b[i] = q.bias[i];
   }
   float av = 0.f;
   if (i < total) {

@@ -81,8 +81,15 @@ __global__ void split_all_kernel(const __grid_constant__ SplitTable t) {
     const float v = (l ? q.wd : q.wf)[i] * sc;
     __half* hi = l ? q.wd16 : q.wf16;
     const __half h = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(h));
     hi[i] = h;
-    *reinterpret_cast<__half*>(reinterpret_cast<char*>(hi + i) + q.plane_bytes) = __float2half_rn(v - __half2float(h));
+    *reinterpret_cast<__half*>(reinterpret_cast<char*>(hi + i) + q.plane_bytes) = lo;
+    __half* hb = l ? q.wd16_b : q.wf16_b;
+    if (hb) {                                   // 1x1 member of a fused sibling block: wd[co][ci] rows stacked, wf[ci][co] as a column block
+      const long long j = l ? i : (i / q.cout) * (long long)q.b_pitch + (i % q.cout);
+      hb[j] = h;
+      *reinterpret_cast<__half*>(reinterpret_cast<char*>(hb + j) + q.b_plane_bytes) = lo;
+    }
   }
 }
 

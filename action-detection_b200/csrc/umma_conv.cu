@@ -125,8 +125,8 @@ __device__ __forceinline__ void epilogue_loop_direct(const UmmaConvParams& p, ui
         tmem_ld16(taddr + c0, ra);
         if (two) tmem_ld16(taddr + c0 + 16, rb);
         tmem_ld_wait();
-        if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr, mrow32 ? mrow32 + cola : nullptr);
-        if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr, mrow32 ? mrow32 + colb : nullptr);
+        if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, p.bias + cola, orow32 + cola, hrow ? hrow + cola : nullptr, mrow32 ? mrow32 + cola : nullptr, p.out_lo_off);
+        if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, p.bias + colb, orow32 + colb, hrow ? hrow + colb : nullptr, mrow32 ? mrow32 + colb : nullptr, p.out_lo_off);
       }
       tc_fence_before();
       __syncwarp();
@@ -396,6 +396,7 @@ int bind_common(UmmaContext& ctx, UmmaConvPlan& plan, View a, View o, int F, int
   p.nseg = tc ? 3 : 1; p.out_f32 = tc ? 1 : 0; p.alpha = tc ? tc->alpha : 1.0f; p.alpha_dev = tc ? tc->alpha_dev : nullptr;
   p.mask32 = nullptr; p.mask32_pitch = 0; p.mask32_coff = 0; p.plane_scale = 1.0f; p.flag = nullptr;
   p.out32 = tc ? tc->out32 : nullptr; p.out_hi = tc ? reinterpret_cast<__half*>(o.base) : nullptr; p.out_lo_off = tc ? o.lo_off : 0;
+  p.out32_2 = p.out32; p.out_hi2 = p.out_hi; p.out_lo_off2 = p.out_lo_off;       // second destination = the first unless a fused bind redirects it
   if (tc && (!tc->out32 || !a.lo_off || !tc->w_lo_off)) { set_thread_error("umma conv: split-operand bind needs operand planes and an fp32 output"); return 1; }
   plan.enabled = true;
   return 0;
@@ -576,23 +577,27 @@ int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx,
 }
 
 int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out1, View out2, int F, int cin, int n1, int n2,
-                             const __half* w_n_k, const float* bias) {
+                             const __half* w_n_k, const float* bias, const UmmaTcOpts* tc) {
   // bind as one convolution with N = n1 + n2 writing to out1's geometry, then redirect columns >= n1
   View o = out1; o.C = n1 + n2;
   if (out1.H != out2.H || out1.W != out2.W || n1 % 16 || n2 % 16 || out2.pitch % 8 || out2.coff % 8) { set_thread_error("fused fwd: bad views"); return 1; }
-  if (int rc = bind_common(ctx, plan, in, o, F, cin, n1 + n2, 1, 1, w_n_k)) return rc;
+  if (int rc = bind_common(ctx, plan, in, o, F, cin, n1 + n2, 1, 1, w_n_k, 1, tc)) return rc;
   plan.p.tap_dy[0] = 0; plan.p.tap_dx[0] = 0;
   plan.p.bias = bias; plan.p.relu = 1; plan.p.accumulate = 0;
   plan.p.n_split = n1; plan.p.out2 = reinterpret_cast<__half*>(out2.base); plan.p.out2_pitch = out2.pitch; plan.p.out2_coff = out2.coff;
+  if (tc) {        // EXACT_TC: out1 / out2 are the operand-plane views of the two destinations, tc->out32 / out32_2 their fp32 buffers
+    if (!tc->out32_2) { set_thread_error("fused fwd: the split-operand bind needs both fp32 destinations"); return 1; }
+    plan.p.out32_2 = tc->out32_2; plan.p.out_hi2 = reinterpret_cast<__half*>(out2.base); plan.p.out_lo_off2 = out2.lo_off;
+  }
   return try_halo(ctx, plan, in, F);
 }
 
 int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, View dz2, View dx, int F, int cin, int k1, int k2,
-                               const __half* w_n_k, int accumulate) {
+                               const __half* w_n_k, int accumulate, const UmmaTcOpts* tc) {
   const int k1p = (k1 + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   // bind with the first source as the A view and the full fused K; then attach the second source
   View a = k1 ? dz1 : dz2;
-  if (int rc = bind_common(ctx, plan, a, dx, F, k1 ? k1 : k2, cin, 1, 1, w_n_k)) return rc;
+  if (int rc = bind_common(ctx, plan, a, dx, F, k1 ? k1 : k2, cin, 1, 1, w_n_k, 1, tc)) return rc;
   UmmaConvParams& p = plan.p;
   p.tap_dy[0] = 0; p.tap_dx[0] = 0; p.bias = nullptr; p.relu = 0; p.accumulate = accumulate;
   if (k1) {
@@ -609,8 +614,13 @@ int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, V
     cuuint32_t bb[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)p.block_n, 1};
     if (int rc = encode(ctx, &plan.tmap_b, 3, const_cast<__half*>(w_n_k), bd, bs, bb)) { plan.enabled = false; return rc; }
     plan.b_ptr = w_n_k;
+    plan.tmap_b_lo = plan.tmap_b;
+    if (plan.b_lo_off)
+      if (int rc = encode(ctx, &plan.tmap_b_lo, 3, reinterpret_cast<__half*>(reinterpret_cast<char*>(const_cast<__half*>(w_n_k)) + plan.b_lo_off), bd, bs, bb)) {
+        plan.enabled = false; return rc; }
     for (int i = 0; i < 3; ++i) plan.b_dims[i] = bd[i];
     for (int i = 0; i < 2; ++i) plan.b_strides[i] = bs[i];
+    if (tc && !dz2.lo_off) { set_thread_error("fused dgrad: the split-operand bind needs the second source's operand planes"); plan.enabled = false; return 1; }
   }
   return try_halo(ctx, plan, a, F, k1 ? &dz2 : nullptr);
 }

@@ -65,6 +65,7 @@ struct UmmaConvParams {
   float alpha;
   const float* alpha_dev;         // optional device scalar multiplied into alpha (1 / the power-of-two scale of the weight planes)
   float* out32; __half* out_hi; long long out_lo_off;
+  float* out32_2; __half* out_hi2; long long out_lo_off2;   // fused sibling forward: columns >= n_split go here (pitch / offset: out2_pitch / out2_coff)
   // out_f32 data gradient that is the LAST writer of its output value v: dz = (alpha * acc + old) * (y > 0) with y = the fp32
   // activation of v; the planes written through out_hi then hold dz * plane_scale (the loss scale) for v's producers'
   // weight / data gradients, and *flag is raised when that leaves the fp16 range
@@ -92,7 +93,7 @@ struct UmmaConvPlan {
 // SSNB_EXACT_TC binding options: split weights (LO plane `w_lo_off` bytes after the HI plane), fp32 output view `out32`
 // (the bind call's own out/dx view then names the fp16 HI plane of the result, lo_off its LO plane; base == nullptr: no
 // planes are written), accumulator scale alpha
-struct UmmaTcOpts { long long w_lo_off = 0; float* out32 = nullptr; float alpha = 1.0f; const float* alpha_dev = nullptr; };
+struct UmmaTcOpts { long long w_lo_off = 0; float* out32 = nullptr; float alpha = 1.0f; const float* alpha_dev = nullptr; float* out32_2 = nullptr; };
 void umma_context_init(UmmaContext& ctx, bool fp16);
 void umma_context_destroy(UmmaContext& ctx);
 // forward convolution plan (stride 1): in/out views, weights wd = [tap][cout][cin] fp16
@@ -106,10 +107,10 @@ int umma_conv_bind_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz, View dx,
                          const __half* w_tap_k_n, int accumulate, const UmmaTcOpts* tc = nullptr);
 // fused forward of sibling 1x1 convs: one input view, weights [n1+n2][cin] (rows stacked), columns [0,n1) -> out1, rest -> out2
 int umma_conv_bind_fused_fwd(UmmaContext& ctx, UmmaConvPlan& plan, View in, View out1, View out2, int F, int cin, int n1, int n2,
-                             const __half* w_n_k, const float* bias);
+                             const __half* w_n_k, const float* bias, const UmmaTcOpts* tc = nullptr);
 // fused data gradient of sibling 1x1 convs: dx (+)= [dz1 | dz2] * W, weights [cin][pad64(k1) + k2]; dz1 may be empty (k1 = 0)
 int umma_conv_bind_fused_dgrad(UmmaContext& ctx, UmmaConvPlan& plan, View dz1, View dz2, View dx, int F, int cin, int k1, int k2,
-                               const __half* w_n_k, int accumulate);
+                               const __half* w_n_k, int accumulate, const UmmaTcOpts* tc = nullptr);
 int umma_conv_launch(UmmaContext& ctx, const UmmaConvPlan& plan, cudaStream_t s, bool mask = false);
 // second-generation kernel (umma_conv_v2.cu); `p` = plan.p with the per-launch fields (mask) already applied
 bool umma_conv_v2_supported(int ntaps);

@@ -338,6 +338,9 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ---- SSNB_EXACT_TC: fp32 epilogue (no software pipelining of the old-gradient reads yet) ----
         float* orow32 = p.out32 + opix * p.out_pitch + p.out_coff;
         __half* hrow = p.out_hi ? p.out_hi + opix * p.out_pitch + p.out_coff : nullptr;
+        // fused sibling forward: columns >= n_split belong to the second destination (its own pitch / channel offset)
+        float* orow32_2 = p.out32_2 + opix * p.out2_pitch + p.out2_coff - p.n_split;
+        __half* hrow2 = p.out_hi2 ? p.out_hi2 + opix * p.out2_pitch + p.out2_coff - p.n_split : nullptr;
         const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f);
         const float* mrow32 = p.mask32 ? p.mask32 + opix * p.mask32_pitch + p.mask32_coff : nullptr;
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -364,8 +367,16 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]);
             }
           }
-          if (valid && cola < p.Cout) store_chunk32(p, alpha, ra, bias_s + cola, orow32 + cola, hrow ? hrow + cola : nullptr, mrow32 ? mrow32 + cola : nullptr);
-          if (two && valid && colb < p.Cout) store_chunk32(p, alpha, rb, bias_s + colb, orow32 + colb, hrow ? hrow + colb : nullptr, mrow32 ? mrow32 + colb : nullptr);
+          if (valid && cola < p.Cout) {
+            const bool d1 = cola < p.n_split;
+            store_chunk32(p, alpha, ra, bias_s + cola, (d1 ? orow32 : orow32_2) + cola, d1 ? (hrow ? hrow + cola : nullptr) : (hrow2 ? hrow2 + cola : nullptr),
+                          mrow32 ? mrow32 + cola : nullptr, d1 ? p.out_lo_off : p.out_lo_off2);
+          }
+          if (two && valid && colb < p.Cout) {
+            const bool d1 = colb < p.n_split;
+            store_chunk32(p, alpha, rb, bias_s + colb, (d1 ? orow32 : orow32_2) + colb, d1 ? (hrow ? hrow + colb : nullptr) : (hrow2 ? hrow2 + colb : nullptr),
+                          mrow32 ? mrow32 + colb : nullptr, d1 ? p.out_lo_off : p.out_lo_off2);
+          }
         }
       } else if (TMAE) {
         // ---- TMA-fed: the operands of 64-column chunk i of this tile are in ring stage `es` (old gradient at +0, activation
@@ -557,7 +568,7 @@ int umma_conv_v2_launch(UmmaContext& ctx, const UmmaConvPlan& plan, const UmmaCo
   // shared-memory ring (p.epi_stages > 0) take the TMA-fed epilogue
   const bool reads = !p.bias && !p.relu && (p.accumulate || p.mask_y);
   const int epi = p.out_f32 ? 3 : ((reads && p.epi_stages > 0 && plan.epi_maps_ready && (!p.mask_y || plan.epi_mask_ready)) ? 2 : 0);
-  if (p.out_f32 && (p.mask_y || p.n_split < p.Cout)) { set_thread_error("umma conv v2: the fp32 epilogue has no mask / second destination"); return 3; }
+  if (p.out_f32 && p.mask_y) { set_thread_error("umma conv v2: the fp32 epilogue takes its mask through mask32"); return 3; }
   int rc;
   if (epi == 3) rc = p.pair ? launch_taps<true, 3>(plan, p, ctx.num_sms, s) : launch_taps<false, 3>(plan, p, ctx.num_sms, s);
   else if (p.pair) rc = epi == 2 ? launch_taps<true, 2>(plan, p, ctx.num_sms, s) : launch_taps<true, 0>(plan, p, ctx.num_sms, s);

@@ -32,7 +32,7 @@ __device__ __forceinline__ void stg256(void* p, const U8& a) {
 // SSNB_EXACT_TC epilogue: one 16-column chunk of an accumulator row in fp32 -- alpha * acc (+ bias, ReLU | + old) ->
 // 64 bytes of fp32, plus the value's fp16 hi / lo operand planes (2 x 32 bytes) for the convolutions that consume it
 __device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, float alpha, const uint32_t* r, const float* bias, float* dst, __half* hdst,
-                                              const float* ymask) {
+                                              const float* ymask, long long lo_off) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * alpha;
@@ -82,7 +82,7 @@ __device__ __forceinline__ void store_chunk32(const UmmaConvParams& p, float alp
       ql.v[j] = *reinterpret_cast<const uint32_t*>(&l);
     }
     stg256(hdst, qh);
-    stg256(reinterpret_cast<char*>(hdst) + p.out_lo_off, ql);
+    stg256(reinterpret_cast<char*>(hdst) + lo_off, ql);
   }
 }
 
