@@ -592,6 +592,7 @@ def roofline_from_rows(rows, n_steps, precision, peaks, peak_src, frames, modali
         tr = None
     return {"bound": "tensor", "kernel": "%s (forward + data gradient, all %d launches of a step)" % (conv_names[0], dom["launches_per_step"]),
             "achieved": dom["achieved"], "peak": sustained, "unit": "TFLOP/s", "frac": dom["frac"], "traffic": tr,
+            "tensor_pipe_frac": dom["tensor_pipe_tflops"] / sustained, "mma_per_algorithmic_product": mma_per_product,
             "traffic_unit": "bytes per launch of the largest forward launch (conv2_3x3), ncu --set full dram read+write, profiles/",
             "peak_source": peak_src + " bf16 sustained (kernels timed inside a long step); frac_of_burst uses the burst figure",
             "note": "algorithmic fp32-conv FLOPs (2*F*H*W*Cout*Cin*k*k) / summed per-launch CUDA-event time of two eager steps; "
