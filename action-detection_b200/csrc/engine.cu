@@ -673,7 +673,7 @@ int engine_tail_view(ssnb_handle h, View* v, int* F, int* fp16) {
 // ---- C ABI -----------------------------------------------------------------------------------------
 extern "C" {
 
-const char* ssnb_version(void) { return "libssn_b200 0.1 (sm_100a)"; }
+const char* ssnb_version(void) { return "libssn_b200 0.2 (sm_100a)"; }
 
 const char* ssnb_last_error(ssnb_handle h) { return h ? h->error.c_str() : ssnb::thread_error().c_str(); }
 

@@ -158,7 +158,7 @@ __global__ void stpp_bwd_v4_kernel(const float* __restrict__ dcourse, const floa
     for (int q = 0; q < PMAX; ++q)
       if (q < pt.n && t >= pt.lo[q] && t < pt.hi[q]) { a.x += g[q].x; a.y += g[q].y; a.z += g[q].z; a.w += g[q].w; }
     if (dcourse && t >= pt.clo && t < pt.chi) { a.x += gc.x; a.y += gc.y; a.z += gc.z; a.w += gc.w; }
-    __stcs(reinterpret_cast<float4*>(dft + (p * S + t) * D + d), a);      // streaming store: written once, read by a later kernel
+    *reinterpret_cast<float4*>(dft + (p * S + t) * D + d) = a;
   }
 }
 

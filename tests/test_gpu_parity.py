@@ -940,3 +940,41 @@ def test_bn_mode_partial(backbone_rgb, precision):
     with torch.no_grad():
         model.base_model(x.to(dev))
     assert torch.equal(rm, bn1.running_mean)
+
+
+@pytest.mark.parametrize("precision", ["exact_tc", "fast"])
+def test_bucketed_backward_matches_single_call(backbone_rgb, precision):
+    """ssnb_backbone_bwd_range (the backward in buckets, for overlapping the gradient all-reduce: ssn_b200.dp.GradSync) leaves
+    exactly the gradients of the single-call backward, and the buckets tile the flat gradient buffer."""
+    dev = _cuda()
+    import ssn_models
+    from ssn_b200.optim import FusedSGD
+    from ssn_b200.dp import GradSync
+    K = 4
+
+    def make():
+        m = ssn_models.SSN(K, 2, 5, 2, "RGB", base_model="BNInception", dropout=0, stpp_cfg=(1, (1, 2), 1))
+        sd = m.state_dict()
+        for k, v in backbone_rgb.items():
+            sd["base_model." + k].copy_(v)
+        m = m.to(dev).train()
+        m.set_precision(_prec(precision), 1024.0)
+        return m
+    torch.manual_seed(7)
+    m1 = make()
+    torch.manual_seed(7)
+    m2 = make()
+    batch = [t.to(dev) for t in synth.synth_batch(2, K, 3, seed=5)]
+    l1 = m1.fused_step(*batch)
+    order = [p for p in m2.parameters() if p.requires_grad]
+    opt = FusedSGD(m2.get_optim_policies(), lr=0.0, momentum=0.0, weight_decay=0.0, order=order)
+    sync = GradSync(opt.flat_grad, order, m2)
+    l2 = m2.fused_step(*batch, grad_sync=sync)
+    sync.finish()
+    assert torch.equal(l1, l2)
+    spans = sorted(sync.launched)
+    assert spans[0][0] == 0 and spans[-1][1] == opt.flat_grad.numel() and all(a[1] == b[0] for a, b in zip(spans, spans[1:])), spans
+    assert len(spans) == 4                                   # heads + three backbone buckets
+    for (n1, p1), (_n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p1.grad is not None:
+            assert torch.equal(p1.grad, p2.grad), n1         # same kernels, same order inside every bucket: bit-identical
