@@ -153,8 +153,6 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // folded-BN bias of every output column of this launch, zero past Cout: the epilogue reads it with broadcast LDS
   // (a global __ldg there sat on the critical path right after the TMEM load: half of the epilogue's stall samples)
   float* bias_s = reinterpret_cast<float*>(smem + UMMA_V2_PIPE_BYTES + BAR_BYTES);
-  if (p.bias)
-    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += (TMAE ? NUM_THREADS + 32 : NUM_THREADS)) bias_s[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a2)) : "memory");
@@ -182,9 +180,16 @@ umma_conv_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  // Programmatic dependent launch: everything above (barrier init, tensor-map prefetch, TMEM allocation) touches nothing the
+  // previous kernel of the stream produced, so it overlaps that kernel's tail; from here on its results are needed.
+  // (Both instructions are no-ops when the launch does not carry the programmatic-serialization attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.bias)
+    for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += (TMAE ? NUM_THREADS + 32 : NUM_THREADS)) bias_s[i] = i < p.Cout ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -533,19 +538,24 @@ int launch_one(const UmmaConvPlan& plan, const UmmaConvParams& p, int num_sms, c
   }
   const int total = p.n_tiles * p.tiles_w * p.tiles_h * p.tiles_q;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   cfg.blockDim = dim3(EPI == 2 ? NUM_THREADS + 32 : NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = s;
   if (PAIR) {
     const int pairs = std::min(total, num_sms / 2);
     cfg.gridDim = dim3(2 * pairs);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   } else {
     cfg.gridDim = dim3(std::min(total, num_sms));
   }
+  // programmatic dependent launch (SSNB_PDL=0 turns it off): this kernel's prologue may overlap the previous kernel's tail
+  static const bool pdl = [] { const char* e = getenv("SSNB_PDL"); return !(e && e[0] == '0'); }();
+  if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  cfg.attrs = na ? attr : nullptr; cfg.numAttrs = na;
   if (cudaLaunchKernelEx(&cfg, kern, plan.tmap_a, plan.tmap_a2, plan.tmap_b, plan.tmap_old, plan.tmap_y, plan.tmap_a_lo, plan.tmap_a2_lo,
                          plan.tmap_b_lo, p) != cudaSuccess) {
     set_thread_error(std::string("umma_conv_v2_kernel launch: ") + cudaGetErrorString(cudaGetLastError())); return 2; }

@@ -565,9 +565,17 @@ def test_fast_fused_vs_unfused_and_oracle(backbone_rgb):
     assert e_feat < 5e-3 and e_ws[len(e_ws) // 2] < 0.3 and e_ws[-1] < 0.5, (e_feat, e_ws[len(e_ws) // 2], e_ws[-1])    # measured 0.15 / 0.19
     # End-to-end gradients of FAST mode on this synthetic random-weight net are dominated by ReLU / max-pool
     # decision flips (forward differs by ~1e-2 => many flips; cf. the fp32 noise floor of ~1e-2 measured in
-    # test_ssn_train_exact_vs_oracle for a 1e-5 forward difference).  Reported, bounded loosely; the
-    # per-kernel bound is test_backbone_per_layer[fast].
-    assert o_feat < 5e-2 and o_w[0][0] < 1.0
+    # test_ssn_train_exact_vs_oracle for a 1e-5 forward difference).  The criterion is the direction and the size of
+    # the whole gradient (aggregate over the 69 weight tensors) -- the same as test_fused_step_bench_shape[fast];
+    # the per-kernel bound is test_backbone_per_layer[fast].
+    num = den = dot = na = 0.0
+    for a, n in zip(dw_fast, names):
+        r = bb[n + ".weight"].grad.double()
+        a = a.double().cpu()
+        num += float((a - r).pow(2).sum()); den += float(r.pow(2).sum()); dot += float((a * r).sum()); na += float(a.pow(2).sum())
+    agg, cos = (num / den) ** 0.5, dot / (na * den) ** 0.5
+    print("fast whole-backbone dW vs fp32 oracle: aggregate rel-L2 %.3f, cosine %.4f" % (agg, cos))
+    assert o_feat < 5e-2 and agg < 0.6 and cos > 0.9, (o_feat, agg, cos)
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
