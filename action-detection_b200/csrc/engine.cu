@@ -85,6 +85,7 @@ struct Op {
   size_t argmax_off = 0;
   int grad_accumulate = 0;  // backward: dIn += (another consumer wrote first)
   int wsplits = 1, wrows = 0;
+  int tsplits = 1;                // upper bound of the split count the tcgen05 weight-gradient planner may pick (sizes `partial`)
   size_t partial_off = 0, bias_partial_off = 0;   // this layer's split-K partials (own region: finalised in one batch)
   UmmaConvPlan umma;        // tcgen05 forward plan (FAST mode, stride-1 layers)
   UmmaConvPlan umma_dgrad;  // tcgen05 data-gradient plan
@@ -318,6 +319,15 @@ static void plan(ssnb_engine* e) {
         rows = (rows + 15) / 16 * 16;
         splits = (M + rows - 1) / rows;
         o.wsplits = (int)splits; o.wrows = (int)rows;
+        // tcgen05 path: one CTA per SM is resident, so the planner wants num_sms / (M tiles x N tiles x tap groups) pixel
+        // splits; the SIMT heuristic above used to cap it and left 57-75 % of the SMs busy on most 3x3 layers
+        {
+          const int chunks = (c.cin + 63) / 64, n_tiles = (chunks + 3) / 4, block_n = ((chunks + n_tiles - 1) / n_tiles) * 64;
+          const int tpc = std::max(1, 4 / (block_n / 64));
+          const int ctas = ((c.cout + 127) / 128) * n_tiles * ((taps + tpc - 1) / tpc);
+          o.tsplits = std::max(o.wsplits, std::min(128, std::max(1, 148 / ctas)));
+        }
+        if (e->fp16 || e->tc) splits = std::max<long long>(splits, o.tsplits);
         const size_t need = (size_t)splits * taps * c.cout * c.cin * 4;
         if (need > pmax) pmax = need;
       }
@@ -411,10 +421,11 @@ static void plan(ssnb_engine* e) {
     for (Op& o : e->ops)
       if (o.kind == OP_CONV) {
         const ConvSpec& c = e->convs[o.conv];
-        size_t need = (size_t)o.wsplits * c.k * c.k * c.cout * c.cin * 4;
+        const int nsplit = (e->fp16 || e->tc) ? std::max(o.wsplits, o.tsplits) : o.wsplits;
+        size_t need = (size_t)nsplit * c.k * c.k * c.cout * c.cin * 4;
         if (o.conv == 0 && (e->fp16 || e->tc)) need = std::max(need, (size_t)128 * 16 * 64 * e->Cs * 4);
         o.partial_off = off; off = align_up(off + need, 1024);
-        o.bias_partial_off = off; off = align_up(off + (size_t)std::max(o.wsplits, 128) * c.cout * 4, 256);
+        o.bias_partial_off = off; off = align_up(off + (size_t)std::max(nsplit, 128) * c.cout * 4, 256);
       }
   e->bpartial_off = off; off = align_up(off + (size_t)1024 * 512 * 4, 1024);   // column-sum partials: <= 1024 CTAs x 512 channels
   e->ws_bytes = off;
@@ -779,7 +790,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
       if (!o.umma_dgrad.p.v2) o.umma_dgrad.enabled = false;
       if (use_wgrad_tc) {
         rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->planes(o.out_val, true), h->planes(o.in_val, false), h->F, c.cin, c.cout, c.k, c.pad,
-                             (float*)(h->ws + o.partial_off), o.wsplits, c.stride);
+                             (float*)(h->ws + o.partial_off), o.tsplits, c.stride);
         if (rc) return h->fail(rc, "tc wgrad_bind(" + c.id + "): " + ssnb::thread_error());
       }
     }
@@ -910,7 +921,7 @@ int ssnb_set_workspace(ssnb_handle h, void* dev_ptr, size_t bytes) {
     if (use_wgrad) {
       // stride-2 layers: dz at its own (output) resolution, the x boxes step over the input with element stride 2
       rc = umma_wgrad_bind(h->umma_ctx, o.umma_wgrad, h->view(o.out_val, true), in, h->F, c.cin, c.cout, c.k, c.pad,
-                           (float*)(h->ws + o.partial_off), o.wsplits, c.stride);
+                           (float*)(h->ws + o.partial_off), o.tsplits, c.stride);
       if (rc) return h->fail(rc, "umma_wgrad_bind(" + c.id + "): " + ssnb::thread_error());
     }
   }
