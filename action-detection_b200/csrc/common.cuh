@@ -97,6 +97,7 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
 
 // the same for many layers per launch (block0 = first CTA of the entry; 256 threads per CTA)
 constexpr int PACK_MAX = 32;
+constexpr int PACK_PER_THREAD = 4;     // elements per thread of pack_all_kernel (block0 counts CTAs of 256 threads x 4 elements)
 struct PackEntry {
   const float *w, *b, *gamma, *beta, *mean, *var;
   void *wf, *wd; float *bias, *scale, *absmax;

@@ -68,8 +68,10 @@ __global__ void wgrad_finalize_s2d_kernel(const float* __restrict__ partial, int
 
 // fused input conversion: NCHW fp32 frames -> packed space-to-depth fp16; one thread per (pixel, ds block):
 // float2 reads coalesced along x, the Cs-channel block is assembled in registers and stored as 16-byte vectors
-template <int CS>
-__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin, int H, int W, __half* __restrict__ dst) {
+// CIN > 0: compile-time channel count (RGB 3 / Flow 10): the channel loop unrolls and the staging array stays in registers
+template <int CS, int CIN>
+__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin_rt, int H, int W, __half* __restrict__ dst) {
+  const int Cin = CIN ? CIN : Cin_rt;
   const int H2 = H / 2, W2 = W / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * H2 * W2 * 4) return;
@@ -84,6 +86,7 @@ __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, int F, int Cin
   for (int c = 0; c < CS; ++c) v[c] = __float2half_rn(0.f);
   const int xs = x2 + ds - 2;
   if (xs >= 0 && xs < W2) {
+#pragma unroll
     for (int c = 0; c < Cin; ++c) {
       const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * xs;
       const float2 r0 = __ldg(reinterpret_cast<const float2*>(pl));
@@ -127,8 +130,11 @@ int launch_nhwc_to_s2d(View src, int F, __half* dst, int Cs, cudaStream_t s) {
 }
 int launch_nchw_to_s2d(const float* src, int F, int Cin, int H, int W, __half* dst, int Cs, cudaStream_t s) {
   const long long n = (long long)F * (H / 2) * (W / 2) * 4;
-  if (Cs == 16) nchw_to_s2d_kernel<16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst);
-  else if (Cs == 40) nchw_to_s2d_kernel<40><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, F, Cin, H, W, dst);
+  const unsigned g = (unsigned)((n + 255) / 256);
+  if (Cs == 16 && Cin == 3) nchw_to_s2d_kernel<16, 3><<<g, 256, 0, s>>>(src, F, Cin, H, W, dst);
+  else if (Cs == 40 && Cin == 10) nchw_to_s2d_kernel<40, 10><<<g, 256, 0, s>>>(src, F, Cin, H, W, dst);
+  else if (Cs == 16) nchw_to_s2d_kernel<16, 0><<<g, 256, 0, s>>>(src, F, Cin, H, W, dst);
+  else if (Cs == 40) nchw_to_s2d_kernel<40, 0><<<g, 256, 0, s>>>(src, F, Cin, H, W, dst);
   else { set_thread_error("nchw_to_s2d: unsupported channel count (RGB 3 or Flow 10)"); return 1; }
   SSNB_LAUNCH_CHECK("nchw_to_s2d_kernel");
   return 0;

@@ -207,29 +207,42 @@ __global__ void pack_all_kernel(const __grid_constant__ PackTable t) {
   const PackEntry& q = t.e[ei];
   const int taps = q.k * q.k;
   const long long total = (long long)q.cout * q.cin * taps;
-  const long long i = (long long)((int)blockIdx.x - q.block0) * blockDim.x + threadIdx.x;
-  if (i < q.cout) {
-    const float s = q.nofold ? 1.0f : q.gamma[i] / sqrtf(q.var[i] + 1e-5f);
-    q.scale[i] = s;
-    q.bias[i] = q.nofold ? q.b[i] : (q.b[i] - q.mean[i]) * s + q.beta[i];
-    if (q.bias_b) q.bias_b[i] = q.bias[i];
-  }
+  const long long base = (long long)((int)blockIdx.x - q.block0) * (PACK_PER_THREAD * TPB) + threadIdx.x;
   float av = 0.f;
-  if (i < total) {
-    const int tap = (int)(i % taps);
-    const int ci = (int)((i / taps) % q.cin);
-    const int co = (int)(i / ((long long)taps * q.cin));
-    const float s = q.nofold ? 1.0f : q.gamma[co] / sqrtf(q.var[co] + 1e-5f);
-    const float fv = q.w[i] * s;
-    const T v = from_f<T>(fv);
-    reinterpret_cast<T*>(q.wf)[((long long)tap * q.cin + ci) * q.cout + co] = v;
-    reinterpret_cast<T*>(q.wd)[((long long)tap * q.cout + co) * q.cin + ci] = v;
-    av = fabsf(fv);
+#pragma unroll
+  for (int j = 0; j < PACK_PER_THREAD; ++j) {
+    const long long i = base + j * TPB;
+    if (i < q.cout) {
+      const float s = q.nofold ? 1.0f : q.gamma[i] / sqrtf(q.var[i] + 1e-5f);
+      q.scale[i] = s;
+      const float bf = q.nofold ? q.b[i] : (q.b[i] - q.mean[i]) * s + q.beta[i];
+      q.bias[i] = bf;
+      if (q.bias_b) q.bias_b[i] = bf;
+    }
+    if (i < total) {
+      const int tap = (int)(i % taps);
+      const int ci = (int)((i / taps) % q.cin);
+      const int co = (int)(i / ((long long)taps * q.cin));
+      const float s = q.nofold ? 1.0f : q.gamma[co] / sqrtf(q.var[co] + 1e-5f);
+      const float fv = q.w[i] * s;
+      const T v = from_f<T>(fv);
+      reinterpret_cast<T*>(q.wf)[((long long)tap * q.cin + ci) * q.cout + co] = v;
+      reinterpret_cast<T*>(q.wd)[((long long)tap * q.cout + co) * q.cin + ci] = v;
+      av = fmaxf(av, fabsf(fv));
+    }
   }
   if (q.absmax) {
+    // one atomic per CTA: per-warp atomics on the 69 per-layer addresses serialised in L2 and dominated this kernel
+    __shared__ float wmax[TPB / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) av = fmaxf(av, __shfl_xor_sync(0xffffffffu, av, o));
-    if (threadIdx.x % 32 == 0 && av > 0.f) atomicMax(reinterpret_cast<int*>(q.absmax), __float_as_int(av));
+    if (threadIdx.x % 32 == 0) wmax[threadIdx.x / 32] = av;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < TPB / 32; ++w) av = fmaxf(av, wmax[w]);
+      if (av > 0.f) atomicMax(reinterpret_cast<int*>(q.absmax), __float_as_int(av));
+    }
   }
 }
 

@@ -109,9 +109,11 @@ __global__ void planes_to_nchw_kernel(const __half* __restrict__ hi, long long l
 
 // NCHW fp32 frames -> conv1's packed space-to-depth operand planes (layout of s2d_glue.cu: channel = ds*Cs + (a*2+b)*Cin + c
 // holds x[f, 2i+a, 2(j+ds-2)+b, c]); one thread per (pixel, ds block)
-template <int CS>
-__global__ void nchw_to_s2d_split_kernel(const float* __restrict__ src, int F, int Cin, int H, int W, __half* __restrict__ dst,
+// CIN > 0: compile-time channel count (RGB 3 / Flow 10): the channel loop unrolls and the staging arrays stay in registers
+template <int CS, int CIN>
+__global__ void nchw_to_s2d_split_kernel(const float* __restrict__ src, int F, int Cin_rt, int H, int W, __half* __restrict__ dst,
                                          long long lo_off) {
+  const int Cin = CIN ? CIN : Cin_rt;
   const int H2 = H / 2, W2 = W / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * H2 * W2 * 4) return;
@@ -127,6 +129,7 @@ __global__ void nchw_to_s2d_split_kernel(const float* __restrict__ src, int F, i
   for (int c = 0; c < CS; ++c) { vh[c] = __float2half_rn(0.f); vl[c] = __float2half_rn(0.f); }
   const int xs = x2 + ds - 2;
   if (xs >= 0 && xs < W2) {
+#pragma unroll
     for (int c = 0; c < Cin; ++c) {
       const float* pl = src + ((f * Cin + c) * H + 2 * y2) * (long long)W + 2 * xs;
       const float2 r0 = __ldg(reinterpret_cast<const float2*>(pl));
@@ -210,8 +213,11 @@ int launch_planes_to_nchw(View planes, int F, float scale, float* dst, cudaStrea
 }
 int launch_nchw_to_s2d_split(const float* src, int F, int Cin, int H, int W, __half* dst_hi, long long lo_off, int Cs, cudaStream_t s) {
   const long long n = (long long)F * (H / 2) * (W / 2) * 4;
-  if (Cs == 16) nchw_to_s2d_split_kernel<16><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, s>>>(src, F, Cin, H, W, dst_hi, lo_off);
-  else if (Cs == 40) nchw_to_s2d_split_kernel<40><<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, s>>>(src, F, Cin, H, W, dst_hi, lo_off);
+  const unsigned g = (unsigned)((n + TPB - 1) / TPB);
+  if (Cs == 16 && Cin == 3) nchw_to_s2d_split_kernel<16, 3><<<g, TPB, 0, s>>>(src, F, Cin, H, W, dst_hi, lo_off);
+  else if (Cs == 40 && Cin == 10) nchw_to_s2d_split_kernel<40, 10><<<g, TPB, 0, s>>>(src, F, Cin, H, W, dst_hi, lo_off);
+  else if (Cs == 16) nchw_to_s2d_split_kernel<16, 0><<<g, TPB, 0, s>>>(src, F, Cin, H, W, dst_hi, lo_off);
+  else if (Cs == 40) nchw_to_s2d_split_kernel<40, 0><<<g, TPB, 0, s>>>(src, F, Cin, H, W, dst_hi, lo_off);
   else { set_thread_error("nchw_to_s2d_split: unsupported channel count (RGB 3 or Flow 10)"); return 1; }
   SSNB_LAUNCH_CHECK("nchw_to_s2d_split_kernel");
   return 0;
