@@ -97,7 +97,13 @@ int launch_pack_conv(const float* w, const float* b, const float* gamma, const f
 
 // the same for many layers per launch (block0 = first CTA of the entry; 256 threads per CTA)
 constexpr int PACK_MAX = 32;
-constexpr int PACK_PER_THREAD = 4;     // elements per thread of pack_all_kernel (block0 counts CTAs of 256 threads x 4 elements)
+constexpr int PACK_PER_THREAD = 4;     // element-wise path of pack_all_kernel (more than PACK_TILE_TAPS taps: conv1): 256 threads x 4 elements per CTA
+constexpr int PACK_TILE = 32, PACK_TILE_TAPS = 9;   // tiled path: one CTA per 32 output x 32 input channels x taps
+inline int pack_ctas(int cout, int cin, int k) {
+  if (k * k <= PACK_TILE_TAPS) return ((cout + PACK_TILE - 1) / PACK_TILE) * ((cin + PACK_TILE - 1) / PACK_TILE);
+  const long long n = (long long)cout * cin * k * k, per = 256LL * PACK_PER_THREAD;
+  return (int)(((n > cout ? n : cout) + per - 1) / per);
+}
 struct PackEntry {
   const float *w, *b, *gamma, *beta, *mean, *var;
   void *wf, *wd; float *bias, *scale, *absmax;

@@ -1032,7 +1032,7 @@ int ssnb_pack_weights(ssnb_handle h, const float* const* w, const float* const* 
       q.cout = c.cout; q.cin = c.cin; q.k = c.k; q.block0 = pblocks.back();
       q.nofold = (h->bn1_train && i == 0) ? 1 : 0; q.pad_[0] = q.pad_[1] = q.pad_[2] = 0;
       q.bias_b = (h->tc && fb) ? (float*)(h->ws + fb->bias) + mb.row : nullptr;
-      pblocks.back() += (int)((std::max<long long>(n, c.cout) + 256 * PACK_PER_THREAD - 1) / (256 * PACK_PER_THREAD));
+      pblocks.back() += pack_ctas(c.cout, c.cin, c.k);
       if (h->tc) {
         SplitEntry& e = stt.back().e[stt.back().n++];
         e.wf = (const float*)(h->ws + p.wf); e.wd = (const float*)(h->ws + p.wd);
