@@ -26,9 +26,12 @@ __device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpr
 // max pooling on packed halves: compares and selects run as half2 mask operations (no fp32 round trip; the first
 // version spent ~400 instructions per thread on conversions and was issue-bound at 2.6 TB/s).  Semantics unchanged:
 // first maximum wins, NaN propagates (ATen's rule).
+// K > 0: compile-time window (the network's max pools are all 3x3): the K*K loads are issued before the first compare
+template <int K>
 __global__ void maxpool_fwd_h8(const __half* __restrict__ src, int H, int W, int C, int spitch, int scoff,
-                               __half* __restrict__ dst, int OH, int OW, int dpitch, int dcoff, int F, int k, int stride,
+                               __half* __restrict__ dst, int OH, int OW, int dpitch, int dcoff, int F, int k_rt, int stride,
                                int pad, uint8_t* __restrict__ argmax) {
+  const int k = K ? K : k_rt;
   const int G = C / 8;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * OH * OW * G) return;
@@ -43,27 +46,43 @@ __global__ void maxpool_fwd_h8(const __half* __restrict__ src, int H, int W, int
   uint32_t bi[4] = {0u, 0u, 0u, 0u};       // 4 x (two 16-bit tap indices, same lanes as the half2 values)
   bool first = true;
   const __half* base = src + (f * H * W) * spitch + scoff + g * 8;
-  for (int r = 0; r < k; ++r) {
-    const int iy = oy * stride + r - pad;
-    if (iy < 0 || iy >= H) continue;
-    for (int s = 0; s < k; ++s) {
-      const int ix = ox * stride + s - pad;
-      if (ix < 0 || ix >= W) continue;
-      const uint4 q = ldg16(base + ((long long)iy * W + ix) * spitch);
-      const uint32_t v[4] = {q.x, q.y, q.z, q.w};
-      const uint32_t tag = (uint32_t)(r * k + s) * 0x00010001u;
+  // one tap: NaN-propagating maximum; the tap index moves where the maximum changed (v > best, or a NaN arrived), or when
+  // nothing was taken yet: 3 instructions per half2
+  auto take = [&](const uint4& q, uint32_t t) {
+    const uint32_t v[4] = {q.x, q.y, q.z, q.w};
+    const uint32_t tag = t * 0x00010001u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __half2 hv = *reinterpret_cast<const __half2*>(&v[j]);
-        const __half2 hb = *reinterpret_cast<const __half2*>(&best[j]);
-        // NaN-propagating maximum; the tap index moves where the maximum changed (v > best, or a NaN arrived), or when
-        // nothing was taken yet: 3 instructions per half2
-        const __half2 hn = __hmax2_nan(hb, hv);
-        const uint32_t m = first ? 0xFFFFFFFFu : __hneu2_mask(hn, hb);
-        best[j] = first ? v[j] : *reinterpret_cast<const uint32_t*>(&hn);
-        bi[j] = (tag & m) | (bi[j] & ~m);
+    for (int j = 0; j < 4; ++j) {
+      const __half2 hv = *reinterpret_cast<const __half2*>(&v[j]);
+      const __half2 hb = *reinterpret_cast<const __half2*>(&best[j]);
+      const __half2 hn = __hmax2_nan(hb, hv);
+      const uint32_t m = first ? 0xFFFFFFFFu : __hneu2_mask(hn, hb);
+      best[j] = first ? v[j] : *reinterpret_cast<const uint32_t*>(&hn);
+      bi[j] = (tag & m) | (bi[j] & ~m);
+    }
+    first = false;
+  };
+  if (K) {
+    constexpr int K1 = K ? K : 1, KK = K1 * K1;
+    uint4 q[KK]; bool ok[KK];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      const int iy = oy * stride + t / K1 - pad, ix = ox * stride + t % K1 - pad;
+      ok[t] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      q[t] = ok[t] ? ldg16(base + ((long long)iy * W + ix) * spitch) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int t = 0; t < KK; ++t)
+      if (ok[t]) take(q[t], (uint32_t)t);
+  } else {
+    for (int r = 0; r < k; ++r) {
+      const int iy = oy * stride + r - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int ix = ox * stride + s - pad;
+        if (ix < 0 || ix >= W) continue;
+        take(ldg16(base + ((long long)iy * W + ix) * spitch), (uint32_t)(r * k + s));
       }
-      first = false;
     }
   }
   *reinterpret_cast<uint4*>(dst + p * dpitch + dcoff + g * 8) = make_uint4(best[0], best[1], best[2], best[3]);
@@ -465,7 +484,11 @@ static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) 
 
 int launch_maxpool_fwd_h8(View src, View dst, int F, int k, int stride, int pad, uint8_t* argmax, cudaStream_t s) {
   const long long n = (long long)F * dst.H * dst.W * (src.C / 8);
-  maxpool_fwd_h8<<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.H, dst.W, dst.pitch,
+  if (k == 3)
+    maxpool_fwd_h8<3><<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.H, dst.W, dst.pitch,
+                                             dst.coff, F, k, stride, pad, argmax);
+  else
+    maxpool_fwd_h8<0><<<nblk(n, 256), 256, 0, s>>>(HP(src), src.H, src.W, src.C, src.pitch, src.coff, HP(dst), dst.H, dst.W, dst.pitch,
                                              dst.coff, F, k, stride, pad, argmax);
   SSNB_LAUNCH_CHECK("maxpool_fwd_h8");
   return 0;

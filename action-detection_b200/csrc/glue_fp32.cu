@@ -28,9 +28,13 @@ __device__ __forceinline__ void store_planes4(__half* hi, long long lo_off, cons
 }
 
 // ---- max pooling ---------------------------------------------------------------------------------------------
+// K > 0: compile-time window size (every max pool of the network is 3x3): all K*K loads are issued before the first compare
+// (the generic loop waits for each load in turn); the compare order -- and with it the first-max-wins / NaN rule -- is the same
+template <int K>
 __global__ void maxpool_fwd_f4(const float* __restrict__ src, int H, int W, int C, int spitch, int scoff, float* __restrict__ dst, int OH,
-                               int OW, int dpitch, int dcoff, __half* __restrict__ hi, long long lo_off, int F, int k, int stride, int pad,
+                               int OW, int dpitch, int dcoff, __half* __restrict__ hi, long long lo_off, int F, int k_rt, int stride, int pad,
                                uint8_t* __restrict__ argmax) {
+  const int k = K ? K : k_rt;
   const int G = C / 4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)F * OH * OW * G) return;
@@ -44,6 +48,25 @@ __global__ void maxpool_fwd_f4(const float* __restrict__ src, int H, int W, int 
   uint32_t bi = 0u;                                   // four 8-bit tap indices
   bool first = true;
   const float* base = src + (f * H * W) * spitch + scoff + g * 4;
+  if (K) {
+    constexpr int KK = K ? K * K : 1;
+    float4 q[KK]; bool ok[KK];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      const int iy = oy * stride + t / (K ? K : 1) - pad, ix = ox * stride + t % (K ? K : 1) - pad;
+      ok[t] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      q[t] = ok[t] ? ldg4(base + ((long long)iy * W + ix) * spitch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      if (!ok[t]) continue;
+      const float v[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (first || v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; bi = (bi & ~(0xFFu << (8 * j))) | ((uint32_t)t << (8 * j)); }   // first max wins (ATen)
+      first = false;
+    }
+  } else {
   for (int r = 0; r < k; ++r) {
     const int iy = oy * stride + r - pad;
     if (iy < 0 || iy >= H) continue;
@@ -58,6 +81,7 @@ __global__ void maxpool_fwd_f4(const float* __restrict__ src, int H, int W, int 
         if (first || v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; bi = (bi & ~(0xFFu << (8 * j))) | (tag << (8 * j)); }   // first max wins (ATen)
       first = false;
     }
+  }
   }
   const float4 o = make_float4(best[0], best[1], best[2], best[3]);
   *reinterpret_cast<float4*>(dst + p * dpitch + dcoff + g * 4) = o;
@@ -388,8 +412,12 @@ int launch_maxpool_fwd_f4(View src, View dst, View dst_planes, int F, int k, int
   if (src.C % 4 || src.pitch % 4 || src.coff % 4 || dst.pitch % 4 || dst.coff % 4 || k * k > 255 || !planes_match(dst, dst_planes)) {
     set_thread_error("maxpool_fwd_f4: unsupported view"); return 1; }
   const long long n = (long long)F * dst.H * dst.W * (src.C / 4);
-  maxpool_fwd_f4<<<nblk(n, 256), 256, 0, s>>>(FP(src), src.H, src.W, src.C, src.pitch, src.coff, FP(dst), dst.H, dst.W, dst.pitch, dst.coff,
-                                             (__half*)dst_planes.base, dst_planes.lo_off, F, k, stride, pad, argmax);
+  if (k == 3)
+    maxpool_fwd_f4<3><<<nblk(n, 256), 256, 0, s>>>(FP(src), src.H, src.W, src.C, src.pitch, src.coff, FP(dst), dst.H, dst.W, dst.pitch, dst.coff,
+                                                  (__half*)dst_planes.base, dst_planes.lo_off, F, k, stride, pad, argmax);
+  else
+    maxpool_fwd_f4<0><<<nblk(n, 256), 256, 0, s>>>(FP(src), src.H, src.W, src.C, src.pitch, src.coff, FP(dst), dst.H, dst.W, dst.pitch, dst.coff,
+                                                  (__half*)dst_planes.base, dst_planes.lo_off, F, k, stride, pad, argmax);
   SSNB_LAUNCH_CHECK("maxpool_fwd_f4");
   return 0;
 }
