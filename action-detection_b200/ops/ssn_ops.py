@@ -27,12 +27,11 @@ class StructuredTemporalPyramidPooling(torch.nn.Module):
         super(StructuredTemporalPyramidPooling, self).__init__()
         self.sc = standalong_classifier
         self.feat_dim = feat_dim
-        starting_parts, starting_mult = parse_stage_config(configs[0])
-        course_parts, course_mult = parse_stage_config(configs[1])
-        ending_parts, ending_mult = parse_stage_config(configs[2])
-        self.feat_multiplier = starting_mult + course_mult + ending_mult
-        self.parts = (starting_parts, course_parts, ending_parts)
-        self.norm_num = (starting_mult, course_mult, ending_mult)
+        # (starting, course, ending) stage -> (pyramid part counts, number of pooled vectors), ops/ssn_ops.py:30-36
+        stages = [parse_stage_config(c) for c in configs[:3]]
+        self.parts = tuple(parts for parts, _ in stages)
+        self.norm_num = tuple(mult for _, mult in stages)
+        self.feat_multiplier = sum(self.norm_num)
 
     def part_table(self, seg_split):
         return stpp_part_table(self.parts, self.norm_num, seg_split)
@@ -146,19 +145,20 @@ class CompletenessLoss(torch.nn.Module):
         self.sigmoid = torch.nn.Sigmoid()
 
     def forward(self, pred, labels, sample_split, sample_group_size):
-        pred_dim = pred.size()[1]
-        pred = pred.view(-1, sample_group_size, pred_dim)
-        labels = labels.view(-1, sample_group_size)
-        pos_group_size = sample_split
-        neg_group_size = sample_group_size - sample_split
-        pos_prob = pred[:, :sample_split, :].contiguous().view(-1, pred_dim)
-        neg_prob = pred[:, sample_split:, :].contiguous().view(-1, pred_dim)
-        pos_ls = OHEMHingeLoss.apply(pos_prob, labels[:, :sample_split].contiguous().view(-1), 1, 1.0, pos_group_size)
-        neg_ls = OHEMHingeLoss.apply(neg_prob, labels[:, sample_split:].contiguous().view(-1), -1,
-                                     self.ohem_ratio, neg_group_size)
-        pos_cnt = pos_prob.size(0)
-        neg_cnt = int(neg_prob.size()[0] * self.ohem_ratio)
-        return pos_ls / float(pos_cnt + neg_cnt) + neg_ls / float(pos_cnt + neg_cnt)
+        """Per video the first `sample_split` rows are positives (all kept), the rest incomplete proposals (hardest
+        `ohem_ratio` kept); both hinge sums are divided by the number of kept rows (ops/ssn_ops.py:223-239)."""
+        n_pos, n_neg = sample_split, sample_group_size - sample_split
+
+        def rows(t):                      # [videos, rows, ...] -> [videos * rows, ...]
+            return t.contiguous().view(-1, *t.shape[2:])
+
+        by_video = pred.view(-1, sample_group_size, pred.size(1))
+        lab = labels.view(-1, sample_group_size)
+        pos_pred, neg_pred = rows(by_video[:, :n_pos]), rows(by_video[:, n_pos:])
+        pos_loss = OHEMHingeLoss.apply(pos_pred, rows(lab[:, :n_pos]), 1, 1.0, n_pos)
+        neg_loss = OHEMHingeLoss.apply(neg_pred, rows(lab[:, n_pos:]), -1, self.ohem_ratio, n_neg)
+        kept = float(pos_pred.size(0) + int(neg_pred.size(0) * self.ohem_ratio))
+        return pos_loss / kept + neg_loss / kept
 
 
 class _ClassWiseRegFn(torch.autograd.Function):

@@ -117,29 +117,25 @@ class SSN(torch.nn.Module):
             self.regressor_fc = None
         return feature_dim
 
+    # bn_mode -> 1-based index of the first BatchNorm2d that stays in eval mode with frozen affine parameters
+    # ('partial': the first one trains, 'full': none frozen), ssn_models.py:95-105
+    _FIRST_FROZEN_BN = {'frozen': 1, 'partial': 2, 'full': None}
+
     def prepare_bn(self):
-        if self.bn_mode == 'partial':
-            self.freeze_count = 2
-        elif self.bn_mode == 'frozen':
-            self.freeze_count = 1
-        elif self.bn_mode == 'full':
-            self.freeze_count = None
-        else:
+        if self.bn_mode not in self._FIRST_FROZEN_BN:
             raise ValueError("unknown bn mode")
+        self.freeze_count = self._FIRST_FROZEN_BN[self.bn_mode]
 
     def train(self, mode=True):
-        """freeze BatchNorm2d statistics and parameters (ssn_models.py:156-174)"""
-        super(SSN, self).train(mode)
-        if self.freeze_count is None:
-            return self
-        count = 0
-        for m in self.base_model.modules():
-            if isinstance(m, nn.BatchNorm2d):
-                count += 1
-                if count >= self.freeze_count:
-                    m.eval()
-                    m.weight.requires_grad = False
-                    m.bias.requires_grad = False
+        """nn.Module.train, then the BatchNorm2d layers from `freeze_count` on go back to eval mode and stop training
+        their affine parameters (ssn_models.py:156-174)"""
+        super().train(mode)
+        if self.freeze_count is not None:
+            bns = [m for m in self.base_model.modules() if isinstance(m, nn.BatchNorm2d)]
+            for bn in bns[self.freeze_count - 1:]:
+                bn.eval()
+                bn.weight.requires_grad = False
+                bn.bias.requires_grad = False
         return self
 
     def set_precision(self, precision, grad_scale=None):
