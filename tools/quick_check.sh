@@ -1,5 +1,6 @@
 #!/bin/bash
-# weight-gradient split cap raised to fill the SMs: per-launch diag in both modes, the bench line, the wgrad-related tests
+# after a kernel change (one GPU, ~3 min): every tensor-core launch vs the SIMT kernels in both modes, the bench line with the
+# per-kernel times of the roofline leg, the tensor-core parity tests
 mkdir -p gpurun_out
 timeout 300 python tools/umma_diag.py 18 tc > gpurun_out/sp_diag_tc.txt 2>&1; echo "diag tc: $(grep -c '^BAD' gpurun_out/sp_diag_tc.txt) BAD; $(tail -1 gpurun_out/sp_diag_tc.txt | cut -c1-80)"
 timeout 300 python tools/umma_diag.py 160 > gpurun_out/sp_diag_fast.txt 2>&1; echo "diag fast: $(grep -c '^BAD' gpurun_out/sp_diag_fast.txt) BAD; $(tail -1 gpurun_out/sp_diag_fast.txt | cut -c1-80)"
