@@ -21,7 +21,7 @@ EXACT_FP32, FAST_FP16, EXACT_TC = 0, 1, 2
 
 class Config(C.Structure):
     _fields_ = [("in_channels", C.c_int32), ("frames", C.c_int32), ("precision", C.c_int32),
-                ("training", C.c_int32), ("grad_scale", C.c_float), ("reserved", C.c_int32 * 3)]
+                ("training", C.c_int32), ("grad_scale", C.c_float), ("bn1_train", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class HeadsCfg(C.Structure):

@@ -35,7 +35,7 @@ class BackboneEngine:
         self.device = torch.device(device)
         self.frames, self.in_channels, self.precision, self.training = frames, in_channels, precision, training
         self.bn1_train = bool(bn1_train)
-        cfg = _lib.Config(in_channels, frames, precision, 1 if training else 0, float(grad_scale), (C.c_int32 * 3)(1 if bn1_train else 0, 0, 0))
+        cfg = _lib.Config(in_channels, frames, precision, 1 if training else 0, float(grad_scale), 1 if bn1_train else 0)
         self.h = C.c_void_p()
         check(lib.ssnb_create(C.byref(cfg), C.byref(self.h)), None, "ssnb_create")
         nbytes = lib.ssnb_workspace_bytes(self.h)

@@ -30,7 +30,7 @@ def test_conv_table_matches_oracle():
 
 def test_engine_plan_without_gpu():
     from ssn_b200 import _lib
-    cfg = _lib.Config(3, 18, _lib.EXACT_FP32, 1, 1.0, (C.c_int32 * 3)())
+    cfg = _lib.Config(3, 18, _lib.EXACT_FP32, 1, 1.0)
     h = C.c_void_p()
     _lib.check(_lib.lib.ssnb_create(C.byref(cfg), C.byref(h)))
     assert _lib.lib.ssnb_workspace_bytes(h) > 0
@@ -44,7 +44,7 @@ def test_engine_plan_without_gpu():
     # calls that need device state fail with an error code, not a crash
     assert _lib.lib.ssnb_backbone_fwd(h, None, None, None) != 0
     _lib.lib.ssnb_destroy(h)
-    bad = _lib.Config(3, 0, 0, 0, 1.0, (C.c_int32 * 3)())
+    bad = _lib.Config(3, 0, 0, 0, 1.0)
     assert _lib.lib.ssnb_create(C.byref(bad), C.byref(h)) != 0
 
 
@@ -132,3 +132,43 @@ def test_flow_model_conv1_is_mean_expanded():
         assert torch.equal(c1.weight.data[:, ch:ch + 1], mean)
     assert m.input_mean == [128] and m.new_length == 5
     assert "base_model.conv1_7x7_s2.weight" in m.state_dict() and m.state_dict()["base_model.conv1_7x7_s2.weight"].shape[1] == 10
+
+
+def test_header_is_plain_c_and_ctypes_mirrors_its_structs(tmp_path):
+    """include/ssnb.h must compile as C99 on its own (it is the drop-in boundary: no C++ or torch types), and the ctypes
+    mirrors in ssn_b200/_lib.py must have the same size and field offsets as the C structs."""
+    import shutil
+    import subprocess
+    from ssn_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = open(os.path.join(ROOT, "include", "ssnb.h")).read()
+
+    def fields(struct):            # field names of `typedef struct { ... } <struct>;` in declaration order
+        body = re.search(r"typedef struct \{([^{}]*)\}\s*" + struct + ";", hdr).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [re.sub(r"\[.*\]", "", n).strip() for n in decl.split(None, 1)[1].split(",")]
+        return names
+
+    structs = {"ssnb_config": _lib.Config, "ssnb_heads_cfg": _lib.HeadsCfg}
+    prints = []
+    for s in structs:
+        prints.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))
+        prints += ['printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (s, f, s, f) for f in fields(s)]
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ssnb.h"\nint main(void) { %s return 0; }\n' % " ".join(prints))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    c_layout = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for s, mirror in structs.items():
+        assert int(c_layout[s]) == C.sizeof(mirror), s
+        c_offsets = {f: int(c_layout["%s.%s" % (s, f)]) for f in fields(s)}
+        assert [name for name, _ in mirror._fields_] == list(c_offsets), (s, list(c_offsets))
+        for name, _ in mirror._fields_:
+            assert getattr(mirror, name).offset == c_offsets[name], (s, name)
